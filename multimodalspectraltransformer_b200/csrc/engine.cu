@@ -1,0 +1,742 @@
+// C-ABI entry points of the MMT B200 engine (include/mmt_b200.h) and the host-side
+// drivers that sequence the kernels for encode / decode.
+#include "engine.cuh"
+#include "kernels_simt.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace mmt {
+thread_local std::string g_last_error;
+
+static const char* kEmbedKeys[5] = {
+    "linear_spec_embedding_1H.point_embedding_layer_1H.fc_H",
+    "linear_spec_embedding_13C.point_embedding_layer_13C.fc_C",
+    "linear_spec_embedding_HSQC.point_embedding_layer_HSQC.fc_HSQC",
+    "linear_spec_embedding_COSY.point_embedding_layer_COSY.fc_COSY",
+    "linear_spec_embedding_IR.linear_spec_embedding_IR"};
+static const char* kEncNames[6] = {"encoder_1H", "encoder_13C", "encoder_HSQC", "encoder_COSY", "encoder_IR", "encoder_cross"};
+
+static int check_launch(mmt_engine* e, const char* what) {
+    e->launches++;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) MMT_FAIL(std::string(what) + " launch -> " + cudaGetErrorString(err));
+    return 0;
+}
+
+static int ensure_arena(mmt_engine* e, size_t bytes) {
+    if (bytes <= e->arena_bytes) return 0;
+    if (e->arena) { MMT_CUDA(cudaDeviceSynchronize()); MMT_CUDA(cudaFree(e->arena)); e->arena = nullptr; e->arena_bytes = 0; }
+    size_t want = bytes + (bytes >> 3);
+    MMT_CUDA(cudaMalloc(&e->arena, want));
+    e->arena_bytes = want;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------
+static int launch_gemm(mmt_engine* e, GemmParams& p, int ngroups, int maxM, cudaStream_t s) {
+    if (maxM <= 0) return 0;
+    if (p.splits < 1) p.splits = 1;
+    if (maxM >= 1024) {
+        dim3 grid((p.N + 127) / 128, (maxM + 127) / 128, ngroups * p.splits);
+        gemm_nt_f32<128, 128, 8, 8><<<grid, 256, 0, s>>>(p);
+    } else {
+        dim3 grid((p.N + 63) / 64, (maxM + 31) / 32, ngroups * p.splits);
+        gemm_nt_f32<32, 64, 2, 4><<<grid, 256, 0, s>>>(p);
+    }
+    return check_launch(e, "gemm_nt_f32");
+}
+
+static GemmParams gemm_params(int N, int K, int64_t ldc, int act) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.K = K; p.ldc = ldc; p.act = act; p.splits = 1; p.out_mode = GEMM_OUT_ROWMAJOR;
+    return p;
+}
+
+static int pick_splits(int M, int N, int K) {
+    if (M >= 1024) return 1;
+    int tiles = ((M + 31) / 32) * ((N + 63) / 64);
+    int s = 1;
+    while (s < 16 && tiles * s < 256 && (K / (s * 2)) >= 64) s *= 2;
+    return s;
+}
+
+static int launch_ln(mmt_engine* e, LnParams& p, int ngroups, int maxM, cudaStream_t s) {
+    if (maxM <= 0) return 0;
+    dim3 grid((maxM + 7) / 8, ngroups);
+    bias_res_layernorm<<<grid, 256, 0, s>>>(p);
+    return check_launch(e, "bias_res_layernorm");
+}
+
+// ---------------------------------------------------------------------------
+// encoder
+// ---------------------------------------------------------------------------
+struct ModeLayout {
+    int present[5];
+    int S_m[5];      // sequence length of each block in the concatenated memory
+    int n_x[5];
+    int off[5];
+    int S_total;
+    int float_mask;
+    int has_MF, has_MS, has_MW;
+};
+
+static ModeLayout mode_layout(const mmt_model_desc& d, uint32_t mode) {
+    ModeLayout L;
+    memset(&L, 0, sizeof(L));
+    L.has_MF = (mode & MMT_MODE_MF) != 0; L.has_MS = (mode & MMT_MODE_MS) != 0; L.has_MW = (mode & MMT_MODE_MW) != 0;
+    const int P = d.pad_points;
+    const int extra = (L.has_MF ? P : 0) + (L.has_MS ? P : 0) + (L.has_MW ? 1 : 0);
+    const int fdim = L.has_MS ? 193 : 129, fdim_ir = L.has_MS ? 130 : 66;   // models_MMT_v15_4.py:834-835
+    int off = 0;
+    for (int m = 0; m < 5; ++m) {
+        L.present[m] = (mode >> m) & 1;
+        L.n_x[m] = (m == 4) ? 1 : P;
+        if (L.present[m]) L.S_m[m] = L.n_x[m] + extra;
+        else L.S_m[m] = (m == 3) ? 65 : (m == 4 ? fdim_ir : fdim);             // :852, :912, :933
+        L.off[m] = off;
+        off += L.S_m[m];
+        if (m < 4 && !L.present[m]) L.float_mask = 1;
+    }
+    L.S_total = off;
+    return L;
+}
+
+static void fill_layer(mmt_engine* e, LayerW& w, const std::string& p, bool decoder) {
+    w.in_w = e->W(p + ".self_attn.in_proj_weight"); w.in_b = e->W(p + ".self_attn.in_proj_bias");
+    w.out_w = e->W(p + ".self_attn.out_proj.weight"); w.out_b = e->W(p + ".self_attn.out_proj.bias");
+    w.l1_w = e->W(p + ".linear1.weight"); w.l1_b = e->W(p + ".linear1.bias");
+    w.l2_w = e->W(p + ".linear2.weight"); w.l2_b = e->W(p + ".linear2.bias");
+    w.n1_w = e->W(p + ".norm1.weight"); w.n1_b = e->W(p + ".norm1.bias");
+    w.n2_w = e->W(p + ".norm2.weight"); w.n2_b = e->W(p + ".norm2.bias");
+    if (decoder) {
+        w.ca_in_w = e->W(p + ".multihead_attn.in_proj_weight"); w.ca_in_b = e->W(p + ".multihead_attn.in_proj_bias");
+        w.ca_out_w = e->W(p + ".multihead_attn.out_proj.weight"); w.ca_out_b = e->W(p + ".multihead_attn.out_proj.bias");
+        w.n3_w = e->W(p + ".norm3.weight"); w.n3_b = e->W(p + ".norm3.bias");
+    }
+}
+
+struct EncBuffers {
+    float* X[5]; float* kb[5]; int* kidx[5]; int* nk[5];
+    float* Xc; int* kidx_c; int* nk_c;
+    float* ir_emb;
+    float* QKV; float* ATT; float* PART; float* H;
+    float* key_bias; uint8_t* pad_mask;   // chunk-local when the caller passed NULL
+};
+
+static void plan_encoder(Arena& a, const ModeLayout& L, int Bc, int d_ff, EncBuffers& b, bool need_kb, bool need_pm) {
+    int64_t rows_mod = 0;
+    for (int m = 0; m < 5; ++m) {
+        int64_t rows = L.present[m] ? (int64_t)Bc * L.S_m[m] : 0;
+        b.X[m] = a.get<float>(rows * D);
+        b.kb[m] = a.get<float>(rows);
+        b.kidx[m] = a.get<int>(rows);
+        b.nk[m] = a.get<int>(Bc);
+        rows_mod += rows;
+    }
+    int64_t R = (int64_t)Bc * L.S_total;
+    int64_t rmax = std::max(rows_mod, R);
+    b.Xc = a.get<float>(R * D);
+    b.kidx_c = a.get<int>(R);
+    b.nk_c = a.get<int>(Bc);
+    b.ir_emb = a.get<float>((int64_t)Bc * D);
+    b.QKV = a.get<float>(rmax * 3 * D);
+    b.ATT = a.get<float>(rmax * D);
+    b.PART = a.get<float>(rmax * D);
+    b.H = a.get<float>(rmax * d_ff);
+    b.key_bias = need_kb ? a.get<float>(R) : nullptr;
+    b.pad_mask = need_pm ? a.get<uint8_t>(R) : nullptr;
+}
+
+// One post-norm encoder layer over `ng` independent groups (models_MMT_v15_4.py:510-533).
+struct EncGroupRun {
+    float* X; int rows; int S; const float* kbias; const int* kidx; const int* nk;
+    const LayerW* w; float* qkv; float* att; float* part; float* h;
+    // destination of the layer output (defaults to X in place)
+    float* out; int64_t stride_b, stride_s, off;
+};
+
+static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
+    int maxM = 0, maxS = 0;
+    for (int i = 0; i < ng; ++i) { maxM = std::max(maxM, gr[i].rows); maxS = std::max(maxS, gr[i].S); }
+    const int dh = D / heads;
+    {   // QKV projection
+        GemmParams p = gemm_params(3 * D, D, 3 * D, 0);
+        for (int i = 0; i < ng; ++i) { p.g[i].A = gr[i].X; p.g[i].lda = D; p.g[i].W = gr[i].w->in_w; p.g[i].bias = gr[i].w->in_b; p.g[i].C = gr[i].qkv; p.g[i].M = gr[i].rows; }
+        MMT_TRY(launch_gemm(e, p, ng, maxM, s));
+    }
+    {   // attention
+        AttnParams p;
+        memset(&p, 0, sizeof(p));
+        p.scale = 1.0f / sqrtf((float)dh);
+        for (int i = 0; i < ng; ++i) { p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = gr[i].att; p.g[i].S = gr[i].S; }
+        dim3 grid(heads, Bc, ng);
+        size_t smem = (size_t)maxS * (2 * dh + 1) * sizeof(float);
+        int threads = maxS > 256 ? 256 : 128;
+        if (dh == 8) {
+            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_encoder_f32<8><<<grid, threads, smem, s>>>(p);
+        } else if (dh == 32) {
+            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_encoder_f32<32><<<grid, threads, smem, s>>>(p);
+        } else if (dh == 16) {
+            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attn_encoder_f32<16><<<grid, threads, smem, s>>>(p);
+        } else MMT_FAIL("unsupported head dim " + std::to_string(dh));
+        MMT_TRY(check_launch(e, "attn_encoder_f32"));
+    }
+    {   // out-proj -> +residual -> LN1 (in place on X)
+        GemmParams p = gemm_params(D, D, D, 0);
+        for (int i = 0; i < ng; ++i) { p.g[i].A = gr[i].att; p.g[i].lda = D; p.g[i].W = gr[i].w->out_w; p.g[i].C = gr[i].part; p.g[i].M = gr[i].rows; }
+        MMT_TRY(launch_gemm(e, p, ng, maxM, s));
+        LnParams q;
+        memset(&q, 0, sizeof(q));
+        q.splits = 1; q.eps = 1e-5f;
+        for (int i = 0; i < ng; ++i) {
+            LnGroup& g = q.g[i];
+            g.part = gr[i].part; g.bias = gr[i].w->out_b; g.res = gr[i].X; g.gamma = gr[i].w->n1_w; g.beta = gr[i].w->n1_b;
+            g.out = gr[i].X; g.M = gr[i].rows; g.S_in = gr[i].rows > 0 ? gr[i].rows : 1; g.stride_b = 0; g.stride_s = 1; g.off = 0;
+        }
+        MMT_TRY(launch_ln(e, q, ng, maxM, s));
+    }
+    {   // FFN
+        GemmParams p = gemm_params(d_ff, D, d_ff, 1);
+        for (int i = 0; i < ng; ++i) { p.g[i].A = gr[i].X; p.g[i].lda = D; p.g[i].W = gr[i].w->l1_w; p.g[i].bias = gr[i].w->l1_b; p.g[i].C = gr[i].h; p.g[i].M = gr[i].rows; }
+        MMT_TRY(launch_gemm(e, p, ng, maxM, s));
+        GemmParams p2 = gemm_params(D, d_ff, D, 0);
+        for (int i = 0; i < ng; ++i) { p2.g[i].A = gr[i].h; p2.g[i].lda = d_ff; p2.g[i].W = gr[i].w->l2_w; p2.g[i].C = gr[i].part; p2.g[i].M = gr[i].rows; }
+        MMT_TRY(launch_gemm(e, p2, ng, maxM, s));
+        LnParams q;
+        memset(&q, 0, sizeof(q));
+        q.splits = 1; q.eps = 1e-5f;
+        for (int i = 0; i < ng; ++i) {
+            LnGroup& g = q.g[i];
+            g.part = gr[i].part; g.bias = gr[i].w->l2_b; g.res = gr[i].X; g.gamma = gr[i].w->n2_w; g.beta = gr[i].w->n2_b;
+            g.out = gr[i].out ? gr[i].out : gr[i].X; g.M = gr[i].rows;
+            if (gr[i].out) { g.S_in = gr[i].S; g.stride_b = gr[i].stride_b; g.stride_s = gr[i].stride_s; g.off = gr[i].off; }
+            else { g.S_in = gr[i].rows > 0 ? gr[i].rows : 1; g.stride_b = 0; g.stride_s = 1; g.off = 0; }
+        }
+        MMT_TRY(launch_ln(e, q, ng, maxM, s));
+    }
+    return 0;
+}
+
+static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, int B_total, uint32_t mode, const ModeLayout& L,
+                        float* d_memory, float* d_embedding_src, float* d_key_bias, uint8_t* d_pad_mask, cudaStream_t s) {
+    const mmt_model_desc& d = e->desc;
+    const int P = d.pad_points;
+    Arena a;
+    EncBuffers b;
+    a.plan = true;
+    plan_encoder(a, L, Bc, d.d_ff, b, d_key_bias == nullptr, d_pad_mask == nullptr);
+    MMT_TRY(ensure_arena(e, a.off));
+    a.plan = false; a.base = e->arena; a.cap = e->arena_bytes; a.off = 0;
+    plan_encoder(a, L, Bc, d.d_ff, b, d_key_bias == nullptr, d_pad_mask == nullptr);
+    float* key_bias = d_key_bias ? d_key_bias + (int64_t)b0 * L.S_total : b.key_bias;
+    uint8_t* pad_mask = d_pad_mask ? d_pad_mask + (int64_t)b0 * L.S_total : b.pad_mask;
+
+    // IR projection 1000 -> 128 (+ReLU)   (models_MMT_v15_4.py:437-444, 761-767)
+    if (L.present[4]) {
+        GemmParams p = gemm_params(D, d.ir_bins, D, 1);
+        p.g[0].A = in.d_src_IR + (int64_t)b0 * d.ir_bins; p.g[0].lda = d.ir_bins;
+        p.g[0].W = e->W(std::string(kEmbedKeys[4]) + ".weight"); p.g[0].bias = e->W(std::string(kEmbedKeys[4]) + ".bias");
+        p.g[0].C = b.ir_emb; p.g[0].M = Bc;
+        MMT_TRY(launch_gemm(e, p, 1, Bc, s));
+    }
+    {   // embed + concatenate
+        EmbedParams p;
+        memset(&p, 0, sizeof(p));
+        const float* srcs[5] = {in.d_src_1H, in.d_src_13C, in.d_src_HSQC, in.d_src_COSY, b.ir_emb};
+        const float* masks[5] = {in.d_mask_1H, in.d_mask_13C, in.d_mask_HSQC, in.d_mask_COSY, nullptr};
+        for (int m = 0; m < 5; ++m) {
+            EmbedGroup& g = p.g[m];
+            g.present = L.present[m]; g.kind = (m == 4) ? 2 : (m == 1 ? 1 : 0);
+            g.S_m = L.S_m[m]; g.n_x = L.n_x[m]; g.off = L.off[m]; g.blank_is_ir = (m == 4);
+            if (!g.present) continue;
+            if (m < 4) {
+                if (!srcs[m] || !masks[m]) MMT_FAIL("spectra pointer missing for a modality in training_mode");
+                int cols = (m == 1) ? 1 : 2;
+                g.src = srcs[m] + (int64_t)b0 * P * cols; g.mask = masks[m] + (int64_t)b0 * P;
+                g.W = e->W(std::string(kEmbedKeys[m]) + ".weight"); g.b = e->W(std::string(kEmbedKeys[m]) + ".bias");
+            } else {
+                g.src = b.ir_emb;
+            }
+            g.X = b.X[m]; g.kbias = b.kb[m];
+        }
+        p.has_MF = L.has_MF; p.has_MS = L.has_MS; p.has_MW = L.has_MW;
+        if (L.has_MF) {
+            if (!in.d_src_MF || !in.d_mask_MF) MMT_FAIL("src_MF / mask_MF missing");
+            p.src_MF = in.d_src_MF + (int64_t)b0 * P; p.mask_MF = in.d_mask_MF + (int64_t)b0 * P;
+            p.E_MF = e->W("linear_embedding_MF.embedding.weight"); p.mf_vocab = d.mf_vocab;
+        }
+        if (L.has_MS) {
+            if (!in.d_src_MS || !in.d_mask_MS) MMT_FAIL("src_MS / mask_MS missing");
+            p.src_MS = in.d_src_MS + (int64_t)b0 * P; p.mask_MS = in.d_mask_MS + (int64_t)b0 * P;
+            p.E_MS = e->W("linear_embedding_MS.embedding.weight"); p.ms_vocab = d.ms_vocab;
+        }
+        if (L.has_MW) {
+            if (!in.d_trg_MW) MMT_FAIL("trg_MW missing");
+            p.trg_MW = in.d_trg_MW + b0;
+            p.W_MW = e->W("linear_embedding_MW.linear_spec_embedding_MW.weight");
+            p.b_MW = e->W("linear_embedding_MW.linear_spec_embedding_MW.bias");
+        }
+        p.B = Bc; p.S_total = L.S_total; p.P = P; p.float_mask = L.float_mask;
+        p.cross_X = b.Xc; p.key_bias = key_bias; p.pad_mask = pad_mask;
+        p.embedding_src = d_embedding_src; p.B_total = B_total; p.b0 = b0;
+        embed_tokens<<<dim3(Bc, 5), 128, 0, s>>>(p);
+        MMT_TRY(check_launch(e, "embed_tokens"));
+    }
+    {   // key compaction for the modality encoders and encoder_cross
+        KeyIndexParams p;
+        memset(&p, 0, sizeof(p));
+        int ng = 0;
+        for (int m = 0; m < 5; ++m) if (L.present[m]) { p.g[ng].kbias = b.kb[m]; p.g[ng].kidx = b.kidx[m]; p.g[ng].nk = b.nk[m]; p.g[ng].S = L.S_m[m]; ++ng; }
+        p.g[ng].kbias = key_bias; p.g[ng].kidx = b.kidx_c; p.g[ng].nk = b.nk_c; p.g[ng].S = L.S_total; ++ng;
+        p.B = Bc;
+        build_key_index<<<dim3(Bc, ng), 32, 0, s>>>(p);
+        MMT_TRY(check_launch(e, "build_key_index"));
+    }
+    // five modality encoders, batched as groups of one launch
+    {
+        EncGroupRun gr[5];
+        int ng = 0;
+        int64_t row_off = 0;
+        for (int m = 0; m < 5; ++m) {
+            if (!L.present[m]) continue;
+            EncGroupRun& g = gr[ng];
+            memset(&g, 0, sizeof(g));
+            g.X = b.X[m]; g.rows = Bc * L.S_m[m]; g.S = L.S_m[m]; g.kbias = b.kb[m]; g.kidx = b.kidx[m]; g.nk = b.nk[m];
+            g.qkv = b.QKV + row_off * 3 * D; g.att = b.ATT + row_off * D; g.part = b.PART + row_off * D; g.h = b.H + row_off * d.d_ff;
+            row_off += g.rows;
+            ++ng;
+        }
+        for (int l = 0; l < d.n_enc_layers && ng > 0; ++l) {
+            int gi = 0;
+            for (int m = 0; m < 5; ++m) {
+                if (!L.present[m]) continue;
+                gr[gi].w = &e->enc[m][l];
+                if (l == d.n_enc_layers - 1) {   // last layer writes into the concatenated memory [Bc][S_total][D]
+                    gr[gi].out = b.Xc; gr[gi].stride_b = L.S_total; gr[gi].stride_s = 1; gr[gi].off = L.off[m];
+                }
+                ++gi;
+            }
+            MMT_TRY(encoder_layer_fp32(e, gr, ng, Bc, d.n_heads, d.d_ff, s));
+        }
+    }
+    // encoder_cross over the concatenated memory (models_MMT_v15_4.py:941-944)
+    {
+        EncGroupRun g;
+        memset(&g, 0, sizeof(g));
+        g.X = b.Xc; g.rows = Bc * L.S_total; g.S = L.S_total; g.kbias = key_bias; g.kidx = b.kidx_c; g.nk = b.nk_c;
+        g.qkv = b.QKV; g.att = b.ATT; g.part = b.PART; g.h = b.H;
+        for (int l = 0; l < d.n_enc_layers; ++l) {
+            g.w = &e->enc[5][l];
+            if (l == d.n_enc_layers - 1) { g.out = d_memory; g.stride_b = 1; g.stride_s = B_total; g.off = b0; }   // (S,B,D)
+            MMT_TRY(encoder_layer_fp32(e, &g, 1, Bc, d.n_heads_cross, d.d_ff, s));
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// decoder
+// ---------------------------------------------------------------------------
+struct DecBuffers {
+    float *x, *qkv, *att, *part, *qc, *h;
+    float* kv_pool; int* block_table;
+    float* cross_kv;
+    int *nk, *row_start; int64_t* row_off; float* kbias_c;
+    int* ctl;   // [0] step, [1] done_ctas, [8..8+max_len) nonpad counts
+};
+constexpr int MAX_SPLITS = 16;
+
+static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b) {
+    const int L = d.n_dec_layers;
+    const int pps = (max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
+    b.x = a.get<float>(Nw * D);
+    b.qkv = a.get<float>(Nw * 3 * D);
+    b.att = a.get<float>(Nw * D);
+    b.part = a.get<float>(Nw * D * MAX_SPLITS);
+    b.qc = a.get<float>(Nw * D);
+    b.h = a.get<float>(Nw * d.d_ff);
+    b.kv_pool = a.get<float>((size_t)L * Nw * pps * 2 * PAGE_TOKENS * D);
+    b.block_table = a.get<int>(Nw * pps);
+    int64_t R = (int64_t)Bmw * S;
+    b.cross_kv = a.get<float>((size_t)L * 2 * R * D);
+    b.nk = a.get<int>(Bmw);
+    b.row_start = a.get<int>(Bmw);
+    b.row_off = a.get<int64_t>(R);
+    b.kbias_c = a.get<float>(R);
+    b.ctl = a.get<int>(8 + 256);
+}
+
+__global__ void init_block_table(int* bt, int64_t n_pages) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pages) bt[i] = (int)i;   // identity page map: sequence n owns pages [n*pps, (n+1)*pps)
+}
+
+struct DecodeRun {
+    const mmt_decode_args* a;
+    int mode;                 // 0 greedy, 1 multinomial, 2 forced
+    const int64_t* trg;       // forced tokens (T, N_total)
+    int T;                    // steps to run
+    int64_t* tokens; float* probs; float* logits;   // outputs, leading dimension N_total
+};
+
+// Projects the memory of one wave to per-layer cross-attention K/V (head-major) once;
+// the reference redoes this projection on every step (validate_generate_MMT_v15_4.py:751).
+static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, int Bmw, DecBuffers& b, cudaStream_t s) {
+    const mmt_model_desc& d = e->desc;
+    MemIndexParams mp;
+    mp.key_bias = a.d_key_bias + (int64_t)b0 * a.S; mp.S = a.S; mp.Bm = Bmw;
+    mp.stride_s = a.stride_s; mp.stride_b = a.stride_b;
+    mp.nk = b.nk; mp.row_start = b.row_start; mp.row_off = b.row_off; mp.kbias_c = b.kbias_c;
+    build_memory_index<<<Bmw, 32, 0, s>>>(mp);
+    MMT_TRY(check_launch(e, "build_memory_index"));
+    const int64_t R = (int64_t)Bmw * a.S;
+    const int dh = D / d.n_heads;
+    for (int l = 0; l < d.n_dec_layers; ++l) {
+        GemmParams p = gemm_params(2 * D, D, 0, 0);
+        p.g[0].A = a.d_memory + (int64_t)b0 * a.stride_b; p.g[0].a_row_off = b.row_off; p.g[0].lda = 0;
+        p.g[0].W = e->dec[l].ca_in_w + (int64_t)D * D;     // rows D..3D of in_proj: K then V
+        p.g[0].bias = e->dec[l].ca_in_b + D;
+        p.g[0].C = b.cross_kv + (size_t)l * 2 * R * D; p.g[0].M = (int)R;
+        p.out_mode = GEMM_OUT_HEADMAJOR; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
+        MMT_TRY(launch_gemm(e, p, 1, (int)R, s));
+    }
+    return 0;
+}
+
+static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw, int Bmw, DecBuffers& b, cudaStream_t s) {
+    const mmt_model_desc& d = e->desc;
+    const mmt_decode_args& a = *r.a;
+    const int H = d.n_heads, dh = D / H;
+    const int pps = (a.max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
+    const int64_t R = (int64_t)Bmw * a.S;
+    const float scale = 1.0f / sqrtf((float)dh);
+    const int* step = b.ctl;
+    const int64_t N_total = (int64_t)a.Bm * a.n_cand;
+    const int M = (int)Nw;
+
+    if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, nullptr);
+    else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, nullptr);
+    MMT_TRY(check_launch(e, "decode_embed"));
+
+    auto ln = [&](const float* part, int splits, const float* bias, const float* gamma, const float* beta) -> int {
+        LnParams q;
+        memset(&q, 0, sizeof(q));
+        q.splits = splits; q.part_stride = Nw * D; q.eps = 1e-5f;
+        LnGroup& g = q.g[0];
+        g.part = part; g.bias = bias; g.res = b.x; g.gamma = gamma; g.beta = beta; g.out = b.x; g.M = M;
+        g.S_in = M; g.stride_b = 0; g.stride_s = 1; g.off = 0;
+        return launch_ln(e, q, 1, M, s);
+    };
+    auto gemm = [&](const float* A, int64_t lda, const float* W, const float* bias, float* C, int N, int K, int act, int splits) -> int {
+        GemmParams p = gemm_params(N, K, N, act);
+        p.g[0].A = A; p.g[0].lda = lda; p.g[0].W = W; p.g[0].bias = bias; p.g[0].C = C; p.g[0].M = M;
+        p.splits = splits; p.part_stride = Nw * D;
+        return launch_gemm(e, p, 1, M, s);
+    };
+    const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
+    for (int l = 0; l < d.n_dec_layers; ++l) {
+        const LayerW& w = e->dec[l];
+        MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
+        float* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D;
+        if (dh == 8) decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, b.att);
+        else MMT_FAIL("decoder head dim must be 8");
+        MMT_TRY(check_launch(e, "decode_self_attention"));
+        MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
+        MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
+        MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
+        decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, b.cross_kv + (size_t)l * 2 * R * D, R, b.nk, b.row_start, b.kbias_c,
+                                                             a.n_cand, Nw, H, scale, b.att);
+        MMT_TRY(check_launch(e, "decode_cross_attention"));
+        MMT_TRY(gemm(b.att, D, w.ca_out_w, nullptr, b.part, D, D, 0, 1));
+        MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
+        MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
+        int splits = pick_splits(M, D, d.d_ff);
+        MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, splits));
+        MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
+    }
+    SampleParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.x = b.x; sp.W = e->W("fc_out.weight"); sp.b = e->W("fc_out.bias"); sp.V = d.vocab; sp.N = Nw; sp.ldn = N_total;
+    sp.temperature = a.temperature; sp.mode = r.mode;
+    int smc = a.rng_sm_count > 0 ? a.rng_sm_count : e->sm_count;
+    int mts = a.rng_max_threads_per_sm > 0 ? a.rng_max_threads_per_sm : e->max_threads_per_sm;
+    int64_t Nrng = a.N_total > 0 ? a.N_total : N_total;
+    sp.rng.seed = a.philox_seed; sp.rng.offset = a.philox_offset; sp.rng.numel = Nrng * d.vocab;
+    sp.rng.threads = torch_rng_threads(sp.rng.numel, smc, mts);
+    sp.rng_inc = torch_rng_increment(sp.rng.numel, smc, mts);
+    sp.seq_index_base = a.seq_index_base + n0;
+    sp.tokens = r.tokens ? r.tokens + n0 : nullptr; sp.probs = r.probs ? r.probs + n0 : nullptr;
+    sp.logits = r.logits ? r.logits + n0 * d.vocab : nullptr;
+    sp.ctl.step = b.ctl; sp.ctl.done_ctas = b.ctl + 1; sp.ctl.nonpad = (r.mode == 0) ? b.ctl + 8 : nullptr;
+    sp.advance = 1;
+    sample_tokens<<<(unsigned)((Nw + 7) / 8), 256, 0, s>>>(sp);
+    MMT_TRY(check_launch(e, "sample_tokens"));
+    return 0;
+}
+
+static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaStream_t s) {
+    const mmt_model_desc& d = e->desc;
+    const mmt_decode_args& a = *r.a;
+    if (a.Bm <= 0 || a.n_cand <= 0 || a.S <= 0) MMT_FAIL("decode: empty batch");
+    if (a.max_len < 1 || a.max_len > d.max_len || a.max_len > 128) MMT_FAIL("decode: max_len must be in [1, min(128, pe_trg rows)]");
+    if (r.T > a.max_len) MMT_FAIL("decode: T > max_len");
+    if (!(a.temperature > 0.f) && r.mode != 2) MMT_FAIL("decode: temperature must be > 0");
+    if ((a.stride_s % 4) || (a.stride_b % 4) || ((uintptr_t)a.d_memory % 16)) MMT_FAIL("decode: memory must be 16-byte aligned with strides that are multiples of 4 floats");
+    const int64_t N_total = (int64_t)a.Bm * a.n_cand;
+    // waves: bound the self-attention KV pool (fp32: max_len*6*2*128*4 B per sequence)
+    const int64_t max_wave_seqs = 16384;
+    int Bm_wave = (int)std::max<int64_t>(1, std::min<int64_t>(a.Bm, max_wave_seqs / a.n_cand));
+    const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
+    Arena ar;
+    DecBuffers b;
+    ar.plan = true;
+    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b);
+    MMT_TRY(ensure_arena(e, ar.off));
+    ar.plan = false; ar.base = e->arena; ar.cap = e->arena_bytes; ar.off = 0;
+    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b);
+    const int pps = (a.max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
+    const bool early = (r.mode == 0) && a.stop_on_all_pad && n_waves == 1;
+    int steps_done = r.T;
+    std::vector<int64_t> nonpad_total(r.T, 0);
+    for (int wv = 0; wv < n_waves; ++wv) {
+        const int b0 = wv * Bm_wave;
+        const int Bmw = std::min(Bm_wave, a.Bm - b0);
+        const int64_t Nw = (int64_t)Bmw * a.n_cand, n0 = (int64_t)b0 * a.n_cand;
+        MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
+        init_block_table<<<(unsigned)((Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, Nw * pps);
+        MMT_TRY(check_launch(e, "init_block_table"));
+        MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, s));
+        for (int t = 0; t < r.T; ++t) {
+            MMT_TRY(decode_step_fp32(e, r, n0, Nw, Bmw, b, s));
+            if (early && ((t + 1) % 16 == 0 || t + 1 == r.T) ) {
+                MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
+                MMT_CUDA(cudaStreamSynchronize(s));
+                bool stop = false;
+                for (int q = 0; q <= t; ++q) if (e->h_pinned[q] == 0) { steps_done = q + 1; stop = true; break; }
+                if (stop) break;
+            }
+        }
+        if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1) {
+            MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
+            MMT_CUDA(cudaStreamSynchronize(s));
+            for (int q = 0; q < r.T; ++q) nonpad_total[q] += e->h_pinned[q];
+        }
+    }
+    if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1)
+        for (int q = 0; q < r.T; ++q) if (nonpad_total[q] == 0) { steps_done = q + 1; break; }
+    if (h_steps) *h_steps = steps_done;
+    return 0;
+}
+
+}  // namespace mmt
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace mmt;
+
+extern "C" {
+
+int32_t mmt_abi_version(void) { return MMT_ABI_VERSION; }
+const char* mmt_last_error(void) { return g_last_error.c_str(); }
+
+static int check_desc(const mmt_model_desc* d) {
+    if (!d) MMT_FAIL("null model desc");
+    if (d->d_model != D) MMT_FAIL("only hidden_size 128 is supported");
+    if (d->n_heads != 16 || d->n_heads_cross < 1 || (D % d->n_heads_cross)) MMT_FAIL("unsupported head counts");
+    if (d->vocab > VOCAB_MAX || d->vocab < 1) MMT_FAIL("vocab must be <= 64");
+    if (d->max_len > 128 || d->max_len < 1) MMT_FAIL("max_len must be <= 128");
+    if (d->d_ff % 64 || d->ir_bins % 4) MMT_FAIL("d_ff must be a multiple of 64 and ir_bins of 4");
+    return 0;
+}
+
+int32_t mmt_weight_count(const mmt_model_desc* desc) { if (check_desc(desc)) return -1; return (int32_t)build_registry(*desc).slots.size(); }
+const char* mmt_weight_name(const mmt_model_desc* desc, int32_t i) {
+    static thread_local std::string name;
+    if (check_desc(desc)) return nullptr;
+    Registry r = build_registry(*desc);
+    if (i < 0 || i >= (int)r.slots.size()) return nullptr;
+    name = r.slots[i].name;
+    return name.c_str();
+}
+int64_t mmt_weight_numel(const mmt_model_desc* desc, int32_t i) {
+    if (check_desc(desc)) return -1;
+    Registry r = build_registry(*desc);
+    return (i < 0 || i >= (int)r.slots.size()) ? -1 : r.slots[i].numel;
+}
+int64_t mmt_weight_offset(const mmt_model_desc* desc, int32_t i) {
+    if (check_desc(desc)) return -1;
+    Registry r = build_registry(*desc);
+    return (i < 0 || i >= (int)r.slots.size()) ? -1 : r.slots[i].off;
+}
+int64_t mmt_weight_total(const mmt_model_desc* desc) { if (check_desc(desc)) return -1; return build_registry(*desc).total; }
+
+int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n_floats, int32_t device, mmt_engine** out) {
+    if (!out) MMT_FAIL("null out");
+    *out = nullptr;
+    MMT_TRY(check_desc(desc));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) MMT_FAIL("no CUDA device: this engine has no CPU fallback");
+    if (device < 0 || device >= ndev) MMT_FAIL("bad device index");
+    cudaDeviceProp prop;
+    MMT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) MMT_FAIL(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a (B200) only");
+    MMT_CUDA(cudaSetDevice(device));
+    mmt_engine* e = new mmt_engine();
+    e->desc = *desc; e->device = device; e->sm_count = prop.multiProcessorCount; e->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
+    e->reg = build_registry(*desc);
+    if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
+    auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };
+    if (cudaMalloc(&e->w32, n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc weights failed");
+    if (cudaMalloc(&e->w16, n_floats * sizeof(__nv_bfloat16)) != cudaSuccess) return fail("cudaMalloc bf16 weights failed");
+    if (cudaMemcpy(e->w32, h_weights, n_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return fail("weight H2D copy failed");
+    f32_to_bf16<<<(unsigned)((n_floats + 255) / 256), 256>>>(e->w32, n_floats, e->w16);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("bf16 weight conversion failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (cudaMallocHost(&e->h_pinned, 1024 * sizeof(int32_t)) != cudaSuccess) return fail("cudaMallocHost failed");
+    for (int k = 0; k < 6; ++k) {
+        e->enc[k].resize(desc->n_enc_layers);
+        for (int l = 0; l < desc->n_enc_layers; ++l) fill_layer(e, e->enc[k][l], std::string(kEncNames[k]) + ".layers." + std::to_string(l), false);
+    }
+    e->dec.resize(desc->n_dec_layers);
+    for (int l = 0; l < desc->n_dec_layers; ++l) fill_layer(e, e->dec[l], "decoder.layers." + std::to_string(l), true);
+    *out = e;
+    return 0;
+}
+
+void mmt_destroy(mmt_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    if (e->w32) cudaFree(e->w32);
+    if (e->w16) cudaFree(e->w16);
+    if (e->arena) cudaFree(e->arena);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    delete e;
+}
+
+int32_t mmt_memory_len(const mmt_model_desc* desc, uint32_t mode_bits) {
+    if (check_desc(desc)) return -1;
+    return mode_layout(*desc, mode_bits).S_total;
+}
+int32_t mmt_mask_is_float(uint32_t mode_bits) {
+    for (int m = 0; m < 4; ++m) if (!((mode_bits >> m) & 1)) return 1;
+    return 0;
+}
+
+int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mode_bits, int32_t precision,
+                   float* d_memory, float* d_embedding_src, float* d_key_bias, uint8_t* d_pad_mask,
+                   float* d_fingerprint, float* d_avg_memory, void* stream) {
+    if (!e || !in) MMT_FAIL("null engine / spectra");
+    if (B <= 0) MMT_FAIL("encode: B must be > 0");
+    if (!d_memory) MMT_FAIL("encode: d_memory is required");
+    if (precision != MMT_PREC_FP32 && precision != MMT_PREC_BF16) MMT_FAIL("bad precision");
+    // reference constraints: some NMR modality and MW must be present
+    if (!(mode_bits & 0xF)) MMT_FAIL("training_mode needs at least one of 1H/13C/HSQC/COSY (the reference crashes without)");
+    if (!(mode_bits & MMT_MODE_MW)) MMT_FAIL("training_mode needs MW (the reference crashes without)");
+    cudaStream_t s = (cudaStream_t)stream;
+    MMT_CUDA(cudaSetDevice(e->device));
+    const ModeLayout L = mode_layout(e->desc, mode_bits);
+    const int chunk = 256;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        int Bc = std::min(chunk, B - b0);
+        MMT_TRY(encode_chunk(e, *in, b0, Bc, B, mode_bits, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, s));
+    }
+    if (d_fingerprint || d_avg_memory) {
+        Arena a;
+        a.plan = false; a.base = e->arena; a.cap = e->arena_bytes; a.off = 0;
+        MMT_TRY(ensure_arena(e, (size_t)B * D * sizeof(float) + 256));
+        a.base = e->arena;
+        float* avg = d_avg_memory ? d_avg_memory : a.get<float>((size_t)B * D);
+        mean_over_sequence<<<B, 128, 0, s>>>(d_memory, L.S_total, B, avg);
+        MMT_TRY(check_launch(e, "mean_over_sequence"));
+        if (d_fingerprint) {
+            GemmParams p = gemm_params(e->desc.fp_size, D, e->desc.fp_size, 0);
+            p.g[0].A = avg; p.g[0].lda = D; p.g[0].W = e->W("fp1.weight"); p.g[0].bias = e->W("fp1.bias"); p.g[0].C = d_fingerprint; p.g[0].M = B;
+            MMT_TRY(launch_gemm(e, p, 1, B, s));
+        }
+    }
+    return 0;
+}
+
+int32_t mmt_decode(mmt_engine* e, const mmt_decode_args* a, int64_t* d_tokens, float* d_probs, int32_t* h_steps, void* stream) {
+    if (!e || !a) MMT_FAIL("null engine / args");
+    if (!d_tokens) MMT_FAIL("decode: d_tokens is required");
+    if (a->sampling != MMT_SAMPLE_GREEDY && a->sampling != MMT_SAMPLE_MULTINOMIAL) MMT_FAIL("bad sampling mode");
+    MMT_CUDA(cudaSetDevice(e->device));
+    DecodeRun r;
+    r.a = a; r.mode = a->sampling; r.trg = nullptr; r.T = a->max_len; r.tokens = d_tokens; r.probs = d_probs; r.logits = nullptr;
+    return run_decode(e, r, h_steps, (cudaStream_t)stream);
+}
+
+int32_t mmt_teacher_forced(mmt_engine* e, const mmt_decode_args* a, const int64_t* d_trg, int32_t T, float* d_logits, void* stream) {
+    if (!e || !a || !d_trg || !d_logits) MMT_FAIL("null argument");
+    if (T < 1) MMT_FAIL("T must be >= 1");
+    MMT_CUDA(cudaSetDevice(e->device));
+    DecodeRun r;
+    r.a = a; r.mode = 2; r.trg = d_trg; r.T = T; r.tokens = nullptr; r.probs = nullptr; r.logits = d_logits;
+    return run_decode(e, r, nullptr, (cudaStream_t)stream);
+}
+
+uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm) {
+    return torch_rng_increment(numel, sm_count, max_threads_per_sm);
+}
+
+int32_t mmt_pack_tokens_u8(const int64_t* d_tokens, int64_t n, uint8_t* d_out, void* stream) {
+    if (n <= 0) return 0;
+    pack_tokens_u8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_tokens, n, d_out);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, void* stream) {
+    if (n <= 0) return 0;
+    unpack_tokens_u8<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, n, d_tokens);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature, int32_t sampling,
+                   uint64_t philox_seed, uint64_t philox_offset, int64_t seq_index_base, int64_t N_total,
+                   int32_t rng_sm_count, int32_t rng_max_threads_per_sm,
+                   int64_t* d_token, float* d_prob, float* d_logits_out, void* stream) {
+    if (!e || !d_x) MMT_FAIL("null argument");
+    if (N <= 0) return 0;
+    MMT_CUDA(cudaSetDevice(e->device));
+    SampleParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.x = d_x; sp.W = e->W("fc_out.weight"); sp.b = e->W("fc_out.bias"); sp.V = e->desc.vocab; sp.N = N; sp.ldn = N;
+    sp.temperature = temperature; sp.mode = sampling;
+    int smc = rng_sm_count > 0 ? rng_sm_count : e->sm_count;
+    int mts = rng_max_threads_per_sm > 0 ? rng_max_threads_per_sm : e->max_threads_per_sm;
+    int64_t Nrng = N_total > 0 ? N_total : N;
+    sp.rng.seed = philox_seed; sp.rng.offset = philox_offset; sp.rng.numel = Nrng * sp.V;
+    sp.rng.threads = torch_rng_threads(sp.rng.numel, smc, mts);
+    sp.rng_inc = torch_rng_increment(sp.rng.numel, smc, mts);
+    sp.seq_index_base = seq_index_base;
+    sp.tokens = d_token; sp.probs = d_prob; sp.logits = d_logits_out;
+    sp.advance = 0;
+    sample_tokens<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(sp);
+    return check_launch(e, "sample_tokens");
+}
+
+int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const float* d_bias, float* d_C,
+                   int64_t M, int32_t N, int32_t K, int32_t act, int32_t precision, void* stream) {
+    if (!e || !d_A || !d_W || !d_C) MMT_FAIL("null argument");
+    if (K % 4) MMT_FAIL("K must be a multiple of 4");
+    if (M > 0x7fffffff) MMT_FAIL("M too large");
+    MMT_CUDA(cudaSetDevice(e->device));
+    if (precision != MMT_PREC_FP32) MMT_FAIL("mmt_linear: bf16 tcgen05 path not built in this revision");
+    GemmParams p = gemm_params(N, K, N, act);
+    p.g[0].A = d_A; p.g[0].lda = K; p.g[0].W = d_W; p.g[0].bias = d_bias; p.g[0].C = d_C; p.g[0].M = (int)M;
+    return launch_gemm(e, p, 1, (int)M, (cudaStream_t)stream);
+}
+
+int64_t mmt_launch_count(const mmt_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// Host-side engine state: weight registry, workspace arena, launch helpers.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mmt_b200.h"
+#include "common.cuh"
+
+namespace mmt {
+
+extern thread_local std::string g_last_error;
+
+#define MMT_FAIL(msg)                                                                   \
+    do {                                                                                \
+        ::mmt::g_last_error = std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg); \
+        return 1;                                                                       \
+    } while (0)
+#define MMT_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t err__ = (call);                                                     \
+        if (err__ != cudaSuccess) MMT_FAIL(std::string(#call) + " -> " + cudaGetErrorString(err__)); \
+    } while (0)
+#define MMT_TRY(call)                                                                   \
+    do {                                                                                \
+        if ((call) != 0) return 1;                                                      \
+    } while (0)
+
+struct Slot { std::string name; int64_t numel; int64_t off; };
+
+struct Registry {
+    std::vector<Slot> slots;
+    std::unordered_map<std::string, int> index;
+    int64_t total = 0;
+    void add(const std::string& name, int64_t numel) {
+        // every tensor starts on a 64-element boundary (256 B in the fp32 blob, 128 B in the
+        // bf16 copy: vector loads and TMA descriptors need 16-byte aligned bases)
+        index[name] = (int)slots.size();
+        slots.push_back({name, numel, total});
+        total += (numel + 63) / 64 * 64;
+    }
+};
+
+inline Registry build_registry(const mmt_model_desc& d) {
+    Registry r;
+    const int64_t h = d.d_model, F = d.d_ff;
+    auto lin = [&](const std::string& p, int64_t out, int64_t in) { r.add(p + ".weight", out * in); r.add(p + ".bias", out); };
+    lin("linear_spec_embedding_1H.point_embedding_layer_1H.fc_H", h, 2);
+    lin("linear_spec_embedding_13C.point_embedding_layer_13C.fc_C", h, 1);
+    lin("linear_spec_embedding_HSQC.point_embedding_layer_HSQC.fc_HSQC", h, 2);
+    lin("linear_spec_embedding_COSY.point_embedding_layer_COSY.fc_COSY", h, 2);
+    lin("linear_spec_embedding_IR.linear_spec_embedding_IR", h, d.ir_bins);
+    r.add("linear_embedding_MF.embedding.weight", (int64_t)d.mf_vocab * h);
+    r.add("linear_embedding_MS.embedding.weight", (int64_t)d.ms_vocab * h);
+    lin("linear_embedding_MW.linear_spec_embedding_MW", h, 1);
+    r.add("embed_trg.weight", (int64_t)d.vocab * h);
+    r.add("pe_trg.weight", (int64_t)d.max_len * h);
+    auto attn = [&](const std::string& p) {
+        r.add(p + ".in_proj_weight", 3 * h * h); r.add(p + ".in_proj_bias", 3 * h);
+        lin(p + ".out_proj", h, h);
+    };
+    auto norm = [&](const std::string& p) { r.add(p + ".weight", h); r.add(p + ".bias", h); };
+    const char* encs[6] = {"encoder_1H", "encoder_13C", "encoder_HSQC", "encoder_COSY", "encoder_IR", "encoder_cross"};
+    for (const char* e : encs)
+        for (int l = 0; l < d.n_enc_layers; ++l) {
+            std::string p = std::string(e) + ".layers." + std::to_string(l);
+            attn(p + ".self_attn");
+            lin(p + ".linear1", F, h); lin(p + ".linear2", h, F);
+            norm(p + ".norm1"); norm(p + ".norm2");
+        }
+    for (int l = 0; l < d.n_dec_layers; ++l) {
+        std::string p = "decoder.layers." + std::to_string(l);
+        attn(p + ".self_attn"); attn(p + ".multihead_attn");
+        lin(p + ".linear1", F, h); lin(p + ".linear2", h, F);
+        norm(p + ".norm1"); norm(p + ".norm2"); norm(p + ".norm3");
+    }
+    lin("fp1", d.fp_size, h);
+    lin("fc_out", d.vocab, h);
+    lin("real_data_linear", d.vocab, h);
+    return r;
+}
+
+struct LayerW {   // fp32 pointers into the device blob
+    const float *in_w, *in_b, *out_w, *out_b;        // self attention
+    const float *ca_in_w, *ca_in_b, *ca_out_w, *ca_out_b;   // decoder cross attention
+    const float *l1_w, *l1_b, *l2_w, *l2_b;
+    const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;
+};
+
+// Bump allocator over one grow-only device arena; `plan` mode only measures.
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    bool plan = true;
+    template <typename T>
+    T* get(size_t n) {
+        size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+        T* p = plan ? nullptr : reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+}  // namespace mmt
+
+struct mmt_engine {
+    mmt_model_desc desc;
+    int device = 0, sm_count = 0, max_threads_per_sm = 0;
+    mmt::Registry reg;
+    float* w32 = nullptr;
+    __nv_bfloat16* w16 = nullptr;
+    std::vector<mmt::LayerW> enc[6];   // 5 modality stacks + cross
+    std::vector<mmt::LayerW> dec;
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    int64_t launches = 0;
+    int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)
+
+    const float* W(const std::string& name) const { return w32 + reg.slots.at(reg.index.at(name)).off; }
+    const __nv_bfloat16* Wb(const float* p) const { return w16 + (p - w32); }
+};

@@ -1,0 +1,757 @@
+// fp32 SIMT kernels of the MMT path ("check mode": every contraction is an fp32
+// FMA chain so greedy ids reproduce the reference's fp32 PyTorch path), plus the
+// kernels that are HBM/latency-bound in every precision mode (embedders, KV-cached
+// attention, sampler).
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace mmt {
+
+// ===========================================================================
+// GEMM  C[M,N] = act(A[M,K] . W[N,K]^T + bias)     (both operands K-contiguous)
+// ===========================================================================
+constexpr int GEMM_MAX_GROUPS = 6;
+
+struct GemmGroup {
+    const float* A;            // [M, lda]
+    const int64_t* a_row_off;  // optional gather: row r of A starts at A + a_row_off[r]
+    const float* W;            // [N, K]
+    const float* bias;         // [N] or nullptr
+    float* C;                  // output
+    const int* M_dev;          // optional device-side row count (<= M)
+    int64_t lda;
+    int M;
+};
+
+enum { GEMM_OUT_ROWMAJOR = 0, GEMM_OUT_HEADMAJOR = 1 };
+
+struct GemmParams {
+    GemmGroup g[GEMM_MAX_GROUPS];
+    int N, K;
+    int splits;            // split-K factor; >1 => raw partial sums, no bias/act
+    int64_t part_stride;   // floats between consecutive split partials
+    int64_t ldc;
+    int act;               // 0 none, 1 relu
+    int out_mode;          // GEMM_OUT_*
+    int hm_heads, hm_dh;   // head-major: C[((c/D)*heads + (c%D)/dh) * hm_rows + r][c%dh]
+    int64_t hm_rows;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_nt_f32(const __grid_constant__ GemmParams p) {
+    constexpr int BK = 16;
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int RV = TM < 4 ? TM : 4;   // rows of a thread come in groups of RV
+    constexpr int CV = TN < 4 ? TN : 4;
+    constexpr int RG = TM / RV, CG = TN / CV;
+    constexpr int LDA_S = BM + 4, LDW_S = BN + 4;
+    __shared__ __align__(16) float As[2][BK][LDA_S];
+    __shared__ __align__(16) float Ws[2][BK][LDW_S];
+
+    const int grp = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const GemmGroup& g = p.g[grp];
+    const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (m0 >= M) return;
+    const int N = p.N, K = p.K;
+    int kchunk = ((K / p.splits + BK - 1) / BK) * BK;
+    const int kb = split * kchunk;
+    const int ke = min(K, kb + kchunk);
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+    constexpr int A_LD = (BM * 4 + NT - 1) / NT;   // float4 loads per thread for the A tile
+    constexpr int W_LD = (BN * 4 + NT - 1) / NT;
+    float4 ra[A_LD], rw[W_LD];
+
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            int idx = tid + i * NT;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < BM * 4) {
+                int row = idx >> 2, kq = idx & 3;
+                int r = m0 + row, k = k0 + kq * 4;
+                if (r < M && k < ke) {
+                    const float* src = g.a_row_off ? (g.A + g.a_row_off[r]) : (g.A + (int64_t)r * g.lda);
+                    if (k + 3 < ke) v = *reinterpret_cast<const float4*>(src + k);
+                    else { v.x = src[k]; if (k + 1 < ke) v.y = src[k + 1]; if (k + 2 < ke) v.z = src[k + 2]; }
+                }
+            }
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < W_LD; ++i) {
+            int idx = tid + i * NT;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < BN * 4) {
+                int row = idx >> 2, kq = idx & 3;
+                int c = n0 + row, k = k0 + kq * 4;
+                if (c < N && k < ke) {
+                    const float* src = g.W + (int64_t)c * K;
+                    if (k + 3 < ke) v = *reinterpret_cast<const float4*>(src + k);
+                    else { v.x = src[k]; if (k + 1 < ke) v.y = src[k + 1]; if (k + 2 < ke) v.z = src[k + 2]; }
+                }
+            }
+            rw[i] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            int idx = tid + i * NT;
+            if (idx < BM * 4) {
+                int row = idx >> 2, kq = (idx & 3) * 4;
+                As[buf][kq + 0][row] = ra[i].x; As[buf][kq + 1][row] = ra[i].y;
+                As[buf][kq + 2][row] = ra[i].z; As[buf][kq + 3][row] = ra[i].w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W_LD; ++i) {
+            int idx = tid + i * NT;
+            if (idx < BN * 4) {
+                int row = idx >> 2, kq = (idx & 3) * 4;
+                Ws[buf][kq + 0][row] = rw[i].x; Ws[buf][kq + 1][row] = rw[i].y;
+                Ws[buf][kq + 2][row] = rw[i].z; Ws[buf][kq + 3][row] = rw[i].w;
+            }
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    int buf = 0;
+    if (kb < ke) {
+        load_tiles(kb);
+        store_tiles(0);
+    }
+    __syncthreads();
+    for (int k0 = kb; k0 < ke; k0 += BK) {
+        const bool more = (k0 + BK) < ke;
+        if (more) load_tiles(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], w[TN];
+#pragma unroll
+            for (int gi = 0; gi < RG; ++gi)
+#pragma unroll
+                for (int i = 0; i < RV; ++i) a[gi * RV + i] = As[buf][kk][gi * (BM / RG) + ty * RV + i];
+#pragma unroll
+            for (int gj = 0; gj < CG; ++gj)
+#pragma unroll
+                for (int j = 0; j < CV; ++j) w[gj * CV + j] = Ws[buf][kk][gj * (BN / CG) + tx * CV + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        if (more) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    // epilogue
+    float* Cbase = g.C + (p.splits > 1 ? (int64_t)split * p.part_stride : 0);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int r = m0 + (i / RV) * (BM / RG) + ty * RV + (i % RV);
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int c = n0 + (j / CV) * (BN / CG) + tx * CV + (j % CV);
+            if (c >= N) continue;
+            float v = acc[i][j];
+            if (p.splits == 1) {
+                if (g.bias) v += g.bias[c];
+                if (p.act == 1) v = fmaxf(v, 0.f);
+            }
+            if (p.out_mode == GEMM_OUT_ROWMAJOR) {
+                Cbase[(int64_t)r * p.ldc + c] = v;
+            } else {
+                int kv = c / D, cc = c % D;
+                int h = cc / p.hm_dh, d = cc % p.hm_dh;
+                Cbase[(((int64_t)kv * p.hm_heads + h) * p.hm_rows + r) * p.hm_dh + d] = v;
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// out[map(r)] = LayerNorm(res[r] + bias + sum_s part[s][r]) * gamma + beta      (D = 128)
+// one warp per row; map(r) = (r / S_in)*stride_b + (r % S_in)*stride_s + off (in rows)
+// ===========================================================================
+struct LnGroup {
+    const float* part;   // [splits][M][D]
+    const float* bias;   // [D]
+    const float* res;    // [M][D]
+    const float* gamma; const float* beta;
+    float* out;
+    __nv_bfloat16* out_bf16;   // optional bf16 copy, same row map
+    const int* M_dev;
+    int M;
+    int S_in; int64_t stride_b, stride_s, off;
+};
+struct LnParams { LnGroup g[GEMM_MAX_GROUPS]; int splits; int64_t part_stride; float eps; };
+
+__global__ void __launch_bounds__(256) bias_res_layernorm(const __grid_constant__ LnParams p) {
+    const LnGroup& g = p.g[blockIdx.y];
+    const int M = g.M_dev ? min(*g.M_dev, g.M) : g.M;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= M) return;
+    const int c = lane * 4;
+    float4 v = *reinterpret_cast<const float4*>(g.part + (int64_t)r * D + c);
+    for (int s = 1; s < p.splits; ++s) {
+        float4 q = *reinterpret_cast<const float4*>(g.part + (int64_t)s * p.part_stride + (int64_t)r * D + c);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (g.bias) {
+        float4 b = *reinterpret_cast<const float4*>(g.bias + c);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (g.res) {
+        float4 q = *reinterpret_cast<const float4*>(g.res + (int64_t)r * D + c);
+        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);
+    float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+    float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
+    float rstd = rsqrtf(var + p.eps);
+    float4 ga = *reinterpret_cast<const float4*>(g.gamma + c);
+    float4 be = *reinterpret_cast<const float4*>(g.beta + c);
+    float4 o = make_float4(dx * rstd * ga.x + be.x, dy * rstd * ga.y + be.y, dz * rstd * ga.z + be.z, dw * rstd * ga.w + be.w);
+    int64_t orow = (int64_t)(r / g.S_in) * g.stride_b + (int64_t)(r % g.S_in) * g.stride_s + g.off;
+    *reinterpret_cast<float4*>(g.out + orow * D + c) = o;
+    if (g.out_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        *reinterpret_cast<uint2*>(g.out_bf16 + orow * D + c) = pk;
+    }
+}
+
+// ===========================================================================
+// Encoder input assembly: per-modality sequences [X tokens | MF | MS | MW]
+// (reference models_MMT_v15_4.py:733-792 embedders + :549-731 concatenation)
+// ===========================================================================
+struct EmbedGroup {
+    int present;             // 0 => blank modality (zeros + float-ones / bool-false mask)
+    int kind;                // 0: 2-col peaks, 1: 1-col peaks (13C), 2: IR (pre-projected row)
+    const float* src;        // (B,64,2) | (B,64) | ir_emb (B,D)
+    const float* mask;       // (B,64) non-zero = pad; unused for IR
+    const float* W;          // (D,2) | (D,1)
+    const float* b;          // (D)
+    float* X;                // out [B*S_m][D] (modality-encoder input), nullptr when blank
+    float* kbias;            // out [B][S_m]  0 / -inf  (modality encoder key bias), nullptr when blank
+    int S_m;                 // sequence length of this modality (or blank length)
+    int n_x;                 // leading spectrum tokens (64 or 1)
+    int off;                 // row offset inside the concatenated memory
+    int blank_is_ir;         // blank IR gets a bool False mask (bias 0), others float ones (+1)
+};
+struct EmbedParams {
+    EmbedGroup g[5];
+    const int64_t* src_MF; const uint8_t* mask_MF; const float* E_MF; int mf_vocab;
+    const int64_t* src_MS; const uint8_t* mask_MS; const float* E_MS; int ms_vocab;
+    const float* trg_MW; const float* W_MW; const float* b_MW;
+    int has_MF, has_MS, has_MW;
+    int B, S_total, P;       // P = pad_points (64); B = spectra in this chunk
+    int B_total, b0;         // embedding_src is (S_total, B_total, D); this chunk starts at column b0
+    int float_mask;          // concatenated mask promoted to float (pads add +1.0 instead of -inf)
+    float* cross_X;          // [B][S_total][D]: only blank rows are written here (zeros)
+    float* key_bias;         // out (B,S_total)
+    uint8_t* pad_mask;       // out (B,S_total)
+    float* embedding_src;    // optional out (S_total,B,D)
+};
+
+__global__ void __launch_bounds__(128) embed_tokens(const __grid_constant__ EmbedParams p) {
+    const EmbedGroup& g = p.g[blockIdx.y];
+    const int b = blockIdx.x, d = threadIdx.x;
+    const int B = p.B_total;
+    const int bo = p.b0 + b;
+    if (!g.present) {
+        for (int s = 0; s < g.S_m; ++s) {
+            int srow = g.off + s;
+            p.cross_X[((int64_t)b * p.S_total + srow) * D + d] = 0.f;
+            if (p.embedding_src) p.embedding_src[((int64_t)srow * B + bo) * D + d] = 0.f;
+            if (d == 0) {
+                p.key_bias[(int64_t)b * p.S_total + srow] = g.blank_is_ir ? 0.f : 1.f;
+                p.pad_mask[(int64_t)b * p.S_total + srow] = g.blank_is_ir ? 0 : 1;
+            }
+        }
+        return;
+    }
+    float w0 = 0.f, w1 = 0.f, bb = 0.f;
+    if (g.kind == 0) { w0 = g.W[d * 2]; w1 = g.W[d * 2 + 1]; bb = g.b[d]; }
+    else if (g.kind == 1) { w0 = g.W[d]; bb = g.b[d]; }
+    const float wmw = p.has_MW ? p.W_MW[d] : 0.f, bmw = p.has_MW ? p.b_MW[d] : 0.f;
+    for (int s = 0; s < g.S_m; ++s) {
+        float v;
+        bool pad;
+        int t = s;
+        if (t < g.n_x) {
+            if (g.kind == 0) {
+                const float* x = g.src + ((int64_t)b * p.P + t) * 2;
+                v = fmaf(x[1], w1, fmaf(x[0], w0, bb));       // nn.Linear: x0*w0 + x1*w1 + b (order immaterial to 1 ulp)
+                pad = g.mask[(int64_t)b * p.P + t] != 0.f;
+            } else if (g.kind == 1) {
+                v = fmaf(g.src[(int64_t)b * p.P + t], w0, bb);
+                pad = g.mask[(int64_t)b * p.P + t] != 0.f;
+            } else {
+                v = g.src[(int64_t)b * D + d];                 // IR: already relu(W x + b)
+                pad = false;
+            }
+        } else {
+            t -= g.n_x;
+            if (p.has_MF && t < p.P) {
+                int64_t id = p.src_MF[(int64_t)b * p.P + t];
+                v = (id >= 0 && id < p.mf_vocab) ? p.E_MF[id * D + d] : 0.f;
+                pad = p.mask_MF[(int64_t)b * p.P + t] != 0;
+            } else {
+                if (p.has_MF) t -= p.P;
+                if (p.has_MS && t < p.P) {
+                    int64_t id = p.src_MS[(int64_t)b * p.P + t];
+                    v = (id >= 0 && id < p.ms_vocab) ? p.E_MS[id * D + d] : 0.f;
+                    pad = p.mask_MS[(int64_t)b * p.P + t] != 0;
+                } else {
+                    v = fmaf(p.trg_MW[b], wmw, bmw);
+                    pad = false;
+                }
+            }
+        }
+        v = fmaxf(v, 0.f);
+        g.X[((int64_t)b * g.S_m + s) * D + d] = v;
+        int srow = g.off + s;
+        if (p.embedding_src) p.embedding_src[((int64_t)srow * B + bo) * D + d] = v;
+        if (d == 0) {
+            g.kbias[(int64_t)b * g.S_m + s] = pad ? MMT_NEG_INF : 0.f;
+            p.key_bias[(int64_t)b * p.S_total + srow] = p.float_mask ? (pad ? 1.f : 0.f) : (pad ? MMT_NEG_INF : 0.f);
+            p.pad_mask[(int64_t)b * p.S_total + srow] = pad ? 1 : 0;
+        }
+    }
+}
+
+// ===========================================================================
+// Key compaction: indices of keys whose additive bias is not -inf.
+// ===========================================================================
+struct KeyIndexGroup { const float* kbias; int* kidx; int* nk; int S; };
+struct KeyIndexParams { KeyIndexGroup g[GEMM_MAX_GROUPS]; int B; };
+
+__global__ void __launch_bounds__(32) build_key_index(const __grid_constant__ KeyIndexParams p) {
+    const KeyIndexGroup& g = p.g[blockIdx.y];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    int count = 0;
+    for (int base = 0; base < g.S; base += 32) {
+        int j = base + lane;
+        bool valid = j < g.S && g.kbias[(int64_t)b * g.S + j] != MMT_NEG_INF;
+        unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) g.kidx[(int64_t)b * g.S + count + __popc(m & ((1u << lane) - 1))] = j;
+        count += __popc(m);
+    }
+    if (lane == 0) g.nk[b] = count;
+}
+
+// ===========================================================================
+// Encoder self-attention, one CTA per (head, sequence, modality); K/V of the
+// un-masked keys staged in shared memory; each thread owns query rows.
+// ===========================================================================
+struct AttnGroup {
+    const float* qkv;    // [B*S][3*D]
+    const float* kbias;  // [B][S] additive bias per ORIGINAL key index
+    const int* kidx;     // [B][S] compacted key indices
+    const int* nk;       // [B]
+    float* out;          // [B*S][D]
+    int S;
+};
+struct AttnParams { AttnGroup g[GEMM_MAX_GROUPS]; float scale; };
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ AttnParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const AttnGroup& g = p.g[blockIdx.z];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int S = g.S;
+    const int nk = g.nk[b];
+    float* Ks = smem;                 // [nk][DH]
+    float* Vs = Ks + (size_t)S * DH;  // [nk][DH]
+    float* bs = Vs + (size_t)S * DH;  // [nk]
+    const float* base = g.qkv + (int64_t)b * S * (3 * D);
+    constexpr int V4 = DH / 4;
+    for (int i = threadIdx.x; i < nk * V4; i += blockDim.x) {
+        int jj = i / V4, q4 = i % V4;
+        int j = g.kidx[(int64_t)b * S + jj];
+        const float* row = base + (int64_t)j * (3 * D) + h * DH + q4 * 4;
+        *reinterpret_cast<float4*>(Ks + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + D);
+        *reinterpret_cast<float4*>(Vs + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + 2 * D);
+        if (q4 == 0) bs[jj] = g.kbias[(int64_t)b * S + j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        float q[DH], acc[DH];
+        const float* qrow = base + (int64_t)i * (3 * D) + h * DH;
+#pragma unroll
+        for (int d4 = 0; d4 < V4; ++d4) {
+            float4 t = *reinterpret_cast<const float4*>(qrow + d4 * 4);
+            q[d4 * 4] = t.x * p.scale; q[d4 * 4 + 1] = t.y * p.scale; q[d4 * 4 + 2] = t.z * p.scale; q[d4 * 4 + 3] = t.w * p.scale;
+        }
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+        float m = MMT_NEG_INF, l = 0.f;
+        for (int j = 0; j < nk; ++j) {
+            float s = bs[j];
+#pragma unroll
+            for (int d4 = 0; d4 < V4; ++d4) {
+                float4 k = *reinterpret_cast<const float4*>(Ks + j * DH + d4 * 4);
+                s = fmaf(q[d4 * 4], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
+                s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
+            }
+            if (s > m) {
+                float corr = expf(m - s);   // m = -inf on the first key -> 0
+                l *= corr;
+#pragma unroll
+                for (int d = 0; d < DH; ++d) acc[d] *= corr;
+                m = s;
+            }
+            float e = expf(s - m);
+            l += e;
+#pragma unroll
+            for (int d4 = 0; d4 < V4; ++d4) {
+                float4 v = *reinterpret_cast<const float4*>(Vs + j * DH + d4 * 4);
+                acc[d4 * 4] = fmaf(e, v.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(e, v.y, acc[d4 * 4 + 1]);
+                acc[d4 * 4 + 2] = fmaf(e, v.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(e, v.w, acc[d4 * 4 + 3]);
+            }
+        }
+        float inv = 1.0f / l;
+        float* orow = g.out + ((int64_t)b * S + i) * D + h * DH;
+#pragma unroll
+        for (int d4 = 0; d4 < V4; ++d4)
+            *reinterpret_cast<float4*>(orow + d4 * 4) =
+                make_float4(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv, acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
+    }
+}
+
+// mean over the S rows of a sequence-first memory (S,B,D) -> (B,D)   (models_MMT_v15_4.py:946)
+__global__ void __launch_bounds__(128) mean_over_sequence(const float* mem, int S, int B, float* avg) {
+    const int b = blockIdx.x, d = threadIdx.x;
+    float s = 0.f;
+    for (int i = 0; i < S; ++i) s += mem[((int64_t)i * B + b) * D + d];
+    avg[(int64_t)b * D + d] = s / (float)S;
+}
+
+// ===========================================================================
+// Decoder
+// ===========================================================================
+// Compact the un-masked memory rows of every memory and record, per packed row,
+// where it lives in the caller's (strided, sequence-first) memory tensor.
+struct MemIndexParams {
+    const float* key_bias;  // (Bm,S)
+    int S, Bm;
+    int64_t stride_s, stride_b;
+    int* nk;                // [Bm]
+    int* row_start;         // [Bm]  (= b*S: fixed-stride packing keeps the kernel single-pass)
+    int64_t* row_off;       // [Bm*S] float offset of packed row (b*S + jj) in d_memory
+    float* kbias_c;         // [Bm*S] bias of packed row
+};
+__global__ void __launch_bounds__(32) build_memory_index(const MemIndexParams p) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    int count = 0;
+    for (int base = 0; base < p.S; base += 32) {
+        int j = base + lane;
+        float bias = j < p.S ? p.key_bias[(int64_t)b * p.S + j] : MMT_NEG_INF;
+        bool valid = j < p.S && bias != MMT_NEG_INF;
+        unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            int pos = b * p.S + count + __popc(m & ((1u << lane) - 1));
+            p.row_off[pos] = (int64_t)j * p.stride_s + (int64_t)b * p.stride_b;
+            p.kbias_c[pos] = bias;
+        }
+        count += __popc(m);
+    }
+    // unused tail rows point at row 0 of this memory so the K/V projection GEMM can run densely
+    for (int jj = count + lane; jj < p.S; jj += 32) {
+        p.row_off[b * p.S + jj] = (int64_t)b * p.stride_b;
+        p.kbias_c[b * p.S + jj] = MMT_NEG_INF;
+    }
+    if (lane == 0) { p.nk[b] = count; p.row_start[b] = b * p.S; }
+}
+
+struct StepCtl {
+    int* step;          // device step counter t
+    int* done_ctas;     // scratch for the last-CTA-advances-the-step protocol
+    int* nonpad;        // [max_len] count of non-<PAD> picks per step
+};
+
+// x[n] = E_tok[token_in(t, n)] + E_pos[t]        (validate_generate_MMT_v15_4.py:746-747)
+__global__ void __launch_bounds__(128) decode_embed(const int64_t* tokens, int tok_shift, int sos, int64_t N, int64_t ldn,
+                                                    const float* E_tok, const float* E_pos, int vocab,
+                                                    const int* step, float* x, __nv_bfloat16* x_bf16) {
+    const int t = *step;
+    const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    int64_t tok;
+    if (tok_shift) tok = (t == 0) ? sos : tokens[(int64_t)(t - 1) * ldn + n];
+    else tok = tokens[(int64_t)t * ldn + n];
+    if (tok < 0 || tok >= vocab) tok = 0;
+    float4 a = *reinterpret_cast<const float4*>(E_tok + tok * D + lane * 4);
+    float4 b = *reinterpret_cast<const float4*>(E_pos + (int64_t)t * D + lane * 4);
+    float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    *reinterpret_cast<float4*>(x + n * D + lane * 4) = o;
+    if (x_bf16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        *reinterpret_cast<uint2*>(x_bf16 + n * D + lane * 4) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+}
+
+// Causal self-attention of the new position over the paged KV cache; one warp per
+// (sequence, head).  Appends this step's K,V to the cache first.
+// page layout: [2 (K,V)][H][PAGE_TOKENS][DH] floats.
+template <int DH>
+__global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, float* kv_pool, const int* block_table,
+                                                             int pages_per_seq, int64_t N, int H, float scale,
+                                                             const int* step, float* out) {
+    const int t = *step;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= N * H) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = w / H;
+    const int h = (int)(w % H);
+    constexpr int PAGE_FLOATS = 2 * PAGE_TOKENS * D;
+    const int* bt = block_table + n * pages_per_seq;
+    const float* row = qkv + n * (3 * D) + h * DH;
+    // append K,V of position t
+    if (lane < 2 * DH) {
+        int kv = lane / DH, d = lane % DH;
+        float* page = kv_pool + (int64_t)bt[t / PAGE_TOKENS] * PAGE_FLOATS;
+        page[((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + d] = row[(1 + kv) * D + d];
+    }
+    __syncwarp();
+    float q[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) q[d] = row[d] * scale;
+    // pass 1: scores (each lane owns keys lane, lane+32, ...)
+    constexpr int MAXK = 4;   // max_len 128 / 32
+    float s[MAXK];
+    float m = MMT_NEG_INF;
+#pragma unroll
+    for (int i = 0; i < MAXK; ++i) {
+        int j = lane + i * 32;
+        s[i] = MMT_NEG_INF;
+        if (j <= t) {
+            const float* page = kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_FLOATS;
+            const float* k = page + ((0 * H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH;
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) a = fmaf(q[d], k[d], a);
+            s[i] = a;
+            m = fmaxf(m, a);
+        }
+    }
+    m = warp_max(m);
+    float l = 0.f, acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXK; ++i) {
+        int j = lane + i * 32;
+        if (j <= t) {
+            float e = expf(s[i] - m);
+            l += e;
+            const float* page = kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_FLOATS;
+            const float* v = page + ((1 * H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, v[d], acc[d]);
+        }
+    }
+    l = warp_sum(l);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d]);
+    if (lane < DH) {
+        float v = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
+        out[n * D + h * DH + lane] = v / l;
+    }
+}
+
+// Cross-attention of the new position over the (compacted) projected memory;
+// one warp per (sequence, head).  K/V layout: [2][H][rows_total][DH] (head-major).
+template <int DH>
+__global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in, const float* kv, int64_t rows_total,
+                                                              const int* nk, const int* row_start, const float* kbias_c,
+                                                              int n_cand, int64_t N, int H, float scale, float* out) {
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= N * H) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = w / H;
+    const int h = (int)(w % H);
+    const int64_t b = n / n_cand;
+    const int cnt = nk[b];
+    const int64_t r0 = row_start[b];
+    const float* Kh = kv + ((int64_t)(0 * H + h) * rows_total + r0) * DH;
+    const float* Vh = kv + ((int64_t)(1 * H + h) * rows_total + r0) * DH;
+    const float* bias = kbias_c + r0;
+    float q[DH], acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) { q[d] = q_in[n * D + h * DH + d] * scale; acc[d] = 0.f; }
+    float m = MMT_NEG_INF, l = 0.f;
+    for (int j = lane; j < cnt; j += 32) {
+        float s = bias[j];
+        const float4* kp = reinterpret_cast<const float4*>(Kh + (int64_t)j * DH);
+#pragma unroll
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
+            float4 k = kp[d4];
+            s = fmaf(q[d4 * 4], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
+            s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
+        }
+        if (s > m) {
+            float corr = expf(m - s);
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] *= corr;
+            m = s;
+        }
+        float e = expf(s - m);
+        l += e;
+        const float4* vp = reinterpret_cast<const float4*>(Vh + (int64_t)j * DH);
+#pragma unroll
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
+            float4 v = vp[d4];
+            acc[d4 * 4] = fmaf(e, v.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(e, v.y, acc[d4 * 4 + 1]);
+            acc[d4 * 4 + 2] = fmaf(e, v.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(e, v.w, acc[d4 * 4 + 3]);
+        }
+    }
+    // merge the 32 per-lane partial softmaxes
+    float M = warp_max(m);
+    float corr = (m == MMT_NEG_INF) ? 0.f : expf(m - M);
+    l = warp_sum(l * corr);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d] * corr);
+    if (lane < DH) {
+        float v = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
+        out[n * D + h * DH + lane] = v / l;
+    }
+}
+
+// ===========================================================================
+// Fused vocab projection + softmax(logits / T) + greedy | multinomial pick
+// (validate_generate_MMT_v15_4.py:753-759, 868-872).  One warp per sequence.
+// ===========================================================================
+struct SampleParams {
+    const float* x;          // [N][D] decoder output of the newest position
+    const float* W;          // fc_out.weight [V][D]
+    const float* b;          // fc_out.bias [V]
+    int V;
+    int64_t N;               // sequences handled by this launch
+    int64_t ldn;             // row length of tokens / probs / logits (sequences in the whole call)
+    float temperature;
+    int mode;                // 0 greedy, 1 multinomial, 2 forced (logits only)
+    RngGeom rng;             // rng.offset is the offset of step 0; step t adds t*rng_inc
+    uint64_t rng_inc;
+    int64_t seq_index_base;
+    int64_t* tokens;         // [max_len][N] or nullptr
+    float* probs;            // [max_len][N] or nullptr
+    float* logits;           // [T][N][V] (forced / unit test) or nullptr
+    StepCtl ctl;             // ctl.step may be nullptr (stand-alone use, t = 0)
+    int advance;             // 1: the last CTA increments *ctl.step
+};
+
+__global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ SampleParams p) {
+    __shared__ float Ws[VOCAB_MAX * (D + 1)];
+    __shared__ __align__(16) float xs[8][D];
+    const int t = p.ctl.step ? *p.ctl.step : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < p.V * D; i += blockDim.x) Ws[(i / D) * (D + 1) + (i % D)] = p.W[i];
+    const int64_t n = (int64_t)blockIdx.x * 8 + warp;
+    if (n < p.N) *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+    __syncthreads();
+    if (n < p.N) {
+        const int v0 = lane, v1 = lane + 32;
+        float a0 = 0.f, a1 = 0.f;
+        const float* w0 = Ws + v0 * (D + 1);
+        const float* w1 = Ws + (v1 < p.V ? v1 : 0) * (D + 1);
+#pragma unroll 8
+        for (int k = 0; k < D; ++k) {
+            float xv = xs[warp][k];
+            a0 = fmaf(xv, w0[k], a0);
+            a1 = fmaf(xv, w1[k], a1);
+        }
+        const bool ok0 = v0 < p.V, ok1 = v1 < p.V;
+        float lg0 = ok0 ? a0 + p.b[v0] : MMT_NEG_INF;
+        float lg1 = ok1 ? a1 + p.b[v1] : MMT_NEG_INF;
+        if (p.logits) {
+            float* out = p.logits + ((int64_t)t * p.ldn + n) * p.V;
+            if (ok0) out[v0] = lg0;
+            if (ok1) out[v1] = lg1;
+        }
+        if (p.mode != 2) {
+            float z0 = ok0 ? lg0 / p.temperature : MMT_NEG_INF;
+            float z1 = ok1 ? lg1 / p.temperature : MMT_NEG_INF;
+            float mx = warp_max(fmaxf(z0, z1));
+            float e0 = ok0 ? expf(z0 - mx) : 0.f;
+            float e1 = ok1 ? expf(z1 - mx) : 0.f;
+            float sum = warp_sum(e0 + e1);
+            float p0 = e0 / sum, p1 = e1 / sum;
+            float r0 = p0, r1 = p1;
+            if (p.mode == 1) {
+                RngGeom g = p.rng;
+                g.offset += (uint64_t)t * p.rng_inc;
+                int64_t li = (p.seq_index_base + n) * p.V;
+                if (ok0) r0 = p0 / torch_exponential_at(g, li + v0);
+                if (ok1) r1 = p1 / torch_exponential_at(g, li + v1);
+            }
+            // argmax with lowest-index ties (torch argmax / multinomial)
+            float best = ok0 ? r0 : MMT_NEG_INF;
+            int bi = ok0 ? v0 : 0x7fffffff;
+            float bp = p0;
+            if (ok1 && (r1 > best)) { best = r1; bi = v1; bp = p1; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                float op = __shfl_xor_sync(0xffffffffu, bp, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bp = op; }
+            }
+            if (lane == 0) {
+                if (p.tokens) p.tokens[(int64_t)t * p.ldn + n] = bi;
+                if (p.probs) p.probs[(int64_t)t * p.ldn + n] = bp;
+                if (p.ctl.nonpad && bi != 0) atomicAdd(p.ctl.nonpad + t, 1);
+            }
+        }
+    }
+    if (p.advance) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            int done = atomicAdd(p.ctl.done_ctas, 1);
+            if (done == (int)gridDim.x - 1) {
+                *p.ctl.done_ctas = 0;
+                *p.ctl.step = t + 1;
+            }
+        }
+    }
+}
+
+__global__ void pack_tokens_u8(const int64_t* in, int64_t n, uint8_t* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)in[i];
+}
+__global__ void unpack_tokens_u8(const uint8_t* in, int64_t n, int64_t* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int64_t)in[i];
+}
+__global__ void f32_to_bf16(const float* in, int64_t n, __nv_bfloat16* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+}  // namespace mmt

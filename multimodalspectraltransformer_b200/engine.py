@@ -1,0 +1,245 @@
+"""Python handle on one libmmt_b200 engine (weights resident on one B200).
+
+PyTorch is plumbing here: it owns the input/output tensors and the CUDA stream;
+all arithmetic of the path runs in the hand-written kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import DecodeArgs, ModelDesc, Spectra
+
+_PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+
+
+def _desc_from(config, state_dict=None) -> ModelDesc:
+    g = lambda k, dflt: int(getattr(config, k, dflt))
+    d_ff = 2048                         # torch default dim_feedforward; the reference never overrides it
+    if state_dict is not None and "decoder.layers.0.linear1.weight" in state_dict:
+        d_ff = int(state_dict["decoder.layers.0.linear1.weight"].shape[0])
+    return ModelDesc(
+        d_model=g("hidden_size", 128), n_heads=g("num_heads", 16), n_heads_cross=int(g("num_heads", 16) / 4),
+        d_ff=d_ff, n_enc_layers=g("num_encoder_layers", 6), n_dec_layers=g("num_decoder_layers", 6),
+        vocab=g("out_size", 43), max_len=g("max_len", 128), mf_vocab=g("MF_vocab_size", 212),
+        ms_vocab=g("MS_vocab_size", 43), ir_bins=g("input_dim_IR", 1000), fp_size=g("fingerprint_size", 512),
+        pad_points=g("padding_points_number", 64))
+
+
+def default_precision(config) -> str:
+    """``config.precision`` ("fp32" check mode | "bf16" tensor-core mode); fp32 when unset."""
+    return str(getattr(config, "precision", "fp32"))
+
+
+class Engine:
+    """Weights of one MultimodalTransformer packed on ``device`` + the kernel drivers."""
+
+    def __init__(self, state_dict, config, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mmt_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"mmt_b200 engine cannot run on device {device!r}; there is no CPU fallback")
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.desc = _desc_from(config, state_dict)
+        L, d = self.L, C.byref(self.desc)
+        n = L.mmt_weight_count(d)
+        if n < 0:
+            _lib.check(1)
+        total = L.mmt_weight_total(d)
+        blob = torch.zeros(total, dtype=torch.float32)
+        for i in range(n):
+            name = L.mmt_weight_name(d, i).decode()
+            numel, off = L.mmt_weight_numel(d, i), L.mmt_weight_offset(d, i)
+            if name not in state_dict:
+                if name.startswith("real_data_linear"):
+                    continue
+                raise KeyError(f"state_dict lacks {name}")
+            t = state_dict[name].detach().to("cpu", torch.float32).reshape(-1)
+            if t.numel() != numel:
+                raise ValueError(f"{name}: {t.numel()} elements, engine expects {numel}")
+            blob[off:off + numel] = t
+        h = C.c_void_p()
+        _lib.check(L.mmt_create(d, blob.data_ptr(), total, self.dev_index, C.byref(h)))
+        self.h = h
+        self._finalizer = weakref.finalize(self, L.mmt_destroy, h)
+        props = torch.cuda.get_device_properties(self.dev_index)
+        self.sm_count = props.multi_processor_count
+        self.max_threads_per_sm = props.max_threads_per_multi_processor
+        self.vocab = self.desc.vocab
+
+    # ------------------------------------------------------------------ util
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev_index).cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.L.mmt_launch_count(self.h))
+
+    def memory_len(self, training_mode: str) -> int:
+        return int(self.L.mmt_memory_len(C.byref(self.desc), _lib.mode_bits(training_mode)))
+
+    def philox_increment(self, n_total: int) -> int:
+        return int(self.L.mmt_philox_increment(n_total * self.vocab, self.sm_count, self.max_threads_per_sm))
+
+    # ---------------------------------------------------------------- encode
+    def encode(self, data, training_mode: str, precision="fp32", want_embedding_src=False):
+        """data: dict of CUDA tensors in the collate contract. Returns
+        (memory (S,B,128), pad_mask u8 (B,S), key_bias (B,S), fingerprint (B,fp), avg (B,128), embedding_src|None)."""
+        bits = _lib.mode_bits(training_mode)
+        dev = self.device
+        keep = []
+
+        def f32(k):
+            t = data[k].to(dev, torch.float32).contiguous()
+            keep.append(t)
+            return t
+
+        sp = Spectra()
+        B = None
+        for m in ("1H", "13C", "HSQC", "COSY"):
+            if bits & _lib.MODE_BITS[m]:
+                x, mk = f32(f"src_{m}"), f32(f"mask_{m}")
+                setattr(sp, f"d_src_{m}", x.data_ptr()); setattr(sp, f"d_mask_{m}", mk.data_ptr())
+                B = x.shape[0]
+        if B is None:
+            raise TypeError("training_mode needs at least one of 1H/13C/HSQC/COSY (the reference fails on "
+                            "current_batch_size=False, validate_generate_MMT_v15_4.py:122-131,165)")
+        if bits & _lib.MODE_BITS["IR"]:
+            sp.d_src_IR = f32("src_IR").data_ptr()
+        for m in ("MF", "MS"):
+            if bits & _lib.MODE_BITS[m]:
+                ids = data[f"src_{m}"].to(dev, torch.int64).contiguous()
+                mk = (data[f"mask_{m}"].to(dev) != 0).to(torch.uint8).contiguous()
+                keep += [ids, mk]
+                setattr(sp, f"d_src_{m}", ids.data_ptr()); setattr(sp, f"d_mask_{m}", mk.data_ptr())
+        if bits & _lib.MODE_BITS["MW"]:
+            sp.d_trg_MW = f32("trg_MW").reshape(-1).data_ptr()
+        else:
+            raise AttributeError("training_mode needs MW (the reference fails at trg_MW.unsqueeze, "
+                                 "validate_generate_MMT_v15_4.py:118)")
+        S = self.memory_len(training_mode)
+        D, FP = self.desc.d_model, self.desc.fp_size
+        memory = torch.empty(S, B, D, device=dev, dtype=torch.float32)
+        emb = torch.empty(S, B, D, device=dev, dtype=torch.float32) if want_embedding_src else None
+        key_bias = torch.empty(B, S, device=dev, dtype=torch.float32)
+        pad = torch.empty(B, S, device=dev, dtype=torch.uint8)
+        fp = torch.empty(B, FP, device=dev, dtype=torch.float32)
+        avg = torch.empty(B, D, device=dev, dtype=torch.float32)
+        _lib.check(self.L.mmt_encode(self.h, C.byref(sp), B, bits, _PREC[precision], memory.data_ptr(),
+                                     emb.data_ptr() if emb is not None else None, key_bias.data_ptr(),
+                                     pad.data_ptr(), fp.data_ptr(), avg.data_ptr(), self._stream()))
+        for t in keep:   # the kernels read these on the current stream
+            t.record_stream(torch.cuda.current_stream(self.dev_index))
+        return memory, pad, key_bias, fp, avg, emb
+
+    # ---------------------------------------------------------------- decode
+    def _decode_args(self, memory, key_bias, n_cand, max_len, temperature, sampling, stop_on_all_pad, precision,
+                     seed=0, offset=0, seq_index_base=0, n_total=0):
+        if memory.dim() != 3 or memory.shape[2] != self.desc.d_model:
+            raise ValueError("memory must be (S, B, 128)")
+        memory = memory.to(self.device, torch.float32)
+        if memory.stride(2) != 1 or memory.stride(0) % 4 or memory.stride(1) % 4 or memory.data_ptr() % 16:
+            memory = memory.contiguous()
+        key_bias = key_bias.to(self.device, torch.float32).contiguous()
+        S, Bm = memory.shape[0], memory.shape[1]
+        if tuple(key_bias.shape) != (Bm, S):
+            raise ValueError(f"mask shape {tuple(key_bias.shape)} does not match memory {(Bm, S)}")
+        a = DecodeArgs(d_memory=memory.data_ptr(), stride_s=memory.stride(0), stride_b=memory.stride(1),
+                       d_key_bias=key_bias.data_ptr(), S=S, Bm=Bm, n_cand=n_cand, max_len=max_len,
+                       temperature=float(temperature), sampling=sampling, stop_on_all_pad=int(stop_on_all_pad),
+                       precision=_PREC[precision], philox_seed=seed, philox_offset=offset,
+                       seq_index_base=seq_index_base, N_total=n_total, rng_sm_count=0, rng_max_threads_per_sm=0)
+        return a, (memory, key_bias)
+
+    def decode(self, memory, key_bias, *, n_cand=1, max_len=128, temperature=1.0, sampling="greedy",
+               stop_on_all_pad=False, precision="fp32", seed=0, offset=0, seq_index_base=0, n_total=0):
+        """Returns (tokens (T,N) i64, probs (T,N) f32, steps) with T == max_len rows allocated."""
+        smp = _lib.SAMPLE_GREEDY if sampling == "greedy" else _lib.SAMPLE_MULTINOMIAL
+        a, keep = self._decode_args(memory, key_bias, n_cand, max_len, temperature, smp, stop_on_all_pad, precision,
+                                    seed, offset, seq_index_base, n_total)
+        N = a.Bm * n_cand
+        tokens = torch.empty(max_len, N, device=self.device, dtype=torch.int64)
+        probs = torch.empty(max_len, N, device=self.device, dtype=torch.float32)
+        steps = C.c_int32(max_len)
+        _lib.check(self.L.mmt_decode(self.h, C.byref(a), tokens.data_ptr(), probs.data_ptr(), C.byref(steps), self._stream()))
+        for t in keep:
+            t.record_stream(torch.cuda.current_stream(self.dev_index))
+        return tokens, probs, int(steps.value)
+
+    def teacher_forced(self, memory, key_bias, trg, *, n_cand=1, precision="fp32"):
+        """trg (T,N) i64 -> logits (T,N,V)."""
+        trg = trg.to(self.device, torch.int64).contiguous()
+        T, N = trg.shape
+        a, keep = self._decode_args(memory, key_bias, n_cand, max(T, 1), 1.0, 0, False, precision)
+        if a.Bm * n_cand != N:
+            raise ValueError("target batch does not match memory batch")
+        logits = torch.empty(T, N, self.vocab, device=self.device, dtype=torch.float32)
+        _lib.check(self.L.mmt_teacher_forced(self.h, C.byref(a), trg.data_ptr(), T, logits.data_ptr(), self._stream()))
+        for t in keep + (trg,):
+            t.record_stream(torch.cuda.current_stream(self.dev_index))
+        return logits
+
+    # ------------------------------------------------------------ unit hooks
+    def sample(self, x, temperature=1.0, sampling="greedy", seed=0, offset=0, seq_index_base=0, n_total=0,
+               want_logits=False):
+        x = x.to(self.device, torch.float32).contiguous()
+        N = x.shape[0]
+        tok = torch.empty(N, device=self.device, dtype=torch.int64)
+        pr = torch.empty(N, device=self.device, dtype=torch.float32)
+        lg = torch.empty(N, self.vocab, device=self.device, dtype=torch.float32) if want_logits else None
+        smp = _lib.SAMPLE_GREEDY if sampling == "greedy" else _lib.SAMPLE_MULTINOMIAL
+        _lib.check(self.L.mmt_sample(self.h, x.data_ptr(), N, float(temperature), smp, seed, offset, seq_index_base,
+                                     n_total, 0, 0, tok.data_ptr(), pr.data_ptr(),
+                                     lg.data_ptr() if lg is not None else None, self._stream()))
+        return tok, pr, lg
+
+    def linear(self, A, W, bias=None, act=0, precision="fp32"):
+        A = A.to(self.device, torch.float32).contiguous()
+        W = W.to(self.device, torch.float32).contiguous()
+        b = bias.to(self.device, torch.float32).contiguous() if bias is not None else None
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, device=self.device, dtype=torch.float32)
+        _lib.check(self.L.mmt_linear(self.h, A.data_ptr(), W.data_ptr(), b.data_ptr() if b is not None else None,
+                                     out.data_ptr(), M, N, K, act, _PREC[precision], self._stream()))
+        return out
+
+    def pack_tokens(self, tokens):
+        tokens = tokens.contiguous()
+        out = torch.empty(tokens.shape, device=self.device, dtype=torch.uint8)
+        _lib.check(self.L.mmt_pack_tokens_u8(tokens.data_ptr(), tokens.numel(), out.data_ptr(), self._stream()))
+        return out
+
+    def unpack_tokens(self, packed):
+        packed = packed.contiguous()
+        out = torch.empty(packed.shape, device=self.device, dtype=torch.int64)
+        _lib.check(self.L.mmt_unpack_tokens_u8(packed.data_ptr(), packed.numel(), out.data_ptr(), self._stream()))
+        return out
+
+
+# one engine per (model object, parameter version): callers pass a live nn.Module every
+# call, exactly like the reference's functions, never weights.
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+def _param_version(model):
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+def engine_for(model, config) -> Engine:
+    dev = torch.device(getattr(config, "device", "cuda"))
+    if dev.type != "cuda":
+        raise RuntimeError(f"config.device={dev} - the B200 engine has no CPU path")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    ver = (_param_version(model), str(dev))
+    hit = _ENGINES.get(model)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    eng = Engine(model.state_dict(), getattr(model, "config", config), dev)
+    _ENGINES[model] = (ver, eng)
+    return eng

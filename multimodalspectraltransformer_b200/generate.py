@@ -1,0 +1,155 @@
+"""The reference's generation entry points, same names / arguments / return layouts,
+running on the B200 engine.
+
+    run_model                    validate_generate_MMT_v15_4.py:95-267
+    greedy_sequence              validate_generate_MMT_v15_4.py:723-775
+    multinomial_sequence         validate_generate_MMT_v15_4.py:841-880
+    multinomial_sequence_multi   run_batch_gen_val_MMT_v15_4.py:121-158
+    duplicate_tensor / _dict     run_batch_gen_val_MMT_v15_4.py:93-107
+    greedy_sequence_2            mmt_result_test_functions_15_4.py:984-1032
+    multinomial_sequence_multi_2 mmt_result_test_functions_15_4.py:791-829
+
+``model`` may be this package's ``MultimodalTransformer`` or the reference's own
+instance: only its ``state_dict()`` is read.  Runtime knobs (``device``,
+``training_mode``, ``max_len``, ``temperature``, optional ``precision``) are read
+from ``config`` at call time, never cached (callers mutate it mid-run,
+mmt_result_test_functions_15_4.py:547).
+
+Extensions (keyword-only, default = reference behaviour):
+  n_candidates=k   decode k sequences per memory column without materialising the
+                   reference's 128x tensor duplication (cross-attention K/V shared);
+  seq_index_base / n_total  place the call inside a larger logical batch so sharded
+                   runs draw the Philox numbers of the unsharded run.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import engine as _engine
+
+SOS_KEY, PAD = "<SOS>", 0
+
+
+# ------------------------------------------------------------------ helpers
+def _mask_to_bias(mask: torch.Tensor) -> torch.Tensor:
+    """Key-padding mask -> additive attention bias, torch semantics: bool True -> -inf;
+    floating masks are added as they are.  Integer masks, which
+    torch >= 2 rejects and the reference's collate_fn produces for mask_MF, are read
+    as bool (non-zero = pad) -- SURVEY.md B.1."""
+    if mask.is_floating_point():
+        return mask.to(torch.float32)
+    pad = mask if mask.dtype == torch.bool else (mask != 0)
+    return torch.zeros(pad.shape, dtype=torch.float32, device=pad.device).masked_fill_(pad, float("-inf"))
+
+
+def _encode(eng, data, config, want_embedding_src=False):
+    prec = _engine.default_precision(config)
+    memory, pad, key_bias, fp, avg, emb = eng.encode(data, config.training_mode, prec, want_embedding_src)
+    from . import _lib
+    if _lib.lib().mmt_mask_is_float(_lib.mode_bits(config.training_mode)):
+        mask = pad.to(torch.float32)       # torch.cat promoted the reference's mask to float 0/1
+    else:
+        mask = pad.to(torch.bool)
+    return memory, mask, fp, avg, emb
+
+
+def _check_sos(stoi):
+    sos = stoi[SOS_KEY]
+    if sos != 3:
+        raise ValueError("the engine hard-codes <SOS> = 3 (stoi.json)")
+    return sos
+
+
+def _philox_state(dev_index):
+    g = torch.cuda.default_generators[dev_index]
+    return g, int(g.initial_seed()), int(g.get_offset())
+
+
+# ------------------------------------------------------------------- encoder
+def run_model(model, data_dict, config):
+    """-> (memory (S,B,128), src_padding_mask (B,S), trg_enc_SMI, fingerprint (B,512), src_HSQC, src_COSY)."""
+    eng = _engine.engine_for(model, config)
+    x = data_dict
+    dev = config.device
+    memory, mask, fingerprint, _, _ = _encode(eng, x, config)
+    src_HSQC = x["src_HSQC"].to(dev) if "HSQC" in config.training_mode else x["src_HSQC_"].to(dev)
+    src_COSY = x["src_COSY"].to(dev) if "COSY" in config.training_mode else x["src_COSY_"].to(dev)
+    return memory, mask, x["trg_enc_SMI"].to(dev), fingerprint, src_HSQC, src_COSY
+
+
+def duplicate_tensor(tensor, n_times):
+    repeat_dims = [n_times] + [1] * (tensor.dim() - 1)
+    return tensor.repeat(*repeat_dims).to("cuda")
+
+
+def duplicate_dict(data_dict, n_times):
+    return {k: duplicate_tensor(v, n_times) for k, v in data_dict.items()}
+
+
+# ------------------------------------------------------------------- decoder
+def _decode(model, memory, src_padding_mask, config, sampling, stop_on_all_pad, n_candidates, seq_index_base, n_total):
+    model.eval()                                    # the reference flips eval() and leaves it
+    eng = _engine.engine_for(model, config)
+    prec = _engine.default_precision(config)
+    bias = _mask_to_bias(src_padding_mask.to(eng.device))
+    N = memory.size(1) * n_candidates
+    kw = {}
+    gen = None
+    if sampling == "multinomial":
+        gen, seed, offset = _philox_state(eng.dev_index)
+        kw = dict(seed=seed, offset=offset)
+    tokens, probs, steps = eng.decode(memory, bias, n_cand=n_candidates, max_len=int(config.max_len),
+                                      temperature=float(config.temperature), sampling=sampling,
+                                      stop_on_all_pad=stop_on_all_pad, precision=prec,
+                                      seq_index_base=seq_index_base, n_total=n_total, **kw)
+    if gen is not None:   # consume exactly what max_len torch.multinomial calls would have
+        inc = eng.philox_increment(n_total if n_total else N)
+        gen.set_offset(offset + inc * int(config.max_len))
+    return tokens, probs, steps
+
+
+def greedy_sequence(model, stoi, itos, memory, src_padding_mask, config, *, n_candidates=1):
+    """-> ((T,N) i64 tokens without <SOS>, (T-1,N) f32 probs).  T < max_len only when one
+    step emitted <PAD> for every sequence.  NB the reference fails for N == 1
+    (SURVEY.md B.6); this returns the shapes its N > 1 code path would."""
+    _check_sos(stoi)
+    tokens, probs, steps = _decode(model, memory, src_padding_mask, config, "greedy", True, n_candidates, 0, 0)
+    return tokens[:steps], probs[1:steps]
+
+
+def greedy_sequence_2(model, stoi, itos, memory, src_padding_mask, config, *, n_candidates=1):
+    """mrtf variant: probabilities are NOT sliced -> ((T,N), (T,N))."""
+    _check_sos(stoi)
+    tokens, probs, steps = _decode(model, memory, src_padding_mask, config, "greedy", True, n_candidates, 0, 0)
+    return tokens[:steps], probs[:steps]
+
+
+def multinomial_sequence(model, stoi, memory, src_padding_mask, config, *, n_candidates=1, seq_index_base=0, n_total=0):
+    """-> ((T,N) i64, (N,T) f32): probabilities transposed, always max_len steps."""
+    _check_sos(stoi)
+    tokens, probs, _ = _decode(model, memory, src_padding_mask, config, "multinomial", False, n_candidates, seq_index_base, n_total)
+    return tokens, probs.transpose(0, 1)
+
+
+def multinomial_sequence_multi(model, memory, src_padding_mask, stoi, config, *, n_candidates=1, seq_index_base=0, n_total=0):
+    """-> ((T,N) i64, (T,N) f32); the reference's .squeeze() drops the N axis of the
+    probabilities when N == 1 (run_batch_gen_val_MMT_v15_4.py:149)."""
+    _check_sos(stoi)
+    tokens, probs, _ = _decode(model, memory, src_padding_mask, config, "multinomial", False, n_candidates, seq_index_base, n_total)
+    if probs.shape[1] == 1:
+        probs = probs.squeeze(1)
+    return tokens, probs
+
+
+def multinomial_sequence_multi_2(model, memory, src_padding_mask, stoi, config, *, n_candidates=1, seq_index_base=0, n_total=0):
+    """mrtf variant: probabilities lose their first row -> ((T,N), (T-1,N))."""
+    tokens, probs = multinomial_sequence_multi(model, memory, src_padding_mask, stoi, config, n_candidates=n_candidates,
+                                               seq_index_base=seq_index_base, n_total=n_total)
+    return tokens, probs[1:]
+
+
+def teacher_forced_logits(model, memory, src_padding_mask, trg_SMI_input, config, *, n_candidates=1):
+    """Decoder tail of forward(..., trg) (models_MMT_v15_4.py:955-976): (T,N) ids -> (T,N,V) logits."""
+    eng = _engine.engine_for(model, config)
+    bias = _mask_to_bias(src_padding_mask.to(eng.device))
+    return eng.teacher_forced(memory, bias, trg_SMI_input, n_cand=n_candidates, precision=_engine.default_precision(config))

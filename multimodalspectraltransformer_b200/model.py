@@ -1,0 +1,87 @@
+"""``MultimodalTransformer`` with the reference's constructor, attribute names and
+``forward`` contract (reference utils_MMT/models_MMT_v15_4.py:487-976), executing on
+the B200 engine.
+
+The sub-modules below only *hold parameters*: their names and creation order are
+the reference's, so ``state_dict()`` keys, checkpoint loading and
+``torch.manual_seed(s)`` random initialisation are identical to the reference
+model (its attribute names are de-facto API: the reference's own generation
+functions reach into ``model.embed_trg``, ``model.decoder``, ... SURVEY.md 1).
+No torch module is ever *called* on the product path: ``forward`` hands the
+tensors to the CUDA engine and raises when no sm_100a device is present.
+"""
+from __future__ import annotations
+
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+
+
+def _holder(**children):
+    m = nn.Module()
+    for k, v in children.items():
+        m.add_module(k, v)
+    return m
+
+
+class MultimodalTransformer(nn.Module):
+    def __init__(self, config, src_pad_idx=0):
+        super().__init__()
+        self.config = config
+        h = config.hidden_size
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            # embedders (models_MMT_v15_4.py:495-502)
+            self.linear_spec_embedding_1H = _holder(point_embedding_layer_1H=_holder(fc_H=nn.Linear(config.input_dim_1H, h)))
+            self.linear_spec_embedding_13C = _holder(point_embedding_layer_13C=_holder(fc_C=nn.Linear(config.input_dim_13C, h)))
+            self.linear_spec_embedding_HSQC = _holder(point_embedding_layer_HSQC=_holder(fc_HSQC=nn.Linear(config.input_dim_HSQC, h)))
+            self.linear_spec_embedding_COSY = _holder(point_embedding_layer_COSY=_holder(fc_COSY=nn.Linear(config.input_dim_COSY, h)))
+            self.linear_spec_embedding_IR = _holder(linear_spec_embedding_IR=nn.Linear(config.input_dim_IR, h))
+            self.linear_embedding_MF = _holder(embedding=nn.Embedding(config.MF_vocab_size, h, padding_idx=0))
+            self.linear_embedding_MS = _holder(embedding=nn.Embedding(config.MS_vocab_size, h, padding_idx=0))
+            self.linear_embedding_MW = _holder(linear_spec_embedding_MW=nn.Linear(1, h))
+            # target embedding (:505-506)
+            self.embed_trg = nn.Embedding(config.in_size, h)
+            self.pe_trg = nn.Embedding(config.max_len, h)
+            # encoder / decoder stacks (:510-541); parameter containers only
+            for name in ("1H", "13C", "HSQC", "COSY", "IR"):
+                setattr(self, f"encoder_{name}", nn.TransformerEncoder(
+                    nn.TransformerEncoderLayer(d_model=h, nhead=config.num_heads), num_layers=config.num_encoder_layers))
+            self.encoder_cross = nn.TransformerEncoder(
+                nn.TransformerEncoderLayer(d_model=h, nhead=int(config.num_heads / 4)), num_layers=config.num_encoder_layers)
+            self.decoder = nn.TransformerDecoder(
+                nn.TransformerDecoderLayer(d_model=h, nhead=config.num_heads), num_layers=config.num_decoder_layers)
+            self.fp1 = nn.Linear(h, config.fingerprint_size)
+            self.dropout2 = nn.Dropout(config.drop_out)
+            self.fc_out = nn.Linear(h, config.out_size)
+            self.real_data_linear = nn.Linear(h, config.out_size)
+
+    # the causal mask the reference builds per step; kept for API compatibility only
+    def generate_square_subsequent_mask(self, sz):
+        mask = torch.triu(torch.full((sz, sz), float("-inf")), diagonal=1)
+        return mask.to(self.config.device)
+
+    def forward(self, src_1H, mask_1H, src_13C, mask_13C, src_HSQC, mask_HSQC, src_COSY, mask_COSY, src_IR, mask_IR,
+                src_MF, mask_MF, src_MS, mask_MS, trg_MW, trg_SMI_input=None):
+        """models_MMT_v15_4.py:803-976.  trg None -> (memory, embedding_src, src_padding_mask, fingerprint);
+        else -> (output (T,N,V), fingerprint, memory, src_padding_mask)."""
+        from .generate import _encode, _mask_to_bias
+        data = dict(src_1H=src_1H, mask_1H=mask_1H, src_13C=src_13C, mask_13C=mask_13C, src_HSQC=src_HSQC,
+                    mask_HSQC=mask_HSQC, src_COSY=src_COSY, mask_COSY=mask_COSY, src_IR=src_IR, mask_IR=mask_IR,
+                    src_MF=src_MF, mask_MF=mask_MF, src_MS=src_MS, mask_MS=mask_MS, trg_MW=trg_MW)
+        eng = _engine.engine_for(self, self.config)
+        prec = _engine.default_precision(self.config)
+        memory, mask, fingerprint, avg, emb = _encode(eng, data, self.config, want_embedding_src=True)
+        if trg_SMI_input is None:
+            return memory, emb, mask, fingerprint
+        if self.training and self.config.drop_out > 0:
+            raise RuntimeError("the B200 engine is inference-only: call model.eval() (dropout2 is not implemented)")
+        logits = eng.teacher_forced(memory, _mask_to_bias(mask), trg_SMI_input, precision=prec)
+        if getattr(self.config, "use_real_data", False):      # :965-971
+            rd = torch.nn.functional.linear(avg, self.real_data_linear.weight.to(avg.device),
+                                            self.real_data_linear.bias.to(avg.device))
+            logits = (logits + rd.unsqueeze(0)) / 2
+        return logits, fingerprint, memory, mask
