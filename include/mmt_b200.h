@@ -195,6 +195,13 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
 /* launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t mmt_launch_count(const mmt_engine* e);
 
+/* Per-kernel-class device time for the roofline report: while enabled, every
+ * launch is bracketed by CUDA events recorded on the launching stream.
+ * mmt_profile_report synchronises the device and writes a JSON object
+ * {"kernel": {"launches": n, "ms": total, "flops": algorithmic GEMM flops}, ...}. */
+int32_t mmt_profile_enable(mmt_engine* e, int32_t on);
+int32_t mmt_profile_report(mmt_engine* e, char* buf, int64_t buf_len);
+
 #ifdef __cplusplus
 }
 #endif

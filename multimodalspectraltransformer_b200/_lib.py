@@ -25,6 +25,7 @@ EXPORTS = [
     "mmt_weight_offset", "mmt_weight_total", "mmt_create", "mmt_destroy", "mmt_memory_len",
     "mmt_mask_is_float", "mmt_encode", "mmt_decode", "mmt_teacher_forced", "mmt_philox_increment",
     "mmt_pack_tokens_u8", "mmt_unpack_tokens_u8", "mmt_sample", "mmt_linear", "mmt_launch_count",
+    "mmt_profile_enable", "mmt_profile_report",
 ]
 
 MODE_BITS = {"1H": 1, "13C": 2, "HSQC": 4, "COSY": 8, "IR": 16, "MF": 32, "MS": 64, "MW": 128}
@@ -125,6 +126,8 @@ def lib():
     L.mmt_sample.restype = i32
     L.mmt_linear.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]; L.mmt_linear.restype = i32
     L.mmt_launch_count.argtypes = [vp]; L.mmt_launch_count.restype = i64
+    L.mmt_profile_enable.argtypes = [vp, i32]; L.mmt_profile_enable.restype = i32
+    L.mmt_profile_report.argtypes = [vp, C.c_char_p, i64]; L.mmt_profile_report.restype = i32
     if L.mmt_abi_version() != 1:
         raise RuntimeError("libmmt_b200.so ABI version mismatch")
     _LIB = L

@@ -17,9 +17,24 @@ static const char* kEmbedKeys[5] = {
     "linear_spec_embedding_IR.linear_spec_embedding_IR"};
 static const char* kEncNames[6] = {"encoder_1H", "encoder_13C", "encoder_HSQC", "encoder_COSY", "encoder_IR", "encoder_cross"};
 
-static int check_launch(mmt_engine* e, const char* what) {
+// Every kernel launch goes through prof_pre()/check_launch(): counts launches and, when
+// profiling is enabled (mmt_profile_enable), brackets the launch with CUDA events recorded
+// on the launching stream so bench.py can report per-kernel-class device time.
+static void prof_pre(mmt_engine* e, cudaStream_t s) {
+    if (!e->profiling) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    e->prof_open = {a, b};
+}
+static int check_launch(mmt_engine* e, const char* what, cudaStream_t s = nullptr, double work = 0.0) {
     e->launches++;
     cudaError_t err = cudaGetLastError();
+    if (e->profiling && e->prof_open.first) {
+        cudaEventRecord(e->prof_open.second, s);
+        e->prof_records.push_back({what, e->prof_open.first, e->prof_open.second, work});
+        e->prof_open = {nullptr, nullptr};
+    }
     if (err != cudaSuccess) MMT_FAIL(std::string(what) + " launch -> " + cudaGetErrorString(err));
     return 0;
 }
@@ -41,12 +56,16 @@ static int launch_gemm(mmt_engine* e, GemmParams& p, int ngroups, int maxM, cuda
     if (p.splits < 1) p.splits = 1;
     if (maxM >= 1024) {
         dim3 grid((p.N + 127) / 128, (maxM + 127) / 128, ngroups * p.splits);
+        prof_pre(e, s);
         gemm_nt_f32<128, 128, 8, 8><<<grid, 256, 0, s>>>(p);
     } else {
         dim3 grid((p.N + 63) / 64, (maxM + 31) / 32, ngroups * p.splits);
+        prof_pre(e, s);
         gemm_nt_f32<32, 64, 2, 4><<<grid, 256, 0, s>>>(p);
     }
-    return check_launch(e, "gemm_nt_f32");
+    double rows = 0;
+    for (int i = 0; i < ngroups; ++i) rows += p.g[i].M;
+    return check_launch(e, "gemm_nt_f32", s, 2.0 * rows * p.N * p.K);
 }
 
 static GemmParams gemm_params(int N, int K, int64_t ldc, int act) {
@@ -67,8 +86,9 @@ static int pick_splits(int M, int N, int K) {
 static int launch_ln(mmt_engine* e, LnParams& p, int ngroups, int maxM, cudaStream_t s) {
     if (maxM <= 0) return 0;
     dim3 grid((maxM + 7) / 8, ngroups);
+    prof_pre(e, s);
     bias_res_layernorm<<<grid, 256, 0, s>>>(p);
-    return check_launch(e, "bias_res_layernorm");
+    return check_launch(e, "bias_res_layernorm", s);
 }
 
 // ---------------------------------------------------------------------------
@@ -178,15 +198,18 @@ static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         int threads = maxS > 256 ? 256 : 128;
         if (dh == 8) {
             MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_pre(e, s);
             attn_encoder_f32<8><<<grid, threads, smem, s>>>(p);
         } else if (dh == 32) {
             MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_pre(e, s);
             attn_encoder_f32<32><<<grid, threads, smem, s>>>(p);
         } else if (dh == 16) {
             MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_pre(e, s);
             attn_encoder_f32<16><<<grid, threads, smem, s>>>(p);
         } else MMT_FAIL("unsupported head dim " + std::to_string(dh));
-        MMT_TRY(check_launch(e, "attn_encoder_f32"));
+        MMT_TRY(check_launch(e, "attn_encoder_f32", s));
     }
     {   // out-proj -> +residual -> LN1 (in place on X)
         GemmParams p = gemm_params(D, D, D, 0);
@@ -286,8 +309,9 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
         p.B = Bc; p.S_total = L.S_total; p.P = P; p.float_mask = L.float_mask;
         p.cross_X = b.Xc; p.key_bias = key_bias; p.pad_mask = pad_mask;
         p.embedding_src = d_embedding_src; p.B_total = B_total; p.b0 = b0;
+        prof_pre(e, s);
         embed_tokens<<<dim3(Bc, 5), 128, 0, s>>>(p);
-        MMT_TRY(check_launch(e, "embed_tokens"));
+        MMT_TRY(check_launch(e, "embed_tokens", s));
     }
     {   // key compaction for the modality encoders and encoder_cross
         KeyIndexParams p;
@@ -296,8 +320,9 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
         for (int m = 0; m < 5; ++m) if (L.present[m]) { p.g[ng].kbias = b.kb[m]; p.g[ng].kidx = b.kidx[m]; p.g[ng].nk = b.nk[m]; p.g[ng].S = L.S_m[m]; ++ng; }
         p.g[ng].kbias = key_bias; p.g[ng].kidx = b.kidx_c; p.g[ng].nk = b.nk_c; p.g[ng].S = L.S_total; ++ng;
         p.B = Bc;
+        prof_pre(e, s);
         build_key_index<<<dim3(Bc, ng), 32, 0, s>>>(p);
-        MMT_TRY(check_launch(e, "build_key_index"));
+        MMT_TRY(check_launch(e, "build_key_index", s));
     }
     // five modality encoders, batched as groups of one launch
     {
@@ -394,8 +419,9 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
     mp.key_bias = a.d_key_bias + (int64_t)b0 * a.S; mp.S = a.S; mp.Bm = Bmw;
     mp.stride_s = a.stride_s; mp.stride_b = a.stride_b;
     mp.nk = b.nk; mp.row_start = b.row_start; mp.row_off = b.row_off; mp.kbias_c = b.kbias_c;
+    prof_pre(e, s);
     build_memory_index<<<Bmw, 32, 0, s>>>(mp);
-    MMT_TRY(check_launch(e, "build_memory_index"));
+    MMT_TRY(check_launch(e, "build_memory_index", s));
     const int64_t R = (int64_t)Bmw * a.S;
     const int dh = D / d.n_heads;
     for (int l = 0; l < d.n_dec_layers; ++l) {
@@ -421,9 +447,10 @@ static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64
     const int64_t N_total = (int64_t)a.Bm * a.n_cand;
     const int M = (int)Nw;
 
+    prof_pre(e, s);
     if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, nullptr);
     else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, nullptr);
-    MMT_TRY(check_launch(e, "decode_embed"));
+    MMT_TRY(check_launch(e, "decode_embed", s));
 
     auto ln = [&](const float* part, int splits, const float* bias, const float* gamma, const float* beta) -> int {
         LnParams q;
@@ -445,15 +472,17 @@ static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64
         const LayerW& w = e->dec[l];
         MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
         float* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D;
+        prof_pre(e, s);
         if (dh == 8) decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, b.att);
         else MMT_FAIL("decoder head dim must be 8");
-        MMT_TRY(check_launch(e, "decode_self_attention"));
+        MMT_TRY(check_launch(e, "decode_self_attention", s));
         MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
         MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
         MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
+        prof_pre(e, s);
         decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, b.cross_kv + (size_t)l * 2 * R * D, R, b.nk, b.row_start, b.kbias_c,
                                                              a.n_cand, Nw, H, scale, b.att);
-        MMT_TRY(check_launch(e, "decode_cross_attention"));
+        MMT_TRY(check_launch(e, "decode_cross_attention", s));
         MMT_TRY(gemm(b.att, D, w.ca_out_w, nullptr, b.part, D, D, 0, 1));
         MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
         MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
@@ -476,8 +505,9 @@ static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64
     sp.logits = r.logits ? r.logits + n0 * d.vocab : nullptr;
     sp.ctl.step = b.ctl; sp.ctl.done_ctas = b.ctl + 1; sp.ctl.nonpad = (r.mode == 0) ? b.ctl + 8 : nullptr;
     sp.advance = 1;
+    prof_pre(e, s);
     sample_tokens<<<(unsigned)((Nw + 7) / 8), 256, 0, s>>>(sp);
-    MMT_TRY(check_launch(e, "sample_tokens"));
+    MMT_TRY(check_launch(e, "sample_tokens", s));
     return 0;
 }
 
@@ -510,8 +540,9 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         const int Bmw = std::min(Bm_wave, a.Bm - b0);
         const int64_t Nw = (int64_t)Bmw * a.n_cand, n0 = (int64_t)b0 * a.n_cand;
         MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
+        prof_pre(e, s);
         init_block_table<<<(unsigned)((Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, Nw * pps);
-        MMT_TRY(check_launch(e, "init_block_table"));
+        MMT_TRY(check_launch(e, "init_block_table", s));
         MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, s));
         for (int t = 0; t < r.T; ++t) {
             MMT_TRY(decode_step_fp32(e, r, n0, Nw, Bmw, b, s));
@@ -654,8 +685,9 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
         MMT_TRY(ensure_arena(e, (size_t)B * D * sizeof(float) + 256));
         a.base = e->arena;
         float* avg = d_avg_memory ? d_avg_memory : a.get<float>((size_t)B * D);
+        prof_pre(e, s);
         mean_over_sequence<<<B, 128, 0, s>>>(d_memory, L.S_total, B, avg);
-        MMT_TRY(check_launch(e, "mean_over_sequence"));
+        MMT_TRY(check_launch(e, "mean_over_sequence", s));
         if (d_fingerprint) {
             GemmParams p = gemm_params(e->desc.fp_size, D, e->desc.fp_size, 0);
             p.g[0].A = avg; p.g[0].lda = D; p.g[0].W = e->W("fp1.weight"); p.g[0].bias = e->W("fp1.bias"); p.g[0].C = d_fingerprint; p.g[0].M = B;
@@ -721,8 +753,10 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
     sp.seq_index_base = seq_index_base;
     sp.tokens = d_token; sp.probs = d_prob; sp.logits = d_logits_out;
     sp.advance = 0;
-    sample_tokens<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(sp);
-    return check_launch(e, "sample_tokens");
+    cudaStream_t cs = (cudaStream_t)stream;
+    prof_pre(e, cs);
+    sample_tokens<<<(unsigned)((N + 7) / 8), 256, 0, cs>>>(sp);
+    return check_launch(e, "sample_tokens", cs);
 }
 
 int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const float* d_bias, float* d_C,
@@ -738,5 +772,40 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
 }
 
 int64_t mmt_launch_count(const mmt_engine* e) { return e ? e->launches : 0; }
+
+int32_t mmt_profile_enable(mmt_engine* e, int32_t on) {
+    if (!e) MMT_FAIL("null engine");
+    for (auto& r : e->prof_records) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof_records.clear();
+    e->profiling = on != 0;
+    return 0;
+}
+
+int32_t mmt_profile_report(mmt_engine* e, char* buf, int64_t buf_len) {
+    if (!e || !buf || buf_len < 2) MMT_FAIL("bad profile buffer");
+    MMT_CUDA(cudaSetDevice(e->device));
+    MMT_CUDA(cudaDeviceSynchronize());
+    struct Agg { int64_t n = 0; double ms = 0, work = 0; };
+    std::vector<std::pair<std::string, Agg>> agg;
+    for (auto& r : e->prof_records) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        size_t i = 0;
+        for (; i < agg.size(); ++i) if (agg[i].first == r.name) break;
+        if (i == agg.size()) agg.push_back({r.name, Agg()});
+        agg[i].second.n++; agg[i].second.ms += ms; agg[i].second.work += r.work;
+    }
+    std::string out = "{";
+    for (size_t i = 0; i < agg.size(); ++i) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e}", i ? ", " : "",
+                 agg[i].first.c_str(), (long long)agg[i].second.n, agg[i].second.ms, agg[i].second.work);
+        out += tmp;
+    }
+    out += "}";
+    if ((int64_t)out.size() + 1 > buf_len) MMT_FAIL("profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
 
 }  // extern "C"

@@ -115,6 +115,11 @@ struct mmt_engine {
     size_t arena_bytes = 0;
     int64_t launches = 0;
     int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)
+    // per-kernel-class device timing (mmt_profile_enable / mmt_profile_report)
+    struct ProfRecord { const char* name; cudaEvent_t a, b; double work; };
+    bool profiling = false;
+    std::pair<cudaEvent_t, cudaEvent_t> prof_open{nullptr, nullptr};
+    std::vector<ProfRecord> prof_records;
 
     const float* W(const std::string& name) const { return w32 + reg.slots.at(reg.index.at(name)).off; }
     const __nv_bfloat16* Wb(const float* p) const { return w16 + (p - w32); }

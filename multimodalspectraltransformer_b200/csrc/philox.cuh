@@ -66,7 +66,8 @@ __device__ __forceinline__ float torch_exponential_at(const RngGeom& g, int64_t 
     // _curand_uniform: (0,1]
     float u = x * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f);
     const float eps = 1.1920928955078125e-07f;  // numeric_limits<float>::epsilon()
-    float lg = (u >= 1.0f - eps / 2.0f) ? (-eps / 2.0f) : logf(u);
+    // at::log on device is the fast __logf (ATen/NumericUtils.h:150-160): lg2.approx * ln2
+    float lg = (u >= 1.0f - eps / 2.0f) ? (-eps / 2.0f) : __logf(u);
     return -1.0f / 1.0f * lg;
 }
 

@@ -79,6 +79,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.L.mmt_launch_count(self.h))
 
+    def profile(self, on: bool):
+        _lib.check(self.L.mmt_profile_enable(self.h, int(on)))
+
+    def profile_report(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(self.L.mmt_profile_report(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def memory_len(self, training_mode: str) -> int:
         return int(self.L.mmt_memory_len(C.byref(self.desc), _lib.mode_bits(training_mode)))
 

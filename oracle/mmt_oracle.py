@@ -31,6 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 D = 128
+FUSED_SDPA = True   # False: spelled-out softmax(QK^T/sqrt(dh)+bias)V, same math (tests check both)
 MODALITIES = ("1H", "13C", "HSQC", "COSY", "IR")
 _EMBED_KEYS = {
     "1H": "linear_spec_embedding_1H.point_embedding_layer_1H.fc_H",
@@ -111,11 +112,17 @@ def _mha(P, prefix, nhead, x_q, x_kv, attn_bias):
     q = q.reshape(Tq, B, nhead, dh).permute(1, 2, 0, 3)
     k = k.reshape(Tk, B, nhead, dh).permute(1, 2, 0, 3)
     v = v.reshape(Tk, B, nhead, dh).permute(1, 2, 0, 3)
-    s = torch.matmul(q, k.transpose(-1, -2)) * (1.0 / math.sqrt(dh))
     if attn_bias is not None:
-        s = s + attn_bias
-    p = torch.softmax(s, dim=-1)
-    o = torch.matmul(p, v).permute(2, 0, 1, 3).reshape(Tq, B, D)
+        attn_bias = attn_bias.expand(B, nhead, Tq, Tk) if attn_bias.dim() == 4 else attn_bias
+    if FUSED_SDPA:
+        # what the reference executes: torch's fused scaled_dot_product_attention (float additive mask)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_bias)
+    else:
+        s = torch.matmul(q, k.transpose(-1, -2)) * (1.0 / math.sqrt(dh))
+        if attn_bias is not None:
+            s = s + attn_bias
+        o = torch.matmul(torch.softmax(s, dim=-1), v)
+    o = o.permute(2, 0, 1, 3).reshape(Tq, B, D)
     return F.linear(o, P[f"{prefix}.out_proj.weight"], P[f"{prefix}.out_proj.bias"])
 
 
@@ -325,7 +332,9 @@ def cuda_exponential_like(numel, seed, offset, sm_count=148, max_threads_per_sm=
     """What ``torch.empty(numel, device='cuda').exponential_(1)`` writes for Philox
     state (seed, offset): torch DistributionTemplates.h distribution_nullary_kernel
     (block 256, grid capped at SMs*(maxThreadsPerSM/256), unroll 4, curand_uniform4,
-    transform -log(u) with the u~1 guard of TransformationHelper.h).  Returns
+    transform -log(u) with the u~1 guard of TransformationHelper.h).  The device
+    evaluates the log with the fast __logf (ATen/NumericUtils.h:150-160); numpy's log
+    is correctly rounded, so values agree to a few ulp, not bit for bit.  Returns
     (float32[numel], counter_offset_increment)."""
     import numpy as np
     block = 256
