@@ -2,6 +2,7 @@
 // drivers that sequence the kernels for encode / decode.
 #include "engine.cuh"
 #include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -92,6 +93,73 @@ static int launch_ln(mmt_engine* e, LnParams& p, int ngroups, int maxM, cudaStre
 }
 
 // ---------------------------------------------------------------------------
+// tcgen05 GEMM launch (bf16 operands): tensor maps are encoded on the host per call
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_encode_tiled = nullptr;
+
+static int tc_init(mmt_engine* e) {
+    if (e->tc_ready) return 0;
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MMT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) MMT_FAIL("cuTensorMapEncodeTiled not available from the driver");
+        g_encode_tiled = (PFN_tmapEncodeTiled)fn;
+    }
+    const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES + 1024;
+    MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    e->tc_ready = true;
+    return 0;
+}
+
+// [rows, cols] bf16 matrix, `ld` elements between rows; box = 64 (K) x 128 (rows), 128-byte swizzle
+static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, int64_t rows, int64_t cols, int64_t ld) {
+    if (((uintptr_t)ptr & 15) || (ld * 2) % 16) MMT_FAIL("tensor map: operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) MMT_FAIL("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+static TcGemmParams tc_params(int M, int N, int K) {
+    TcGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.splits = 1; p.eps = 1e-5f;
+    p.S_in = M > 0 ? M : 1; p.stride_b = 0; p.stride_s = 1; p.off = 0;
+    return p;
+}
+
+// A [M,K] bf16 (row pitch lda), W [N,K] bf16 (dense); the rest of `p` is filled by the caller
+static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int epi, cudaStream_t s) {
+    if (p.M <= 0) return 0;
+    MMT_TRY(tc_init(e));
+    if (p.K % TC_BK || p.N % 4) MMT_FAIL("tcgen05 GEMM needs K % 64 == 0 and N % 4 == 0");
+    if (epi == TC_EPI_LN && (p.N != D || p.splits != 1)) MMT_FAIL("LayerNorm epilogue needs N == 128 and no split-K");
+    const int kb_total = p.K / TC_BK;
+    if (p.splits < 1) p.splits = 1;
+    if (p.splits > kb_total) p.splits = kb_total;
+    const int kb_per = (kb_total + p.splits - 1) / p.splits;
+    p.splits = (kb_total + kb_per - 1) / kb_per;          // no empty split
+    p.stages = std::min(kb_per, kb_per > 2 ? 3 : 2);
+    MMT_TRY(make_tmap(&p.tmA, A, p.M, p.K, lda));
+    MMT_TRY(make_tmap(&p.tmW, W, p.N, p.K, p.K));
+    const size_t smem = (size_t)std::max(p.stages * TC_STAGE_BYTES, TC_STAGING_BYTES) + 1024;
+    dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
+    prof_pre(e, s);
+    if (epi == TC_EPI_LN) gemm_bf16_tc<TC_EPI_LN><<<grid, TC_THREADS, smem, s>>>(p);
+    else gemm_bf16_tc<TC_EPI_STORE><<<grid, TC_THREADS, smem, s>>>(p);
+    return check_launch(e, epi == TC_EPI_LN ? "gemm_bf16_tc_ln" : "gemm_bf16_tc", s, 2.0 * p.M * p.N * p.K);
+}
+
+// ---------------------------------------------------------------------------
 // encoder
 // ---------------------------------------------------------------------------
 struct ModeLayout {
@@ -145,9 +213,11 @@ struct EncBuffers {
     float* ir_emb;
     float* QKV; float* ATT; float* PART; float* H;
     float* key_bias; uint8_t* pad_mask;   // chunk-local when the caller passed NULL
+    // bf16 operand copies (tensor-core mode)
+    __nv_bfloat16* X16[5]; __nv_bfloat16* Xc16; __nv_bfloat16* ATT16; __nv_bfloat16* H16;
 };
 
-static void plan_encoder(Arena& a, const ModeLayout& L, int Bc, int d_ff, EncBuffers& b, bool need_kb, bool need_pm) {
+static void plan_encoder(Arena& a, const ModeLayout& L, int Bc, int d_ff, EncBuffers& b, bool need_kb, bool need_pm, bool bf16) {
     int64_t rows_mod = 0;
     for (int m = 0; m < 5; ++m) {
         int64_t rows = L.present[m] ? (int64_t)Bc * L.S_m[m] : 0;
@@ -164,11 +234,21 @@ static void plan_encoder(Arena& a, const ModeLayout& L, int Bc, int d_ff, EncBuf
     b.nk_c = a.get<int>(Bc);
     b.ir_emb = a.get<float>((int64_t)Bc * D);
     b.QKV = a.get<float>(rmax * 3 * D);
-    b.ATT = a.get<float>(rmax * D);
-    b.PART = a.get<float>(rmax * D);
-    b.H = a.get<float>(rmax * d_ff);
     b.key_bias = need_kb ? a.get<float>(R) : nullptr;
     b.pad_mask = need_pm ? a.get<uint8_t>(R) : nullptr;
+    if (!bf16) {
+        b.ATT = a.get<float>(rmax * D);
+        b.PART = a.get<float>(rmax * D);
+        b.H = a.get<float>(rmax * d_ff);
+        for (int m = 0; m < 5; ++m) b.X16[m] = nullptr;
+        b.Xc16 = b.ATT16 = b.H16 = nullptr;
+    } else {
+        b.ATT = b.PART = b.H = nullptr;
+        for (int m = 0; m < 5; ++m) b.X16[m] = a.get<__nv_bfloat16>((L.present[m] ? (int64_t)Bc * L.S_m[m] : 0) * D);
+        b.Xc16 = a.get<__nv_bfloat16>(R * D);
+        b.ATT16 = a.get<__nv_bfloat16>(rmax * D);
+        b.H16 = a.get<__nv_bfloat16>(rmax * d_ff);
+    }
 }
 
 // One post-norm encoder layer over `ng` independent groups (models_MMT_v15_4.py:510-533).
@@ -177,6 +257,8 @@ struct EncGroupRun {
     const LayerW* w; float* qkv; float* att; float* part; float* h;
     // destination of the layer output (defaults to X in place)
     float* out; int64_t stride_b, stride_s, off;
+    // tensor-core mode: bf16 copies of X / attention output / FFN hidden, bf16 copy of `out`
+    __nv_bfloat16 *x16, *att16, *h16, *out16;
 };
 
 static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
@@ -247,17 +329,77 @@ static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
     return 0;
 }
 
+// The same layer with every projection on the tensor cores (bf16 operands, fp32 accumulate);
+// residual stream, LayerNorm statistics and the attention softmax stay fp32.
+static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
+    int maxS = 0;
+    for (int i = 0; i < ng; ++i) maxS = std::max(maxS, gr[i].S);
+    const int dh = D / heads;
+    for (int i = 0; i < ng; ++i) {   // QKV projection -> fp32 (the attention kernel's softmax input)
+        TcGemmParams p = tc_params(gr[i].rows, 3 * D, D);
+        p.bias = gr[i].w->in_b; p.out_f32 = gr[i].qkv; p.ld_f32 = 3 * D;
+        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->in_w), TC_EPI_STORE, s));
+    }
+    {
+        AttnParams p;
+        memset(&p, 0, sizeof(p));
+        p.scale = 1.0f / sqrtf((float)dh);
+        for (int i = 0; i < ng; ++i) { p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = nullptr; p.g[i].out16 = gr[i].att16; p.g[i].S = gr[i].S; }
+        dim3 grid(heads, Bc, ng);
+        size_t smem = (size_t)maxS * (2 * dh + 1) * sizeof(float);
+        int threads = maxS > 256 ? 256 : 128;
+        if (dh == 8) {
+            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_pre(e, s);
+            attn_encoder_f32<8><<<grid, threads, smem, s>>>(p);
+        } else if (dh == 32) {
+            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_pre(e, s);
+            attn_encoder_f32<32><<<grid, threads, smem, s>>>(p);
+        } else if (dh == 16) {
+            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prof_pre(e, s);
+            attn_encoder_f32<16><<<grid, threads, smem, s>>>(p);
+        } else MMT_FAIL("unsupported head dim " + std::to_string(dh));
+        MMT_TRY(check_launch(e, "attn_encoder_f32", s));
+    }
+    for (int i = 0; i < ng; ++i) {   // out-proj + residual + LN1, in place on X (fp32) and X16
+        TcGemmParams p = tc_params(gr[i].rows, D, D);
+        p.bias = gr[i].w->out_b; p.res = gr[i].X; p.gamma = gr[i].w->n1_w; p.beta = gr[i].w->n1_b;
+        p.out_f32 = gr[i].X; p.ld_f32 = D; p.out_b16 = gr[i].x16; p.ld_b16 = D;
+        MMT_TRY(launch_tc(e, p, gr[i].att16, D, e->Wb(gr[i].w->out_w), TC_EPI_LN, s));
+    }
+    for (int i = 0; i < ng; ++i) {   // FFN1 + ReLU -> bf16 hidden
+        TcGemmParams p = tc_params(gr[i].rows, d_ff, D);
+        p.bias = gr[i].w->l1_b; p.act = 1; p.out_b16 = gr[i].h16; p.ld_b16 = d_ff;
+        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), TC_EPI_STORE, s));
+    }
+    for (int i = 0; i < ng; ++i) {   // FFN2 + residual + LN2
+        TcGemmParams p = tc_params(gr[i].rows, D, d_ff);
+        p.bias = gr[i].w->l2_b; p.res = gr[i].X; p.gamma = gr[i].w->n2_w; p.beta = gr[i].w->n2_b;
+        if (gr[i].out || gr[i].out16) {
+            p.out_f32 = gr[i].out; p.out_b16 = gr[i].out16;
+            p.S_in = gr[i].S; p.stride_b = gr[i].stride_b; p.stride_s = gr[i].stride_s; p.off = gr[i].off;
+        } else {
+            p.out_f32 = gr[i].X; p.out_b16 = gr[i].x16;
+        }
+        p.ld_f32 = D; p.ld_b16 = D;
+        MMT_TRY(launch_tc(e, p, gr[i].h16, d_ff, e->Wb(gr[i].w->l2_w), TC_EPI_LN, s));
+    }
+    return 0;
+}
+
 static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, int B_total, uint32_t mode, const ModeLayout& L,
-                        float* d_memory, float* d_embedding_src, float* d_key_bias, uint8_t* d_pad_mask, cudaStream_t s) {
+                        float* d_memory, float* d_embedding_src, float* d_key_bias, uint8_t* d_pad_mask, bool bf16, cudaStream_t s) {
     const mmt_model_desc& d = e->desc;
     const int P = d.pad_points;
     Arena a;
     EncBuffers b;
     a.plan = true;
-    plan_encoder(a, L, Bc, d.d_ff, b, d_key_bias == nullptr, d_pad_mask == nullptr);
+    plan_encoder(a, L, Bc, d.d_ff, b, d_key_bias == nullptr, d_pad_mask == nullptr, bf16);
     MMT_TRY(ensure_arena(e, a.off));
     a.plan = false; a.base = e->arena; a.cap = e->arena_bytes; a.off = 0;
-    plan_encoder(a, L, Bc, d.d_ff, b, d_key_bias == nullptr, d_pad_mask == nullptr);
+    plan_encoder(a, L, Bc, d.d_ff, b, d_key_bias == nullptr, d_pad_mask == nullptr, bf16);
     float* key_bias = d_key_bias ? d_key_bias + (int64_t)b0 * L.S_total : b.key_bias;
     uint8_t* pad_mask = d_pad_mask ? d_pad_mask + (int64_t)b0 * L.S_total : b.pad_mask;
 
@@ -324,6 +466,17 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
         build_key_index<<<dim3(Bc, ng), 32, 0, s>>>(p);
         MMT_TRY(check_launch(e, "build_key_index", s));
     }
+    if (bf16) {   // bf16 operand copies of the embedded tokens; blank-modality rows of the concatenated memory are zero
+        bool any_blank = false;
+        for (int m = 0; m < 5; ++m) {
+            if (!L.present[m]) { any_blank = true; continue; }
+            const int64_t rows = (int64_t)Bc * L.S_m[m];
+            prof_pre(e, s);
+            pack_rows_bf16<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(b.X[m], nullptr, D, rows, b.X16[m]);
+            MMT_TRY(check_launch(e, "pack_rows_bf16", s));
+        }
+        if (any_blank) MMT_CUDA(cudaMemsetAsync(b.Xc16, 0, (size_t)Bc * L.S_total * D * sizeof(__nv_bfloat16), s));
+    }
     // five modality encoders, batched as groups of one launch
     {
         EncGroupRun gr[5];
@@ -334,7 +487,9 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
             EncGroupRun& g = gr[ng];
             memset(&g, 0, sizeof(g));
             g.X = b.X[m]; g.rows = Bc * L.S_m[m]; g.S = L.S_m[m]; g.kbias = b.kb[m]; g.kidx = b.kidx[m]; g.nk = b.nk[m];
-            g.qkv = b.QKV + row_off * 3 * D; g.att = b.ATT + row_off * D; g.part = b.PART + row_off * D; g.h = b.H + row_off * d.d_ff;
+            g.qkv = b.QKV + row_off * 3 * D;
+            if (bf16) { g.x16 = b.X16[m]; g.att16 = b.ATT16 + row_off * D; g.h16 = b.H16 + row_off * d.d_ff; }
+            else { g.att = b.ATT + row_off * D; g.part = b.PART + row_off * D; g.h = b.H + row_off * d.d_ff; }
             row_off += g.rows;
             ++ng;
         }
@@ -344,11 +499,12 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
                 if (!L.present[m]) continue;
                 gr[gi].w = &e->enc[m][l];
                 if (l == d.n_enc_layers - 1) {   // last layer writes into the concatenated memory [Bc][S_total][D]
-                    gr[gi].out = b.Xc; gr[gi].stride_b = L.S_total; gr[gi].stride_s = 1; gr[gi].off = L.off[m];
+                    gr[gi].out = b.Xc; gr[gi].out16 = b.Xc16; gr[gi].stride_b = L.S_total; gr[gi].stride_s = 1; gr[gi].off = L.off[m];
                 }
                 ++gi;
             }
-            MMT_TRY(encoder_layer_fp32(e, gr, ng, Bc, d.n_heads, d.d_ff, s));
+            if (bf16) MMT_TRY(encoder_layer_bf16(e, gr, ng, Bc, d.n_heads, d.d_ff, s));
+            else MMT_TRY(encoder_layer_fp32(e, gr, ng, Bc, d.n_heads, d.d_ff, s));
         }
     }
     // encoder_cross over the concatenated memory (models_MMT_v15_4.py:941-944)
@@ -357,10 +513,12 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
         memset(&g, 0, sizeof(g));
         g.X = b.Xc; g.rows = Bc * L.S_total; g.S = L.S_total; g.kbias = key_bias; g.kidx = b.kidx_c; g.nk = b.nk_c;
         g.qkv = b.QKV; g.att = b.ATT; g.part = b.PART; g.h = b.H;
+        g.x16 = b.Xc16; g.att16 = b.ATT16; g.h16 = b.H16;
         for (int l = 0; l < d.n_enc_layers; ++l) {
             g.w = &e->enc[5][l];
-            if (l == d.n_enc_layers - 1) { g.out = d_memory; g.stride_b = 1; g.stride_s = B_total; g.off = b0; }   // (S,B,D)
-            MMT_TRY(encoder_layer_fp32(e, &g, 1, Bc, d.n_heads_cross, d.d_ff, s));
+            if (l == d.n_enc_layers - 1) { g.out = d_memory; g.out16 = nullptr; g.stride_b = 1; g.stride_s = B_total; g.off = b0; }   // (S,B,D)
+            if (bf16) MMT_TRY(encoder_layer_bf16(e, &g, 1, Bc, d.n_heads_cross, d.d_ff, s));
+            else MMT_TRY(encoder_layer_fp32(e, &g, 1, Bc, d.n_heads_cross, d.d_ff, s));
         }
     }
     return 0;
@@ -375,10 +533,12 @@ struct DecBuffers {
     float* cross_kv;
     int *nk, *row_start; int64_t* row_off; float* kbias_c;
     int* ctl;   // [0] step, [1] done_ctas, [8..8+max_len) nonpad counts
+    // bf16 operand copies (tensor-core mode)
+    __nv_bfloat16 *x16, *att16, *h16, *mem16;
 };
 constexpr int MAX_SPLITS = 16;
 
-static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b) {
+static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b, bool bf16) {
     const int L = d.n_dec_layers;
     const int pps = (max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
     b.x = a.get<float>(Nw * D);
@@ -396,6 +556,13 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     b.row_off = a.get<int64_t>(R);
     b.kbias_c = a.get<float>(R);
     b.ctl = a.get<int>(8 + 256);
+    b.x16 = b.att16 = b.h16 = b.mem16 = nullptr;
+    if (bf16) {
+        b.x16 = a.get<__nv_bfloat16>(Nw * D);
+        b.att16 = a.get<__nv_bfloat16>(Nw * D);
+        b.h16 = a.get<__nv_bfloat16>(Nw * d.d_ff);
+        b.mem16 = a.get<__nv_bfloat16>(R * D);
+    }
 }
 
 __global__ void init_block_table(int* bt, int64_t n_pages) {
@@ -413,7 +580,7 @@ struct DecodeRun {
 
 // Projects the memory of one wave to per-layer cross-attention K/V (head-major) once;
 // the reference redoes this projection on every step (validate_generate_MMT_v15_4.py:751).
-static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, int Bmw, DecBuffers& b, cudaStream_t s) {
+static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, int Bmw, DecBuffers& b, bool bf16, cudaStream_t s) {
     const mmt_model_desc& d = e->desc;
     MemIndexParams mp;
     mp.key_bias = a.d_key_bias + (int64_t)b0 * a.S; mp.S = a.S; mp.Bm = Bmw;
@@ -424,6 +591,19 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
     MMT_TRY(check_launch(e, "build_memory_index", s));
     const int64_t R = (int64_t)Bmw * a.S;
     const int dh = D / d.n_heads;
+    if (bf16) {   // gather the un-masked memory rows into a dense bf16 operand, then one tcgen05 GEMM per layer
+        prof_pre(e, s);
+        pack_rows_bf16<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(a.d_memory + (int64_t)b0 * a.stride_b, b.row_off, 0, R, b.mem16);
+        MMT_TRY(check_launch(e, "pack_rows_bf16", s));
+        for (int l = 0; l < d.n_dec_layers; ++l) {
+            TcGemmParams p = tc_params((int)R, 2 * D, D);
+            p.bias = e->dec[l].ca_in_b + D;
+            p.out_f32 = b.cross_kv + (size_t)l * 2 * R * D;
+            p.head_major = 1; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
+            MMT_TRY(launch_tc(e, p, b.mem16, D, e->Wb(e->dec[l].ca_in_w + (int64_t)D * D), TC_EPI_STORE, s));
+        }
+        return 0;
+    }
     for (int l = 0; l < d.n_dec_layers; ++l) {
         GemmParams p = gemm_params(2 * D, D, 0, 0);
         p.g[0].A = a.d_memory + (int64_t)b0 * a.stride_b; p.g[0].a_row_off = b.row_off; p.g[0].lda = 0;
@@ -436,7 +616,7 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
     return 0;
 }
 
-static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw, int Bmw, DecBuffers& b, cudaStream_t s) {
+static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw, int Bmw, DecBuffers& b, bool bf16, cudaStream_t s) {
     const mmt_model_desc& d = e->desc;
     const mmt_decode_args& a = *r.a;
     const int H = d.n_heads, dh = D / H;
@@ -448,16 +628,17 @@ static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64
     const int M = (int)Nw;
 
     prof_pre(e, s);
-    if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, nullptr);
-    else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, nullptr);
+    if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+    else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
     MMT_TRY(check_launch(e, "decode_embed", s));
 
+    // x = LN(x + bias + sum_s part[s]) (separate kernel; fp32 mode and split-K FFN2)
     auto ln = [&](const float* part, int splits, const float* bias, const float* gamma, const float* beta) -> int {
         LnParams q;
         memset(&q, 0, sizeof(q));
         q.splits = splits; q.part_stride = Nw * D; q.eps = 1e-5f;
         LnGroup& g = q.g[0];
-        g.part = part; g.bias = bias; g.res = b.x; g.gamma = gamma; g.beta = beta; g.out = b.x; g.M = M;
+        g.part = part; g.bias = bias; g.res = b.x; g.gamma = gamma; g.beta = beta; g.out = b.x; g.out_bf16 = b.x16; g.M = M;
         g.S_in = M; g.stride_b = 0; g.stride_s = 1; g.off = 0;
         return launch_ln(e, q, 1, M, s);
     };
@@ -467,28 +648,59 @@ static int decode_step_fp32(mmt_engine* e, const DecodeRun& r, int64_t n0, int64
         p.splits = splits; p.part_stride = Nw * D;
         return launch_gemm(e, p, 1, M, s);
     };
+    // tensor-core variants: plain projection (fp32 or bf16 out) and projection + residual + LN in place on x / x16
+    auto tc = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, float* C32, __nv_bfloat16* C16, int N, int K, int act, int splits) -> int {
+        TcGemmParams p = tc_params(M, N, K);
+        p.bias = bias; p.act = act; p.out_f32 = C32; p.ld_f32 = N; p.out_b16 = C16; p.ld_b16 = N;
+        p.splits = splits; p.part_stride = Nw * D;
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s);
+    };
+    auto tc_ln = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, int K, const float* gamma, const float* beta) -> int {
+        TcGemmParams p = tc_params(M, D, K);
+        p.bias = bias; p.res = b.x; p.gamma = gamma; p.beta = beta;
+        p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s);
+    };
     const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
+    if (dh != 8) MMT_FAIL("decoder head dim must be 8");
     for (int l = 0; l < d.n_dec_layers; ++l) {
         const LayerW& w = e->dec[l];
-        MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
         float* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D;
+        const float* ckv = b.cross_kv + (size_t)l * 2 * R * D;
+        if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
+        else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
         prof_pre(e, s);
-        if (dh == 8) decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, b.att);
-        else MMT_FAIL("decoder head dim must be 8");
+        decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, bf16 ? nullptr : b.att, b.att16);
         MMT_TRY(check_launch(e, "decode_self_attention", s));
-        MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
-        MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
-        MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
+        if (bf16) {
+            MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
+            MMT_TRY(tc(b.x16, D, w.ca_in_w, w.ca_in_b, b.qc, nullptr, D, D, 0, 1));
+        } else {
+            MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
+            MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
+            MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
+        }
         prof_pre(e, s);
-        decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, b.cross_kv + (size_t)l * 2 * R * D, R, b.nk, b.row_start, b.kbias_c,
-                                                             a.n_cand, Nw, H, scale, b.att);
+        decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, ckv, R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, bf16 ? nullptr : b.att, b.att16);
         MMT_TRY(check_launch(e, "decode_cross_attention", s));
-        MMT_TRY(gemm(b.att, D, w.ca_out_w, nullptr, b.part, D, D, 0, 1));
-        MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
-        MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
-        int splits = pick_splits(M, D, d.d_ff);
-        MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, splits));
-        MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
+        if (bf16) {
+            MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
+            MMT_TRY(tc(b.x16, D, w.l1_w, w.l1_b, nullptr, b.h16, d.d_ff, D, 1, 1));
+            if (M >= 2048) {
+                MMT_TRY(tc_ln(b.h16, d.d_ff, w.l2_w, w.l2_b, d.d_ff, w.n3_w, w.n3_b));
+            } else {   // few rows: split K = 2048 over the grid, reduce the partials in the LayerNorm kernel
+                const int splits = MAX_SPLITS;
+                MMT_TRY(tc(b.h16, d.d_ff, w.l2_w, nullptr, b.part, nullptr, D, d.d_ff, 0, splits));
+                MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
+            }
+        } else {
+            MMT_TRY(gemm(b.att, D, w.ca_out_w, nullptr, b.part, D, D, 0, 1));
+            MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
+            MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
+            int splits = pick_splits(M, D, d.d_ff);
+            MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, splits));
+            MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
+        }
     }
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -524,13 +736,15 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     const int64_t max_wave_seqs = 16384;
     int Bm_wave = (int)std::max<int64_t>(1, std::min<int64_t>(a.Bm, max_wave_seqs / a.n_cand));
     const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
+    if (a.precision != MMT_PREC_FP32 && a.precision != MMT_PREC_BF16) MMT_FAIL("decode: bad precision");
+    const bool bf16 = a.precision == MMT_PREC_BF16;
     Arena ar;
     DecBuffers b;
     ar.plan = true;
-    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b);
+    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b, bf16);
     MMT_TRY(ensure_arena(e, ar.off));
     ar.plan = false; ar.base = e->arena; ar.cap = e->arena_bytes; ar.off = 0;
-    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b);
+    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b, bf16);
     const int pps = (a.max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
     const bool early = (r.mode == 0) && a.stop_on_all_pad && n_waves == 1;
     int steps_done = r.T;
@@ -543,9 +757,9 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         prof_pre(e, s);
         init_block_table<<<(unsigned)((Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, Nw * pps);
         MMT_TRY(check_launch(e, "init_block_table", s));
-        MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, s));
+        MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, bf16, s));
         for (int t = 0; t < r.T; ++t) {
-            MMT_TRY(decode_step_fp32(e, r, n0, Nw, Bmw, b, s));
+            MMT_TRY(decode_step(e, r, n0, Nw, Bmw, b, bf16, s));
             if (early && ((t + 1) % 16 == 0 || t + 1 == r.T) ) {
                 MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
                 MMT_CUDA(cudaStreamSynchronize(s));
@@ -677,7 +891,7 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
     const int chunk = 256;
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int Bc = std::min(chunk, B - b0);
-        MMT_TRY(encode_chunk(e, *in, b0, Bc, B, mode_bits, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, s));
+        MMT_TRY(encode_chunk(e, *in, b0, Bc, B, mode_bits, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, precision == MMT_PREC_BF16, s));
     }
     if (d_fingerprint || d_avg_memory) {
         Arena a;
@@ -765,10 +979,24 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
     if (K % 4) MMT_FAIL("K must be a multiple of 4");
     if (M > 0x7fffffff) MMT_FAIL("M too large");
     MMT_CUDA(cudaSetDevice(e->device));
-    if (precision != MMT_PREC_FP32) MMT_FAIL("mmt_linear: bf16 tcgen05 path not built in this revision");
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (precision == MMT_PREC_BF16) {   // convert the operands to bf16 in the workspace, then one tcgen05 GEMM
+        if (K % TC_BK || N % 4) MMT_FAIL("mmt_linear bf16: K must be a multiple of 64 and N of 4");
+        const size_t nA = (size_t)M * K, nW = (size_t)N * K;
+        MMT_TRY(ensure_arena(e, (nA + nW) * sizeof(__nv_bfloat16) + 512));
+        __nv_bfloat16* A16 = reinterpret_cast<__nv_bfloat16*>(e->arena);
+        __nv_bfloat16* W16 = reinterpret_cast<__nv_bfloat16*>(e->arena + ((nA * 2 + 255) & ~size_t(255)));
+        f32_to_bf16<<<(unsigned)((nA + 255) / 256), 256, 0, cs>>>(d_A, (int64_t)nA, A16);
+        f32_to_bf16<<<(unsigned)((nW + 255) / 256), 256, 0, cs>>>(d_W, (int64_t)nW, W16);
+        MMT_CUDA(cudaGetLastError());
+        TcGemmParams p = tc_params((int)M, N, K);
+        p.bias = d_bias; p.act = act; p.out_f32 = d_C; p.ld_f32 = N;
+        return launch_tc(e, p, A16, K, W16, TC_EPI_STORE, cs);
+    }
+    if (precision != MMT_PREC_FP32) MMT_FAIL("bad precision");
     GemmParams p = gemm_params(N, K, N, act);
     p.g[0].A = d_A; p.g[0].lda = K; p.g[0].W = d_W; p.g[0].bias = d_bias; p.g[0].C = d_C; p.g[0].M = (int)M;
-    return launch_gemm(e, p, 1, (int)M, (cudaStream_t)stream);
+    return launch_gemm(e, p, 1, (int)M, cs);
 }
 
 int64_t mmt_launch_count(const mmt_engine* e) { return e ? e->launches : 0; }

@@ -114,6 +114,7 @@ struct mmt_engine {
     char* arena = nullptr;
     size_t arena_bytes = 0;
     int64_t launches = 0;
+    bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)
     int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)
     // per-kernel-class device timing (mmt_profile_enable / mmt_profile_report)
     struct ProfRecord { const char* name; cudaEvent_t a, b; double work; };

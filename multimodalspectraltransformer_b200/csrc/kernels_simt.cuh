@@ -366,7 +366,8 @@ struct AttnGroup {
     const float* kbias;  // [B][S] additive bias per ORIGINAL key index
     const int* kidx;     // [B][S] compacted key indices
     const int* nk;       // [B]
-    float* out;          // [B*S][D]
+    float* out;          // [B*S][D] fp32 (or nullptr)
+    __nv_bfloat16* out16;  // [B*S][D] bf16 operand copy for the tensor-core out-projection (or nullptr)
     int S;
 };
 struct AttnParams { AttnGroup g[GEMM_MAX_GROUPS]; float scale; };
@@ -428,11 +429,22 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
             }
         }
         float inv = 1.0f / l;
-        float* orow = g.out + ((int64_t)b * S + i) * D + h * DH;
+        if (g.out) {
+            float* orow = g.out + ((int64_t)b * S + i) * D + h * DH;
 #pragma unroll
-        for (int d4 = 0; d4 < V4; ++d4)
-            *reinterpret_cast<float4*>(orow + d4 * 4) =
-                make_float4(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv, acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
+            for (int d4 = 0; d4 < V4; ++d4)
+                *reinterpret_cast<float4*>(orow + d4 * 4) =
+                    make_float4(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv, acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
+        }
+        if (g.out16) {
+            __nv_bfloat16* orow = g.out16 + ((int64_t)b * S + i) * D + h * DH;
+#pragma unroll
+            for (int d4 = 0; d4 < V4; ++d4) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
+                *reinterpret_cast<uint2*>(orow + d4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
+        }
     }
 }
 
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(128) decode_embed(const int64_t* tokens, int t
 template <int DH>
 __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, float* kv_pool, const int* block_table,
                                                              int pages_per_seq, int64_t N, int H, float scale,
-                                                             const int* step, float* out) {
+                                                             const int* step, float* out, __nv_bfloat16* out16) {
     const int t = *step;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= N * H) return;
@@ -577,7 +589,8 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, f
         float v = 0.f;
 #pragma unroll
         for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
-        out[n * D + h * DH + lane] = v / l;
+        if (out) out[n * D + h * DH + lane] = v / l;
+        if (out16) out16[n * D + h * DH + lane] = __float2bfloat16_rn(v / l);
     }
 }
 
@@ -586,7 +599,8 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, f
 template <int DH>
 __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in, const float* kv, int64_t rows_total,
                                                               const int* nk, const int* row_start, const float* kbias_c,
-                                                              int n_cand, int64_t N, int H, float scale, float* out) {
+                                                              int n_cand, int64_t N, int H, float scale, float* out,
+                                                              __nv_bfloat16* out16) {
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= N * H) return;
     const int lane = threadIdx.x & 31;
@@ -638,7 +652,8 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
         float v = 0.f;
 #pragma unroll
         for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
-        out[n * D + h * DH + lane] = v / l;
+        if (out) out[n * D + h * DH + lane] = v / l;
+        if (out16) out16[n * D + h * DH + lane] = __float2bfloat16_rn(v / l);
     }
 }
 

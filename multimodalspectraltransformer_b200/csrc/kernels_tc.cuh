@@ -1,0 +1,293 @@
+// bf16 tensor-core kernels of the MMT path for sm_100a: tcgen05.mma with TMEM accumulators,
+// operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), fused
+// epilogues (bias / ReLU / bf16 cast, or bias + residual + LayerNorm over the 128-wide row).
+//
+//   C[M,N] = epi(A[M,K] . W[N,K]^T)      A, W bf16 with K contiguous, fp32 accumulate
+//
+// One CTA = one 128x128 output tile (UMMA 128x128x16, cta_group::1), 6 warps:
+//   warp 0     TMA producer   (one lane): K slabs of 64 elements (=128 B swizzle rows)
+//   warp 1     MMA issuer     (one lane) + TMEM allocation (128 columns)
+//   warps 2-5  epilogue: TMEM -> registers -> padded smem tile -> coalesced global I/O
+// Several CTAs are resident per SM (68 KB smem at K=128), so one tile's epilogue overlaps
+// the TMA/MMA of its neighbours without a persistent scheduler.
+#pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder entry point is fetched at run time)
+
+#include "common.cuh"
+
+namespace mmt {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
+constexpr int TC_SLAB_BYTES = TC_BM * TC_BK * 2;          // 16 KB: one operand slab (128 rows x 128 B)
+constexpr int TC_STAGE_BYTES = 2 * TC_SLAB_BYTES;          // A slab + W slab
+constexpr int TC_LDS = TC_BN + 4;                          // padded fp32 staging row (conflict-free float4)
+constexpr int TC_STAGING_BYTES = TC_BM * TC_LDS * 4;       // 67,584 B
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 4;
+
+enum { TC_EPI_STORE = 0, TC_EPI_LN = 1 };
+
+struct TcGemmParams {
+    CUtensorMap tmA;          // A [M,K] bf16, box {64,128}, SWIZZLE_128B
+    CUtensorMap tmW;          // W [N,K] bf16, box {64,128}, SWIZZLE_128B
+    int M, N, K;
+    int stages;               // smem ring depth (<= TC_MAX_STAGES)
+    int splits;               // split-K over blockIdx.z: raw fp32 partials, no bias / act
+    int64_t part_stride;      // floats between split partials
+    const float* bias;        // [N] or nullptr
+    int act;                  // 0 none, 1 ReLU
+    float* out_f32; int64_t ld_f32;            // optional fp32 output
+    __nv_bfloat16* out_b16; int64_t ld_b16;    // optional bf16 output
+    // head-major fp32 output (cross-attention K/V): C[((c/128)*heads + (c%128)/dh) * hm_rows + r][c % dh]
+    int head_major, hm_heads, hm_dh; int64_t hm_rows;
+    // LayerNorm epilogue (N == 128): out = LN(acc + bias + res[r]) * gamma + beta
+    const float* res; const float* gamma; const float* beta; float eps;
+    // output row map (in rows): (r / S_in) * stride_b + (r % S_in) * stride_s + off
+    int S_in; int64_t stride_b, stride_s, off;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("mmt: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand slab, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).  LBO is unused for swizzled K-major.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+// ------------------------------------------------------------------ the GEMM
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant__ TcGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
+    const int split = blockIdx.z;
+    const int kb_total = p.K / TC_BK;
+    const int kb_per = (kb_total + p.splits - 1) / p.splits;
+    const int kb_begin = split * kb_per;
+    const int kb_end = min(kb_total, kb_begin + kb_per);
+    const int num_kb = kb_end - kb_begin;      // host guarantees >= 1
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmW);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, TC_BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[s], TC_STAGE_BYTES);
+                uint8_t* a = smem + (size_t)s * TC_STAGE_BYTES;
+                tma_load_2d(a, &p.tmA, &full_bar[s], (kb_begin + i) * TC_BK, m0);
+                tma_load_2d(a + TC_SLAB_BYTES, &p.tmW, &full_bar[s], (kb_begin + i) * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(a_addr);
+                const uint64_t bdesc = umma_desc_sw128(a_addr + TC_SLAB_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)   // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);            // smem slot reusable once these MMAs retire
+            }
+            umma_commit(&tmem_full_bar);               // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: 4 warps, warp (id % 4) owns TMEM lanes [32*(id%4), +32)
+        const int q = warp & 3;
+        float* stage = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * TC_LDS;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < TC_BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            float* dst = stage + (size_t)lane * TC_LDS + c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(dst + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        __syncwarp();
+        const int col = n0 + lane * 4;
+        const bool col_ok = col < p.N;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok && p.splits == 1) bias = *reinterpret_cast<const float4*>(p.bias + col);
+        const int rows = min(32, p.M - (m0 + q * 32));
+        if (EPI == TC_EPI_LN) {
+            const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+            const float4 be = *reinterpret_cast<const float4*>(p.beta + col);
+            for (int i0 = 0; i0 < rows; i0 += 4) {
+                float4 rs[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = m0 + q * 32 + i0 + u;
+                    rs[u] = (i0 + u < rows) ? *reinterpret_cast<const float4*>(p.res + (int64_t)r * D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 + u >= rows) break;
+                    const int r = m0 + q * 32 + i0 + u;
+                    float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(i0 + u) * TC_LDS + lane * 4);
+                    v.x += bias.x + rs[u].x; v.y += bias.y + rs[u].y; v.z += bias.z + rs[u].z; v.w += bias.w + rs[u].w;
+                    const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);
+                    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+                    const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
+                    const float rstd = rsqrtf(var + p.eps);
+                    const float4 o = make_float4(dx * rstd * ga.x + be.x, dy * rstd * ga.y + be.y, dz * rstd * ga.z + be.z, dw * rstd * ga.w + be.w);
+                    const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
+                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ld_f32 + col) = o;
+                    if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(o);
+                }
+            }
+        } else {
+            float* out32 = p.out_f32 ? p.out_f32 + (int64_t)split * p.part_stride : nullptr;
+            for (int i = 0; i < rows; ++i) {
+                const int r = m0 + q * 32 + i;
+                float4 v = *reinterpret_cast<const float4*>(stage + (size_t)i * TC_LDS + lane * 4);
+                if (!col_ok) continue;
+                v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+                if (p.act == 1 && p.splits == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (p.head_major) {
+                    const int kv = col / D, cc = col % D;
+                    const int h = cc / p.hm_dh, d = cc % p.hm_dh;
+                    *reinterpret_cast<float4*>(out32 + (((int64_t)kv * p.hm_heads + h) * p.hm_rows + r) * p.hm_dh + d) = v;
+                } else {
+                    const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
+                    if (out32) *reinterpret_cast<float4*>(out32 + orow * p.ld_f32 + col) = v;
+                    if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(v);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TC_BN);
+    }
+}
+
+// fp32 -> bf16 row pack with an optional gather (row r of the source starts at src + row_off[r])
+__global__ void __launch_bounds__(256) pack_rows_bf16(const float* src, const int64_t* row_off, int64_t lds, int64_t rows, __nv_bfloat16* dst) {
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* s = row_off ? src + row_off[r] : src + r * lds;
+    const float4 v = *reinterpret_cast<const float4*>(s + lane * 4);
+    *reinterpret_cast<uint2*>(dst + r * D + lane * 4) = pack_bf16x4(v);
+}
+
+}  // namespace mmt
