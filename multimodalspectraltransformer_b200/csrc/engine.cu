@@ -5,6 +5,7 @@
 #include "kernels_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace mmt {
@@ -109,7 +110,7 @@ static int tc_init(mmt_engine* e) {
         if (!fn || qres != cudaDriverEntryPointSuccess) MMT_FAIL("cuTensorMapEncodeTiled not available from the driver");
         g_encode_tiled = (PFN_tmapEncodeTiled)fn;
     }
-    const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES + 1024;
+    const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES_WSPLIT + 1024;
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     e->tc_ready = true;
@@ -137,8 +138,10 @@ static TcGemmParams tc_params(int M, int N, int K) {
     return p;
 }
 
-// A [M,K] bf16 (row pitch lda), W [N,K] bf16 (dense); the rest of `p` is filled by the caller
-static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int epi, cudaStream_t s) {
+// A [M,K] bf16 (row pitch lda), W [N,K] bf16 (dense), optional low-order weight term Wlo; the
+// rest of `p` is filled by the caller
+static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int epi, cudaStream_t s,
+                     const __nv_bfloat16* Wlo = nullptr) {
     if (p.M <= 0) return 0;
     MMT_TRY(tc_init(e));
     if (p.K % TC_BK || p.N % 4) MMT_FAIL("tcgen05 GEMM needs K % 64 == 0 and N % 4 == 0");
@@ -148,10 +151,12 @@ static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int
     if (p.splits > kb_total) p.splits = kb_total;
     const int kb_per = (kb_total + p.splits - 1) / p.splits;
     p.splits = (kb_total + kb_per - 1) / kb_per;          // no empty split
-    p.stages = std::min(kb_per, kb_per > 2 ? 3 : 2);
+    p.wsplit = Wlo != nullptr;
+    p.stages = std::min(kb_per, (kb_per > 2 && !p.wsplit) ? 3 : 2);
     MMT_TRY(make_tmap(&p.tmA, A, p.M, p.K, lda));
     MMT_TRY(make_tmap(&p.tmW, W, p.N, p.K, p.K));
-    const size_t smem = (size_t)std::max(p.stages * TC_STAGE_BYTES, TC_STAGING_BYTES) + 1024;
+    if (p.wsplit) MMT_TRY(make_tmap(&p.tmW2, Wlo, p.N, p.K, p.K));
+    const size_t smem = (size_t)std::max(p.stages * (p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES), TC_STAGING_BYTES) + 1024;
     dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
     prof_pre(e, s);
     if (epi == TC_EPI_LN) gemm_bf16_tc<TC_EPI_LN><<<grid, TC_THREADS, smem, s>>>(p);
@@ -338,7 +343,7 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
     for (int i = 0; i < ng; ++i) {   // QKV projection -> fp32 (the attention kernel's softmax input)
         TcGemmParams p = tc_params(gr[i].rows, 3 * D, D);
         p.bias = gr[i].w->in_b; p.out_f32 = gr[i].qkv; p.ld_f32 = 3 * D;
-        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->in_w), TC_EPI_STORE, s));
+        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->in_w), TC_EPI_STORE, s, e->Wlo(gr[i].w->in_w)));
     }
     {
         AttnParams p;
@@ -367,12 +372,12 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         TcGemmParams p = tc_params(gr[i].rows, D, D);
         p.bias = gr[i].w->out_b; p.res = gr[i].X; p.gamma = gr[i].w->n1_w; p.beta = gr[i].w->n1_b;
         p.out_f32 = gr[i].X; p.ld_f32 = D; p.out_b16 = gr[i].x16; p.ld_b16 = D;
-        MMT_TRY(launch_tc(e, p, gr[i].att16, D, e->Wb(gr[i].w->out_w), TC_EPI_LN, s));
+        MMT_TRY(launch_tc(e, p, gr[i].att16, D, e->Wb(gr[i].w->out_w), TC_EPI_LN, s, e->Wlo(gr[i].w->out_w)));
     }
     for (int i = 0; i < ng; ++i) {   // FFN1 + ReLU -> bf16 hidden
         TcGemmParams p = tc_params(gr[i].rows, d_ff, D);
         p.bias = gr[i].w->l1_b; p.act = 1; p.out_b16 = gr[i].h16; p.ld_b16 = d_ff;
-        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), TC_EPI_STORE, s));
+        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), TC_EPI_STORE, s, e->Wlo(gr[i].w->l1_w)));
     }
     for (int i = 0; i < ng; ++i) {   // FFN2 + residual + LN2
         TcGemmParams p = tc_params(gr[i].rows, D, d_ff);
@@ -384,7 +389,7 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
             p.out_f32 = gr[i].X; p.out_b16 = gr[i].x16;
         }
         p.ld_f32 = D; p.ld_b16 = D;
-        MMT_TRY(launch_tc(e, p, gr[i].h16, d_ff, e->Wb(gr[i].w->l2_w), TC_EPI_LN, s));
+        MMT_TRY(launch_tc(e, p, gr[i].h16, d_ff, e->Wb(gr[i].w->l2_w), TC_EPI_LN, s, e->Wlo(gr[i].w->l2_w)));
     }
     return 0;
 }
@@ -600,7 +605,7 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
             p.bias = e->dec[l].ca_in_b + D;
             p.out_f32 = b.cross_kv + (size_t)l * 2 * R * D;
             p.head_major = 1; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
-            MMT_TRY(launch_tc(e, p, b.mem16, D, e->Wb(e->dec[l].ca_in_w + (int64_t)D * D), TC_EPI_STORE, s));
+            MMT_TRY(launch_tc(e, p, b.mem16, D, e->Wb(e->dec[l].ca_in_w + (int64_t)D * D), TC_EPI_STORE, s, e->Wlo(e->dec[l].ca_in_w + (int64_t)D * D)));
         }
         return 0;
     }
@@ -653,13 +658,13 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         TcGemmParams p = tc_params(M, N, K);
         p.bias = bias; p.act = act; p.out_f32 = C32; p.ld_f32 = N; p.out_b16 = C16; p.ld_b16 = N;
         p.splits = splits; p.part_stride = Nw * D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s);
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s, e->Wlo(W));
     };
     auto tc_ln = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, int K, const float* gamma, const float* beta) -> int {
         TcGemmParams p = tc_params(M, D, K);
         p.bias = bias; p.res = b.x; p.gamma = gamma; p.beta = beta;
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s);
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W));
     };
     const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
     if (dh != 8) MMT_FAIL("decoder head dim must be 8");
@@ -758,8 +763,30 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         init_block_table<<<(unsigned)((Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, Nw * pps);
         MMT_TRY(check_launch(e, "init_block_table", s));
         MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, bf16, s));
+        // One decode step is the same kernel sequence at every position (the step counter lives on
+        // the device), so it is captured once per wave into a CUDA graph and replayed max_len times.
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches_per_step = 0;
+        if (e->use_graph && !e->profiling) {
+            if (bf16) MMT_TRY(tc_init(e));
+            if (!e->cap_stream) MMT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+            const int64_t l0 = e->launches;
+            MMT_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed));
+            const int rc = decode_step(e, r, n0, Nw, Bmw, b, bf16, e->cap_stream);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+            launches_per_step = e->launches - l0;
+            e->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+            if (ce != cudaSuccess) MMT_FAIL(std::string("decode step capture failed: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) MMT_FAIL(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+        }
+        struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { if (x) cudaGraphExecDestroy(x); } } guard{exec};
         for (int t = 0; t < r.T; ++t) {
-            MMT_TRY(decode_step(e, r, n0, Nw, Bmw, b, bf16, s));
+            if (exec) { MMT_CUDA(cudaGraphLaunch(exec, s)); e->launches += launches_per_step; }
+            else MMT_TRY(decode_step(e, r, n0, Nw, Bmw, b, bf16, s));
             if (early && ((t + 1) % 16 == 0 || t + 1 == r.T) ) {
                 MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
                 MMT_CUDA(cudaStreamSynchronize(s));
@@ -837,12 +864,14 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     mmt_engine* e = new mmt_engine();
     e->desc = *desc; e->device = device; e->sm_count = prop.multiProcessorCount; e->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
     e->reg = build_registry(*desc);
+    if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };
     if (cudaMalloc(&e->w32, n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc weights failed");
     if (cudaMalloc(&e->w16, n_floats * sizeof(__nv_bfloat16)) != cudaSuccess) return fail("cudaMalloc bf16 weights failed");
     if (cudaMemcpy(e->w32, h_weights, n_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return fail("weight H2D copy failed");
-    f32_to_bf16<<<(unsigned)((n_floats + 255) / 256), 256>>>(e->w32, n_floats, e->w16);
+    if (cudaMalloc(&e->w16lo, n_floats * sizeof(__nv_bfloat16)) != cudaSuccess) return fail("cudaMalloc bf16 weights (low term) failed");
+    f32_to_bf16_split<<<(unsigned)((n_floats + 255) / 256), 256>>>(e->w32, n_floats, e->w16, e->w16lo);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(std::string("bf16 weight conversion failed: ") + cudaGetErrorString(cudaGetLastError()));
     if (cudaMallocHost(&e->h_pinned, 1024 * sizeof(int32_t)) != cudaSuccess) return fail("cudaMallocHost failed");
     for (int k = 0; k < 6; ++k) {
@@ -861,8 +890,10 @@ void mmt_destroy(mmt_engine* e) {
     cudaDeviceSynchronize();
     if (e->w32) cudaFree(e->w32);
     if (e->w16) cudaFree(e->w16);
+    if (e->w16lo) cudaFree(e->w16lo);
     if (e->arena) cudaFree(e->arena);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     delete e;
 }
 
@@ -983,15 +1014,17 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
     if (precision == MMT_PREC_BF16) {   // convert the operands to bf16 in the workspace, then one tcgen05 GEMM
         if (K % TC_BK || N % 4) MMT_FAIL("mmt_linear bf16: K must be a multiple of 64 and N of 4");
         const size_t nA = (size_t)M * K, nW = (size_t)N * K;
-        MMT_TRY(ensure_arena(e, (nA + nW) * sizeof(__nv_bfloat16) + 512));
+        const size_t bA = (nA * 2 + 255) & ~size_t(255), bW = (nW * 2 + 255) & ~size_t(255);
+        MMT_TRY(ensure_arena(e, bA + 2 * bW + 512));
         __nv_bfloat16* A16 = reinterpret_cast<__nv_bfloat16*>(e->arena);
-        __nv_bfloat16* W16 = reinterpret_cast<__nv_bfloat16*>(e->arena + ((nA * 2 + 255) & ~size_t(255)));
+        __nv_bfloat16* W16 = reinterpret_cast<__nv_bfloat16*>(e->arena + bA);
+        __nv_bfloat16* W16lo = reinterpret_cast<__nv_bfloat16*>(e->arena + bA + bW);
         f32_to_bf16<<<(unsigned)((nA + 255) / 256), 256, 0, cs>>>(d_A, (int64_t)nA, A16);
-        f32_to_bf16<<<(unsigned)((nW + 255) / 256), 256, 0, cs>>>(d_W, (int64_t)nW, W16);
+        f32_to_bf16_split<<<(unsigned)((nW + 255) / 256), 256, 0, cs>>>(d_W, (int64_t)nW, W16, W16lo);
         MMT_CUDA(cudaGetLastError());
         TcGemmParams p = tc_params((int)M, N, K);
         p.bias = d_bias; p.act = act; p.out_f32 = d_C; p.ld_f32 = N;
-        return launch_tc(e, p, A16, K, W16, TC_EPI_STORE, cs);
+        return launch_tc(e, p, A16, K, W16, TC_EPI_STORE, cs, W16lo);
     }
     if (precision != MMT_PREC_FP32) MMT_FAIL("bad precision");
     GemmParams p = gemm_params(N, K, N, act);

@@ -108,12 +108,15 @@ struct mmt_engine {
     int device = 0, sm_count = 0, max_threads_per_sm = 0;
     mmt::Registry reg;
     float* w32 = nullptr;
-    __nv_bfloat16* w16 = nullptr;
+    __nv_bfloat16* w16 = nullptr;      // bf16(w32)
+    __nv_bfloat16* w16lo = nullptr;    // bf16(w32 - w16): low-order term of the two-term weight split
     std::vector<mmt::LayerW> enc[6];   // 5 modality stacks + cross
     std::vector<mmt::LayerW> dec;
     char* arena = nullptr;
     size_t arena_bytes = 0;
     int64_t launches = 0;
+    bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
+    cudaStream_t cap_stream = nullptr; // capture-only stream (the caller's stream may be the legacy default stream)
     bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)
     int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)
     // per-kernel-class device timing (mmt_profile_enable / mmt_profile_report)
@@ -124,4 +127,5 @@ struct mmt_engine {
 
     const float* W(const std::string& name) const { return w32 + reg.slots.at(reg.index.at(name)).off; }
     const __nv_bfloat16* Wb(const float* p) const { return w16 + (p - w32); }
+    const __nv_bfloat16* Wlo(const float* p) const { return w16lo + (p - w32); }
 };

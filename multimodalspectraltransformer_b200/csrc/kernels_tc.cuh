@@ -4,6 +4,10 @@
 //
 //   C[M,N] = epi(A[M,K] . W[N,K]^T)      A, W bf16 with K contiguous, fp32 accumulate
 //
+// Weights may be given as a two-term bf16 split W ~= W_hi + W_lo (wsplit): the MMA pass runs
+// twice per K slab on the same A slab, which removes the weight-rounding error (the dominant
+// term of the bf16 logit error, DESIGN.md "bf16 numerics") for no extra HBM traffic.
+//
 // One CTA = one 128x128 output tile (UMMA 128x128x16, cta_group::1), 6 warps:
 //   warp 0     TMA producer   (one lane): K slabs of 64 elements (=128 B swizzle rows)
 //   warp 1     MMA issuer     (one lane) + TMEM allocation (128 columns)
@@ -20,6 +24,7 @@ namespace mmt {
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
 constexpr int TC_SLAB_BYTES = TC_BM * TC_BK * 2;          // 16 KB: one operand slab (128 rows x 128 B)
 constexpr int TC_STAGE_BYTES = 2 * TC_SLAB_BYTES;          // A slab + W slab
+constexpr int TC_STAGE_BYTES_WSPLIT = 3 * TC_SLAB_BYTES;   // A slab + W_hi slab + W_lo slab
 constexpr int TC_LDS = TC_BN + 4;                          // padded fp32 staging row (conflict-free float4)
 constexpr int TC_STAGING_BYTES = TC_BM * TC_LDS * 4;       // 67,584 B
 constexpr int TC_THREADS = 192;
@@ -30,6 +35,8 @@ enum { TC_EPI_STORE = 0, TC_EPI_LN = 1 };
 struct TcGemmParams {
     CUtensorMap tmA;          // A [M,K] bf16, box {64,128}, SWIZZLE_128B
     CUtensorMap tmW;          // W [N,K] bf16, box {64,128}, SWIZZLE_128B
+    CUtensorMap tmW2;         // low-order term of the two-term weight split (wsplit): W ~= W_hi + W_lo, both bf16
+    int wsplit;               // 1: accumulate A.W_hi^T + A.W_lo^T (weight rounding error removed; 2x MMAs, same HBM bytes)
     int M, N, K;
     int stages;               // smem ring depth (<= TC_MAX_STAGES)
     int splits;               // split-K over blockIdx.z: raw fp32 partials, no bias / act
@@ -141,6 +148,114 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
     return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
 }
 
+// ------------------------------------------------------------------ shared epilogue pieces
+// The epilogue warps (4 consecutive warps, warp id % 4 = TMEM lane quarter q) first move their 32
+// accumulator rows TMEM -> registers -> a padded fp32 smem tile (thread = row), then walk the rows
+// with lane = 4 consecutive columns so that every global access is a coalesced 512 B row segment.
+// Rows are processed 8 at a time so that the loads and the LayerNorm shuffle chains of
+// independent rows overlap (a single row's chain is ~500 cycles of pure latency).
+constexpr int EPI_ILP = 8;
+
+template <int NCOLS>
+__device__ __forceinline__ void epi_tmem_to_stage(uint32_t tmem_acc, int q, int lane, float* stage) {
+#pragma unroll
+    for (int c = 0; c < NCOLS / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        float* dst = stage + (size_t)lane * TC_LDS + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + 4 * j) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_sum_ilp(float (&s)[EPI_ILP]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < EPI_ILP; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+}
+
+// out[map(r)] = LN(stage[r] + bias + res[r]) * gamma + beta for the warp's 32 rows (N == 128)
+template <class P>
+__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int lane) {
+    const int col = lane * 4;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + col);
+    const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
+    const float4 be = *reinterpret_cast<const float4*>(p.beta + col);
+    const int rows = min(32, p.M - row0);
+    for (int i0 = 0; i0 < rows; i0 += EPI_ILP) {
+        float4 v[EPI_ILP];
+        float s[EPI_ILP];
+#pragma unroll
+        for (int u = 0; u < EPI_ILP; ++u) {
+            const bool ok = i0 + u < rows;
+            const float4 rs = ok ? *reinterpret_cast<const float4*>(p.res + (int64_t)(row0 + i0 + u) * D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = *reinterpret_cast<const float4*>(stage + (size_t)((i0 + u) & 31) * TC_LDS + col);
+            v[u] = make_float4(a.x + bias.x + rs.x, a.y + bias.y + rs.y, a.z + bias.z + rs.z, a.w + bias.w + rs.w);
+            s[u] = v[u].x + v[u].y + v[u].z + v[u].w;
+        }
+        warp_sum_ilp(s);
+#pragma unroll
+        for (int u = 0; u < EPI_ILP; ++u) {
+            const float mean = s[u] * (1.0f / D);
+            v[u].x -= mean; v[u].y -= mean; v[u].z -= mean; v[u].w -= mean;
+            s[u] = v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+        }
+        warp_sum_ilp(s);
+#pragma unroll
+        for (int u = 0; u < EPI_ILP; ++u) {
+            if (i0 + u < rows) {
+                const int r = row0 + i0 + u;
+                const float rstd = rsqrtf(s[u] * (1.0f / D) + p.eps);
+                const float4 o = make_float4(v[u].x * rstd * ga.x + be.x, v[u].y * rstd * ga.y + be.y, v[u].z * rstd * ga.z + be.z, v[u].w * rstd * ga.w + be.w);
+                const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
+                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ld_f32 + col) = o;
+                if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(o);
+            }
+        }
+    }
+}
+
+// out[map(r)][n0 + ...] = act(stage[r] + bias) for the warp's 32 rows; split > 0 partials are raw sums
+template <class P>
+__device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, int row0, int n0, int split, int lane) {
+    const int col = n0 + lane * 4;
+    if (col >= p.N) return;
+    const bool raw = p.splits > 1;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && !raw) bias = *reinterpret_cast<const float4*>(p.bias + col);
+    const bool relu = p.act == 1 && !raw;
+    float* out32 = p.out_f32 ? p.out_f32 + (int64_t)split * p.part_stride : nullptr;
+    const int rows = min(32, p.M - row0);
+    int kvh = 0, hd = 0;
+    if (p.head_major) { const int kv = col / D, cc = col % D; kvh = kv * p.hm_heads + cc / p.hm_dh; hd = cc % p.hm_dh; }
+    for (int i0 = 0; i0 < rows; i0 += EPI_ILP) {
+        float4 v[EPI_ILP];
+#pragma unroll
+        for (int u = 0; u < EPI_ILP; ++u) v[u] = *reinterpret_cast<const float4*>(stage + (size_t)((i0 + u) & 31) * TC_LDS + lane * 4);
+#pragma unroll
+        for (int u = 0; u < EPI_ILP; ++u) {
+            if (i0 + u >= rows) continue;
+            const int r = row0 + i0 + u;
+            float4 o = make_float4(v[u].x + bias.x, v[u].y + bias.y, v[u].z + bias.z, v[u].w + bias.w);
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.head_major) {
+                *reinterpret_cast<float4*>(out32 + ((int64_t)kvh * p.hm_rows + r) * p.hm_dh + hd) = o;
+            } else {
+                const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
+                if (out32) *reinterpret_cast<float4*>(out32 + orow * p.ld_f32 + col) = o;
+                if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(o);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the GEMM
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant__ TcGemmParams p) {
@@ -160,9 +275,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
     const int kb_end = min(kb_total, kb_begin + kb_per);
     const int num_kb = kb_end - kb_begin;      // host guarantees >= 1
 
+    const int stage_bytes = p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmW);
+        if (p.wsplit) tma_prefetch_desc(&p.tmW2);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
         fence_barrier_init();
@@ -179,10 +296,11 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
                 const int s = i % p.stages;
                 const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full_bar[s], TC_STAGE_BYTES);
-                uint8_t* a = smem + (size_t)s * TC_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                uint8_t* a = smem + (size_t)s * stage_bytes;
                 tma_load_2d(a, &p.tmA, &full_bar[s], (kb_begin + i) * TC_BK, m0);
                 tma_load_2d(a + TC_SLAB_BYTES, &p.tmW, &full_bar[s], (kb_begin + i) * TC_BK, n0);
+                if (p.wsplit) tma_load_2d(a + 2 * TC_SLAB_BYTES, &p.tmW2, &full_bar[s], (kb_begin + i) * TC_BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -193,12 +311,18 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
                 const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t adesc = umma_desc_sw128(a_addr);
                 const uint64_t bdesc = umma_desc_sw128(a_addr + TC_SLAB_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)   // +32 B per K step inside the 128 B swizzle row (encoded >> 4)
                     umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                if (p.wsplit) {
+                    const uint64_t bdesc2 = umma_desc_sw128(a_addr + 2 * TC_SLAB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc2 + (uint64_t)(2 * k), idesc, 1u);
+                }
                 umma_commit(&empty_bar[s]);            // smem slot reusable once these MMAs retire
             }
             umma_commit(&tmem_full_bar);               // accumulator complete
@@ -209,68 +333,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
         float* stage = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * TC_LDS;
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < TC_BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            tmem_ld_wait();
-            float* dst = stage + (size_t)lane * TC_LDS + c * 32;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(dst + 4 * j) =
-                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        }
-        __syncwarp();
-        const int col = n0 + lane * 4;
-        const bool col_ok = col < p.N;
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok && p.splits == 1) bias = *reinterpret_cast<const float4*>(p.bias + col);
-        const int rows = min(32, p.M - (m0 + q * 32));
-        if (EPI == TC_EPI_LN) {
-            const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
-            const float4 be = *reinterpret_cast<const float4*>(p.beta + col);
-            for (int i0 = 0; i0 < rows; i0 += 4) {
-                float4 rs[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int r = m0 + q * 32 + i0 + u;
-                    rs[u] = (i0 + u < rows) ? *reinterpret_cast<const float4*>(p.res + (int64_t)r * D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (i0 + u >= rows) break;
-                    const int r = m0 + q * 32 + i0 + u;
-                    float4 v = *reinterpret_cast<const float4*>(stage + (size_t)(i0 + u) * TC_LDS + lane * 4);
-                    v.x += bias.x + rs[u].x; v.y += bias.y + rs[u].y; v.z += bias.z + rs[u].z; v.w += bias.w + rs[u].w;
-                    const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);
-                    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-                    const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
-                    const float rstd = rsqrtf(var + p.eps);
-                    const float4 o = make_float4(dx * rstd * ga.x + be.x, dy * rstd * ga.y + be.y, dz * rstd * ga.z + be.z, dw * rstd * ga.w + be.w);
-                    const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
-                    if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ld_f32 + col) = o;
-                    if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(o);
-                }
-            }
-        } else {
-            float* out32 = p.out_f32 ? p.out_f32 + (int64_t)split * p.part_stride : nullptr;
-            for (int i = 0; i < rows; ++i) {
-                const int r = m0 + q * 32 + i;
-                float4 v = *reinterpret_cast<const float4*>(stage + (size_t)i * TC_LDS + lane * 4);
-                if (!col_ok) continue;
-                v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
-                if (p.act == 1 && p.splits == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                if (p.head_major) {
-                    const int kv = col / D, cc = col % D;
-                    const int h = cc / p.hm_dh, d = cc % p.hm_dh;
-                    *reinterpret_cast<float4*>(out32 + (((int64_t)kv * p.hm_heads + h) * p.hm_rows + r) * p.hm_dh + d) = v;
-                } else {
-                    const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
-                    if (out32) *reinterpret_cast<float4*>(out32 + orow * p.ld_f32 + col) = v;
-                    if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(v);
-                }
-            }
-        }
+        epi_tmem_to_stage<TC_BN>(tmem_base, q, lane, stage);
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, stage, m0 + q * 32, lane);
+        else epi_rows_store(p, stage, m0 + q * 32, n0, split, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -288,6 +353,17 @@ __global__ void __launch_bounds__(256) pack_rows_bf16(const float* src, const in
     const float* s = row_off ? src + row_off[r] : src + r * lds;
     const float4 v = *reinterpret_cast<const float4*>(s + lane * 4);
     *reinterpret_cast<uint2*>(dst + r * D + lane * 4) = pack_bf16x4(v);
+}
+
+// two-term bf16 split of an fp32 array: hi = bf16(x), lo = bf16(x - hi)
+__global__ void f32_to_bf16_split(const float* in, int64_t n, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float x = in[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
 }
 
 }  // namespace mmt

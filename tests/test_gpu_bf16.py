@@ -21,14 +21,17 @@ REL_TOL = 1e-2
                                         (33, 128, 2048, 0), (1000, 256, 128, 0), (4097, 384, 128, 0), (2500, 128, 2048, 1),
                                         (131, 512, 192, 0)])
 def test_linear_bf16_tcgen05(M, N, K, act):
-    """tcgen05 GEMM == fp64 product of the bf16-rounded operands (only the accumulation order differs)."""
+    """tcgen05 GEMM == fp64 product of the bf16-rounded activations with the two-term bf16 weights
+    W_hi + W_lo (only the accumulation order differs)."""
     s = setup()
     g = torch.Generator().manual_seed(M * 7 + N)
     A = torch.randn(M, K, generator=g).cuda()
     W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     b = torch.randn(N, generator=g).cuda()
     out = s["eng"].linear(A, W, b, act=act, precision="bf16")
-    ref = torch.nn.functional.linear(A.bfloat16().double(), W.bfloat16().double(), b.double())
+    W_hi = W.bfloat16()
+    W_lo = (W - W_hi.float()).bfloat16()
+    ref = torch.nn.functional.linear(A.bfloat16().double(), W_hi.double() + W_lo.double(), b.double())
     if act:
         ref = torch.relu(ref)
     torch.testing.assert_close(out.double(), ref, atol=2e-4, rtol=1e-4)
