@@ -192,6 +192,15 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
 int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const float* d_bias, float* d_C,
                    int64_t M, int32_t N, int32_t K, int32_t act, int32_t precision, void* stream);
 
+/* The fused feed-forward block of one transformer layer (linear1 -> ReLU -> linear2 -> +residual
+ * -> LayerNorm; torch TransformerEncoderLayer._ff_block + norm2, models_MMT_v15_4.py:510-541) in
+ * the bf16 tensor-core mode:  d_out = LN(d_x + W2 relu(W1 bf16(d_x) + b1) + b2) * gamma + beta,
+ * d_x / d_out (M,128) f32, W1 (F,128), W2 (128,F).  splits > 1 exercises the split-F partial path
+ * the small-batch decoder uses. */
+int32_t mmt_ffn(mmt_engine* e, const float* d_x, const float* d_w1, const float* d_b1, const float* d_w2,
+                const float* d_b2, const float* d_gamma, const float* d_beta, float* d_out,
+                int64_t M, int32_t F, int32_t splits, void* stream);
+
 /* launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t mmt_launch_count(const mmt_engine* e);
 

@@ -3,6 +3,8 @@
 #include "engine.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_decode.cuh"
+#include "kernels_ffn.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -113,16 +115,18 @@ static int tc_init(mmt_engine* e) {
     const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES_WSPLIT + 1024;
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
     e->tc_ready = true;
     return 0;
 }
 
 // [rows, cols] bf16 matrix, `ld` elements between rows; box = 64 (K) x 128 (rows), 128-byte swizzle
-static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, int64_t rows, int64_t cols, int64_t ld) {
+static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows = TC_BM) {
     if (((uintptr_t)ptr & 15) || (ld * 2) % 16) MMT_FAIL("tensor map: operand must be 16-byte aligned with a 16-byte multiple row pitch");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -162,6 +166,40 @@ static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int
     if (epi == TC_EPI_LN) gemm_bf16_tc<TC_EPI_LN><<<grid, TC_THREADS, smem, s>>>(p);
     else gemm_bf16_tc<TC_EPI_STORE><<<grid, TC_THREADS, smem, s>>>(p);
     return check_launch(e, epi == TC_EPI_LN ? "gemm_bf16_tc_ln" : "gemm_bf16_tc", s, 2.0 * p.M * p.N * p.K);
+}
+
+static FfnParams ffn_params(int M, int F) {
+    FfnParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = D; p.F = F; p.splits = 1; p.eps = 1e-5f; p.ld_f32 = D; p.ld_b16 = D;
+    p.S_in = M > 0 ? M : 1; p.stride_b = 0; p.stride_s = 1; p.off = 0;
+    return p;
+}
+
+// Fused FFN (kernels_ffn.cuh): X [M,128] bf16 (row pitch ldx); W1 [F,128] / W2 [128,F] as bf16 hi (+ lo) terms.
+// splits == 1 with epi == TC_EPI_LN: out = LN(res + b2 + FFN(X)); splits > 1: raw partials to out_f32.
+static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W1, const __nv_bfloat16* W1lo,
+                      const __nv_bfloat16* W2, const __nv_bfloat16* W2lo, int epi, cudaStream_t s) {
+    if (p.M <= 0) return 0;
+    MMT_TRY(tc_init(e));
+    if (p.F % FF_CH || p.F > FF_MAX_F || p.F < FF_CH) MMT_FAIL("fused FFN needs d_ff % 64 == 0 and d_ff <= 2048");
+    const int chunks = p.F / FF_CH;
+    if (p.splits < 1) p.splits = 1;
+    while (chunks % p.splits) --p.splits;
+    if (epi == TC_EPI_LN && p.splits != 1) MMT_FAIL("fused FFN: the LayerNorm epilogue needs splits == 1");
+    p.wsplit = (W1lo && W2lo) ? 1 : 0;
+    MMT_TRY(make_tmap(&p.tmX, X, p.M, D, ldx));
+    MMT_TRY(make_tmap(&p.tmW1, W1, p.F, D, D, FF_CH));
+    MMT_TRY(make_tmap(&p.tmW2, W2, D, p.F, p.F));
+    if (p.wsplit) {
+        MMT_TRY(make_tmap(&p.tmW1lo, W1lo, p.F, D, D, FF_CH));
+        MMT_TRY(make_tmap(&p.tmW2lo, W2lo, D, p.F, p.F));
+    }
+    dim3 grid(p.splits, (p.M + TC_BM - 1) / TC_BM);
+    prof_pre(e, s);
+    if (epi == TC_EPI_LN) ffn_fused_tc<TC_EPI_LN><<<grid, FF_THREADS, FF_SMEM_BYTES, s>>>(p);
+    else ffn_fused_tc<TC_EPI_STORE><<<grid, FF_THREADS, FF_SMEM_BYTES, s>>>(p);
+    return check_launch(e, "ffn_fused_tc", s, 4.0 * p.M * D * p.F);
 }
 
 // ---------------------------------------------------------------------------
@@ -252,7 +290,7 @@ static void plan_encoder(Arena& a, const ModeLayout& L, int Bc, int d_ff, EncBuf
         for (int m = 0; m < 5; ++m) b.X16[m] = a.get<__nv_bfloat16>((L.present[m] ? (int64_t)Bc * L.S_m[m] : 0) * D);
         b.Xc16 = a.get<__nv_bfloat16>(R * D);
         b.ATT16 = a.get<__nv_bfloat16>(rmax * D);
-        b.H16 = a.get<__nv_bfloat16>(rmax * d_ff);
+        b.H16 = nullptr;   // the fused FFN keeps the hidden activation on the SM
     }
 }
 
@@ -374,22 +412,16 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         p.out_f32 = gr[i].X; p.ld_f32 = D; p.out_b16 = gr[i].x16; p.ld_b16 = D;
         MMT_TRY(launch_tc(e, p, gr[i].att16, D, e->Wb(gr[i].w->out_w), TC_EPI_LN, s, e->Wlo(gr[i].w->out_w)));
     }
-    for (int i = 0; i < ng; ++i) {   // FFN1 + ReLU -> bf16 hidden
-        TcGemmParams p = tc_params(gr[i].rows, d_ff, D);
-        p.bias = gr[i].w->l1_b; p.act = 1; p.out_b16 = gr[i].h16; p.ld_b16 = d_ff;
-        MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), TC_EPI_STORE, s, e->Wlo(gr[i].w->l1_w)));
-    }
-    for (int i = 0; i < ng; ++i) {   // FFN2 + residual + LN2
-        TcGemmParams p = tc_params(gr[i].rows, D, d_ff);
-        p.bias = gr[i].w->l2_b; p.res = gr[i].X; p.gamma = gr[i].w->n2_w; p.beta = gr[i].w->n2_b;
+    for (int i = 0; i < ng; ++i) {   // fused FFN (hidden activation stays on the SM) + residual + LN2
+        FfnParams p = ffn_params(gr[i].rows, d_ff);
+        p.b1 = gr[i].w->l1_b; p.bias = gr[i].w->l2_b; p.res = gr[i].X; p.gamma = gr[i].w->n2_w; p.beta = gr[i].w->n2_b;
         if (gr[i].out || gr[i].out16) {
             p.out_f32 = gr[i].out; p.out_b16 = gr[i].out16;
             p.S_in = gr[i].S; p.stride_b = gr[i].stride_b; p.stride_s = gr[i].stride_s; p.off = gr[i].off;
         } else {
             p.out_f32 = gr[i].X; p.out_b16 = gr[i].x16;
         }
-        p.ld_f32 = D; p.ld_b16 = D;
-        MMT_TRY(launch_tc(e, p, gr[i].h16, d_ff, e->Wb(gr[i].w->l2_w), TC_EPI_LN, s, e->Wlo(gr[i].w->l2_w)));
+        MMT_TRY(launch_ffn(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), e->Wlo(gr[i].w->l1_w), e->Wb(gr[i].w->l2_w), e->Wlo(gr[i].w->l2_w), TC_EPI_LN, s));
     }
     return 0;
 }
@@ -541,7 +573,7 @@ struct DecBuffers {
     // bf16 operand copies (tensor-core mode)
     __nv_bfloat16 *x16, *att16, *h16, *mem16;
 };
-constexpr int MAX_SPLITS = 16;
+constexpr int MAX_SPLITS = 32;
 
 static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b, bool bf16) {
     const int L = d.n_dec_layers;
@@ -549,9 +581,9 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     b.x = a.get<float>(Nw * D);
     b.qkv = a.get<float>(Nw * 3 * D);
     b.att = a.get<float>(Nw * D);
-    b.part = a.get<float>(Nw * D * MAX_SPLITS);
+    b.part = a.get<float>(Nw * D * (Nw <= 2048 ? MAX_SPLITS : 1));   // split partials only exist for small waves
     b.qc = a.get<float>(Nw * D);
-    b.h = a.get<float>(Nw * d.d_ff);
+    b.h = a.get<float>(bf16 ? 0 : Nw * d.d_ff);
     b.kv_pool = a.get<float>((size_t)L * Nw * pps * 2 * PAGE_TOKENS * D);
     b.block_table = a.get<int>(Nw * pps);
     int64_t R = (int64_t)Bmw * S;
@@ -565,7 +597,7 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     if (bf16) {
         b.x16 = a.get<__nv_bfloat16>(Nw * D);
         b.att16 = a.get<__nv_bfloat16>(Nw * D);
-        b.h16 = a.get<__nv_bfloat16>(Nw * d.d_ff);
+        b.h16 = nullptr;   // fused FFN: no hidden activation in HBM
         b.mem16 = a.get<__nv_bfloat16>(R * D);
     }
 }
@@ -632,11 +664,6 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     const int64_t N_total = (int64_t)a.Bm * a.n_cand;
     const int M = (int)Nw;
 
-    prof_pre(e, s);
-    if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
-    else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
-    MMT_TRY(check_launch(e, "decode_embed", s));
-
     // x = LN(x + bias + sum_s part[s]) (separate kernel; fp32 mode and split-K FFN2)
     auto ln = [&](const float* part, int splits, const float* bias, const float* gamma, const float* beta) -> int {
         LnParams q;
@@ -666,45 +693,98 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
         return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W));
     };
-    const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
-    if (dh != 8) MMT_FAIL("decoder head dim must be 8");
-    for (int l = 0; l < d.n_dec_layers; ++l) {
-        const LayerW& w = e->dec[l];
-        float* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D;
-        const float* ckv = b.cross_kv + (size_t)l * 2 * R * D;
-        if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
-        else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
-        prof_pre(e, s);
-        decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, bf16 ? nullptr : b.att, b.att16);
-        MMT_TRY(check_launch(e, "decode_self_attention", s));
-        if (bf16) {
-            MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
-            MMT_TRY(tc(b.x16, D, w.ca_in_w, w.ca_in_b, b.qc, nullptr, D, D, 0, 1));
-        } else {
-            MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
-            MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
-            MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
+    // Small batches: every decoder operation except the FFN is local to one sequence, so two
+    // fused kernels per layer replace the chain of projection / attention / LayerNorm launches
+    // (kernels_decode.cuh); the previous layer's FFN2 split-K partials + norm3 are folded into the
+    // next kernel's prologue (the sampler's for the last layer).
+    const bool fused = e->fused_decode_rows > 0 && Nw <= e->fused_decode_rows;
+    int ffn_splits = 1;
+    if (fused) {
+        if (dh != 8) MMT_FAIL("decoder head dim must be 8");
+        const unsigned blocks = (unsigned)((Nw + DA_R - 1) / DA_R);
+        // bf16: F/64 = 32 chunks over (splits x M/128) CTAs -- enough splits to cover the SMs
+        ffn_splits = pick_splits(M, D, d.d_ff);
+        if (bf16) { ffn_splits = 32; while (ffn_splits > 1 && (int64_t)(ffn_splits / 2) * ((M + 127) / 128) >= e->sm_count) ffn_splits /= 2; }
+        for (int l = 0; l < d.n_dec_layers; ++l) {
+            const LayerW& w = e->dec[l];
+            DecAttnParams q;
+            memset(&q, 0, sizeof(q));
+            if (l == 0) {
+                if (r.mode == 2) { q.tokens = r.trg + n0; q.tok_shift = 0; }
+                else { q.tokens = r.tokens + n0; q.tok_shift = 1; }
+                q.sos = 3; q.ldn = N_total; q.E_tok = e->W("embed_trg.weight"); q.E_pos = e->W("pe_trg.weight"); q.vocab = d.vocab;
+            } else {
+                const LayerW& pw = e->dec[l - 1];
+                q.x_in = b.x; q.part = b.part; q.splits = ffn_splits; q.part_stride = Nw * D;
+                q.pbias = pw.l2_b; q.pgamma = pw.n3_w; q.pbeta = pw.n3_b;
+            }
+            q.in_w = w.in_w; q.in_b = w.in_b; q.out_w = w.out_w; q.out_b = w.out_b; q.n1_w = w.n1_w; q.n1_b = w.n1_b;
+            q.kv_pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D; q.block_table = b.block_table; q.pps = pps;
+            q.step = step;
+            q.cq_w = w.ca_in_w; q.cq_b = w.ca_in_b; q.co_w = w.ca_out_w; q.co_b = w.ca_out_b; q.n2_w = w.n2_w; q.n2_b = w.n2_b;
+            q.ckv = b.cross_kv + (size_t)l * 2 * R * D; q.rows_total = R;
+            q.nk = b.nk; q.row_start = b.row_start; q.kbias_c = b.kbias_c; q.n_cand = a.n_cand;
+            q.x2 = b.x; q.x2_16 = bf16 ? b.x16 : nullptr; q.M = Nw; q.H = H; q.scale = scale; q.eps = 1e-5f;
+            prof_pre(e, s);
+            decode_attn<8><<<blocks, DA_THREADS, 0, s>>>(q);
+            MMT_TRY(check_launch(e, "decode_attn", s));
+            if (bf16) {
+                FfnParams f = ffn_params(M, d.d_ff);
+                f.b1 = w.l1_b; f.splits = ffn_splits; f.out_f32 = b.part; f.part_stride = Nw * D;
+                MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s));
+            } else {
+                MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
+                MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, ffn_splits));
+            }
         }
+    } else {
         prof_pre(e, s);
-        decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, ckv, R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, bf16 ? nullptr : b.att, b.att16);
-        MMT_TRY(check_launch(e, "decode_cross_attention", s));
-        if (bf16) {
-            MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
-            MMT_TRY(tc(b.x16, D, w.l1_w, w.l1_b, nullptr, b.h16, d.d_ff, D, 1, 1));
-            if (M >= 2048) {
-                MMT_TRY(tc_ln(b.h16, d.d_ff, w.l2_w, w.l2_b, d.d_ff, w.n3_w, w.n3_b));
-            } else {   // few rows: split K = 2048 over the grid, reduce the partials in the LayerNorm kernel
-                const int splits = MAX_SPLITS;
-                MMT_TRY(tc(b.h16, d.d_ff, w.l2_w, nullptr, b.part, nullptr, D, d.d_ff, 0, splits));
+        if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+        else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+        MMT_TRY(check_launch(e, "decode_embed", s));
+
+        const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
+        if (dh != 8) MMT_FAIL("decoder head dim must be 8");
+        for (int l = 0; l < d.n_dec_layers; ++l) {
+            const LayerW& w = e->dec[l];
+            float* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D;
+            const float* ckv = b.cross_kv + (size_t)l * 2 * R * D;
+            if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
+            else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
+            prof_pre(e, s);
+            decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, bf16 ? nullptr : b.att, b.att16);
+            MMT_TRY(check_launch(e, "decode_self_attention", s));
+            if (bf16) {
+                MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
+                MMT_TRY(tc(b.x16, D, w.ca_in_w, w.ca_in_b, b.qc, nullptr, D, D, 0, 1));
+            } else {
+                MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
+                MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
+                MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
+            }
+            prof_pre(e, s);
+            decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, ckv, R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, bf16 ? nullptr : b.att, b.att16);
+            MMT_TRY(check_launch(e, "decode_cross_attention", s));
+            if (bf16) {
+                MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
+                if (M >= 2048) {
+                    FfnParams f = ffn_params(M, d.d_ff);
+                    f.b1 = w.l1_b; f.bias = w.l2_b; f.res = b.x; f.gamma = w.n3_w; f.beta = w.n3_b; f.out_f32 = b.x; f.out_b16 = b.x16;
+                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_LN, s));
+                } else {   // few rows: split F over the grid, reduce the partials in the LayerNorm kernel
+                    FfnParams f = ffn_params(M, d.d_ff);
+                    f.b1 = w.l1_b; f.splits = MAX_SPLITS; f.out_f32 = b.part; f.part_stride = Nw * D;
+                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s));
+                    MMT_TRY(ln(b.part, f.splits, w.l2_b, w.n3_w, w.n3_b));
+                }
+            } else {
+                MMT_TRY(gemm(b.att, D, w.ca_out_w, nullptr, b.part, D, D, 0, 1));
+                MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
+                MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
+                int splits = pick_splits(M, D, d.d_ff);
+                MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, splits));
                 MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
             }
-        } else {
-            MMT_TRY(gemm(b.att, D, w.ca_out_w, nullptr, b.part, D, D, 0, 1));
-            MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
-            MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
-            int splits = pick_splits(M, D, d.d_ff);
-            MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, splits));
-            MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
         }
     }
     SampleParams sp;
@@ -722,6 +802,11 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     sp.logits = r.logits ? r.logits + n0 * d.vocab : nullptr;
     sp.ctl.step = b.ctl; sp.ctl.done_ctas = b.ctl + 1; sp.ctl.nonpad = (r.mode == 0) ? b.ctl + 8 : nullptr;
     sp.advance = 1;
+    if (fused) {   // norm3 of the last layer over the FFN2 partials
+        const LayerW& pw = e->dec[d.n_dec_layers - 1];
+        sp.part = b.part; sp.splits = ffn_splits; sp.part_stride = Nw * D;
+        sp.pbias = pw.l2_b; sp.pgamma = pw.n3_w; sp.pbeta = pw.n3_b; sp.eps = 1e-5f;
+    }
     prof_pre(e, s);
     sample_tokens<<<(unsigned)((Nw + 7) / 8), 256, 0, s>>>(sp);
     MMT_TRY(check_launch(e, "sample_tokens", s));
@@ -865,6 +950,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     e->desc = *desc; e->device = device; e->sm_count = prop.multiProcessorCount; e->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
     e->reg = build_registry(*desc);
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
+    if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };
     if (cudaMalloc(&e->w32, n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc weights failed");
@@ -1030,6 +1116,46 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
     GemmParams p = gemm_params(N, K, N, act);
     p.g[0].A = d_A; p.g[0].lda = K; p.g[0].W = d_W; p.g[0].bias = d_bias; p.g[0].C = d_C; p.g[0].M = (int)M;
     return launch_gemm(e, p, 1, (int)M, cs);
+}
+
+int32_t mmt_ffn(mmt_engine* e, const float* d_x, const float* d_w1, const float* d_b1, const float* d_w2, const float* d_b2,
+                const float* d_gamma, const float* d_beta, float* d_out, int64_t M, int32_t F, int32_t splits, void* stream) {
+    if (!e || !d_x || !d_w1 || !d_b1 || !d_w2 || !d_b2 || !d_gamma || !d_beta || !d_out) MMT_FAIL("null argument");
+    if (M <= 0) return 0;
+    if (M > 0x7fffffff) MMT_FAIL("M too large");
+    MMT_CUDA(cudaSetDevice(e->device));
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (splits < 1) splits = 1;
+    const size_t nX = (size_t)M * D, nW = (size_t)F * D;
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t bX = al(nX * 2), bW = al(nW * 2), bP = al((size_t)splits * nX * 4);
+    MMT_TRY(ensure_arena(e, bX + 4 * bW + bP + 512));
+    char* base = e->arena;
+    __nv_bfloat16* X16 = reinterpret_cast<__nv_bfloat16*>(base);
+    __nv_bfloat16* W1h = reinterpret_cast<__nv_bfloat16*>(base + bX);
+    __nv_bfloat16* W1l = reinterpret_cast<__nv_bfloat16*>(base + bX + bW);
+    __nv_bfloat16* W2h = reinterpret_cast<__nv_bfloat16*>(base + bX + 2 * bW);
+    __nv_bfloat16* W2l = reinterpret_cast<__nv_bfloat16*>(base + bX + 3 * bW);
+    float* part = reinterpret_cast<float*>(base + bX + 4 * bW);
+    f32_to_bf16<<<(unsigned)((nX + 255) / 256), 256, 0, cs>>>(d_x, (int64_t)nX, X16);
+    f32_to_bf16_split<<<(unsigned)((nW + 255) / 256), 256, 0, cs>>>(d_w1, (int64_t)nW, W1h, W1l);
+    f32_to_bf16_split<<<(unsigned)((nW + 255) / 256), 256, 0, cs>>>(d_w2, (int64_t)nW, W2h, W2l);
+    MMT_CUDA(cudaGetLastError());
+    FfnParams p = ffn_params((int)M, F);
+    p.b1 = d_b1; p.splits = splits;
+    if (splits == 1) {
+        p.bias = d_b2; p.res = d_x; p.gamma = d_gamma; p.beta = d_beta; p.out_f32 = d_out;
+        return launch_ffn(e, p, X16, D, W1h, W1l, W2h, W2l, TC_EPI_LN, cs);
+    }
+    p.out_f32 = part; p.part_stride = (int64_t)nX;
+    MMT_TRY(launch_ffn(e, p, X16, D, W1h, W1l, W2h, W2l, TC_EPI_STORE, cs));
+    LnParams q;
+    memset(&q, 0, sizeof(q));
+    q.splits = p.splits; q.part_stride = (int64_t)nX; q.eps = 1e-5f;
+    LnGroup& g = q.g[0];
+    g.part = part; g.bias = d_b2; g.res = d_x; g.gamma = d_gamma; g.beta = d_beta; g.out = d_out; g.M = (int)M;
+    g.S_in = (int)M; g.stride_b = 0; g.stride_s = 1; g.off = 0;
+    return launch_ln(e, q, 1, (int)M, cs);
 }
 
 int64_t mmt_launch_count(const mmt_engine* e) { return e ? e->launches : 0; }

@@ -116,6 +116,7 @@ struct mmt_engine {
     size_t arena_bytes = 0;
     int64_t launches = 0;
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
+    int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     cudaStream_t cap_stream = nullptr; // capture-only stream (the caller's stream may be the legacy default stream)
     bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)
     int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)

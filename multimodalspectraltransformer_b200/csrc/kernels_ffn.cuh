@@ -1,0 +1,215 @@
+// Fused transformer FFN on the sm_100a tensor cores:
+//
+//   out = epi( relu(X . W1^T + b1) . W2^T )        X [M,128] bf16, W1 [F,128], W2 [128,F] bf16 (K contiguous)
+//
+// The F-wide hidden activation never leaves the SM.  A CTA owns 128 rows of X (resident in shared
+// memory) and walks its share of F in chunks of 64 columns:
+//
+//   GEMM1   acc1[c&1] (TMEM, 64 cols)  = X . W1[c]^T              tcgen05.mma 128x64x16, K = 128
+//   convert H[c&1] (smem, bf16, 128B-swizzled K-major) = relu(acc1 + b1[c])     4 epilogue warps
+//   GEMM2   acc2 (TMEM, 128 cols)     += H[c&1] . W2[:, c]^T      tcgen05.mma 128x128x16, K = 64
+//
+// software-pipelined so that GEMM1 of chunk c+1 runs on the tensor core while the epilogue warps
+// convert chunk c (acc1 and H are double-buffered; the W1/W2 chunk ring has two TMA stages).
+// Weights are the two-term bf16 split W_hi + W_lo (kernels_tc.cuh): every MMA pass runs twice.
+//
+// grid = (splits, ceil(M/128)).  splits == 1: the epilogue is bias + residual + LayerNorm over the
+// 128-wide row (encoder layers, large decode batches).  splits > 1 (small decode batches: more CTAs
+// than M/128): each CTA handles F/64/splits chunks and writes a raw fp32 partial; the consumer
+// (decode_attn_self / sample_tokens prologue, or bias_res_layernorm) reduces them in a fixed order.
+//
+// warp 0: TMA producer (one lane) | warp 1: MMA issuer (one lane) + TMEM alloc (256 cols) | warps 2-5: epilogue
+#pragma once
+#include "kernels_tc.cuh"
+
+namespace mmt {
+
+constexpr int FF_CH = 64;                                  // hidden columns per chunk
+constexpr int FF_THREADS = 192;
+constexpr int FF_X_BYTES = 2 * TC_SLAB_BYTES;              // X: two K slabs of [128 rows x 64]
+constexpr int FF_H_BYTES = TC_SLAB_BYTES;                  // one H buffer: [128 rows x 64] bf16
+constexpr int FF_W1_SLAB = FF_CH * TC_BK * 2;              // 8 KB: [64 rows x 64 K]
+constexpr int FF_STAGE_BYTES = 4 * FF_W1_SLAB + 2 * TC_SLAB_BYTES;   // W1 hi(2 slabs) + lo(2) + W2 hi + W2 lo = 64 KB
+constexpr int FF_OFF_H = FF_X_BYTES;
+constexpr int FF_OFF_W = FF_OFF_H + 2 * FF_H_BYTES;
+constexpr int FF_OFF_B1 = FF_OFF_W + 2 * FF_STAGE_BYTES;   // 192 KB
+constexpr int FF_MAX_F = 2048;
+constexpr int FF_SMEM_BYTES = FF_OFF_B1 + FF_MAX_F * 4 + 1024;
+static_assert(2 * FF_STAGE_BYTES >= TC_STAGING_BYTES, "final staging tile aliases the weight ring");
+
+struct FfnParams {
+    CUtensorMap tmX;                 // X  [M,128] bf16, box {64,128}
+    CUtensorMap tmW1, tmW1lo;        // W1 [F,128] bf16, box {64,64}
+    CUtensorMap tmW2, tmW2lo;        // W2 [128,F] bf16, box {64,128}
+    int wsplit;
+    int M, N, F;                     // N == 128
+    int splits;
+    const float* b1;                 // [F]
+    int64_t part_stride;             // floats between split partials
+    const float* bias; int act;      // b2 (LayerNorm epilogue only); act unused (0)
+    float* out_f32; int64_t ld_f32;
+    __nv_bfloat16* out_b16; int64_t ld_b16;
+    int head_major, hm_heads, hm_dh; int64_t hm_rows;   // unused (0); keeps the shared epilogue templates happy
+    const float* res; const float* gamma; const float* beta; float eps;
+    int S_in; int64_t stride_b, stride_s, off;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t x_full, w_full[2], w_empty[2], acc1_full[2], h_full[2], h_empty[2], acc2_full;
+    __shared__ uint32_t tmem_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sX = smem;
+    uint8_t* sH = smem + FF_OFF_H;
+    uint8_t* sW = smem + FF_OFF_W;
+    float* b1s = reinterpret_cast<float*>(smem + FF_OFF_B1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, m0 = blockIdx.y * TC_BM;
+    const int n = (p.F / FF_CH) / p.splits;      // chunks of this CTA (host guarantees divisibility, n >= 1)
+    const int c0 = split * n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW1); tma_prefetch_desc(&p.tmW2);
+        if (p.wsplit) { tma_prefetch_desc(&p.tmW1lo); tma_prefetch_desc(&p.tmW2lo); }
+        mbar_init(&x_full, 1); mbar_init(&acc2_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&acc1_full[s], 1);
+            mbar_init(&h_full[s], 128); mbar_init(&h_empty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 256);
+    if (warp >= 2)
+        for (int i = threadIdx.x - 64; i < n * FF_CH; i += 128) b1s[i] = p.b1[c0 * FF_CH + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_acc2 = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&x_full, FF_X_BYTES);
+            tma_load_2d(sX, &p.tmX, &x_full, 0, m0);
+            tma_load_2d(sX + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0);
+            for (int i = 0; i < n; ++i) {
+                const int s = i & 1, c = c0 + i;
+                mbar_wait(&w_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&w_full[s], p.wsplit ? FF_STAGE_BYTES : FF_STAGE_BYTES / 2);
+                uint8_t* w = sW + (size_t)s * FF_STAGE_BYTES;
+                tma_load_2d(w, &p.tmW1, &w_full[s], 0, c * FF_CH);
+                tma_load_2d(w + FF_W1_SLAB, &p.tmW1, &w_full[s], TC_BK, c * FF_CH);
+                tma_load_2d(w + 4 * FF_W1_SLAB, &p.tmW2, &w_full[s], c * FF_CH, 0);
+                if (p.wsplit) {
+                    tma_load_2d(w + 2 * FF_W1_SLAB, &p.tmW1lo, &w_full[s], 0, c * FF_CH);
+                    tma_load_2d(w + 3 * FF_W1_SLAB, &p.tmW1lo, &w_full[s], TC_BK, c * FF_CH);
+                    tma_load_2d(w + 4 * FF_W1_SLAB + TC_SLAB_BYTES, &p.tmW2lo, &w_full[s], c * FF_CH, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = umma_idesc_bf16(TC_BM, FF_CH);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(TC_BM, TC_BN);
+            const uint32_t x_addr = smem_u32(sX);
+            // acc2 += H[j&1] . W2[:, chunk j]^T
+            auto gemm2 = [&](int j) {
+                const int b = j & 1;
+                mbar_wait(&h_full[b], ((uint32_t)j >> 1) & 1u);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sH + (size_t)b * FF_H_BYTES));
+                const uint32_t w2 = smem_u32(sW + (size_t)b * FF_STAGE_BYTES + 4 * FF_W1_SLAB);
+                const uint64_t bdesc = umma_desc_sw128(w2);
+#pragma unroll
+                for (int k = 0; k < FF_CH / 16; ++k)
+                    umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                if (p.wsplit) {
+                    const uint64_t bdesc2 = umma_desc_sw128(w2 + TC_SLAB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < FF_CH / 16; ++k)
+                        umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc2 + (uint64_t)(2 * k), idesc2, 1u);
+                }
+                umma_commit(&w_empty[b]);      // weight stage b reusable
+                umma_commit(&h_empty[b]);      // H buffer b reusable
+            };
+            mbar_wait(&x_full, 0);
+            for (int i = 0; i < n; ++i) {
+                const int s = i & 1;
+                mbar_wait(&w_full[s], ((uint32_t)i >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t w1 = smem_u32(sW + (size_t)s * FF_STAGE_BYTES);
+                const uint32_t acc1 = tmem_base + (uint32_t)(s * FF_CH);
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(x_addr + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
+                    const uint64_t bdesc = umma_desc_sw128(w1 + (k >> 2) * FF_W1_SLAB) + (uint64_t)(2 * (k & 3));
+                    umma_bf16(acc1, adesc, bdesc, idesc1, k > 0 ? 1u : 0u);
+                }
+                if (p.wsplit) {
+#pragma unroll
+                    for (int k = 0; k < D / 16; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(x_addr + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
+                        const uint64_t bdesc = umma_desc_sw128(w1 + (2 + (k >> 2)) * FF_W1_SLAB) + (uint64_t)(2 * (k & 3));
+                        umma_bf16(acc1, adesc, bdesc, idesc1, 1u);
+                    }
+                }
+                umma_commit(&acc1_full[s]);
+                if (i > 0) gemm2(i - 1);
+            }
+            gemm2(n - 1);
+            umma_commit(&acc2_full);
+        }
+    } else {
+        // ---------------- epilogue warps: warp (id % 4) owns TMEM lanes [32*(id%4), +32); thread = row
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        for (int i = 0; i < n; ++i) {
+            const int b = i & 1;
+            mbar_wait(&acc1_full[b], ((uint32_t)i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t pk[FF_CH / 2];
+#pragma unroll
+            for (int c = 0; c < FF_CH / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * FF_CH + c * 32), r);
+                tmem_ld_wait();
+                const float* bb = b1s + i * FF_CH + c * 32;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float lo = fmaxf(__uint_as_float(r[2 * j]) + bb[2 * j], 0.f);
+                    const float hi = fmaxf(__uint_as_float(r[2 * j + 1]) + bb[2 * j + 1], 0.f);
+                    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+                    pk[c * 16 + j] = *reinterpret_cast<uint32_t*>(&v);
+                }
+            }
+            mbar_wait(&h_empty[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+            uint8_t* hrow = sH + (size_t)b * FF_H_BYTES + (size_t)row * 128;
+#pragma unroll
+            for (int cj = 0; cj < 8; ++cj)      // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
+                *reinterpret_cast<uint4*>(hrow + ((cj ^ (row & 7)) << 4)) = make_uint4(pk[4 * cj], pk[4 * cj + 1], pk[4 * cj + 2], pk[4 * cj + 3]);
+            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            mbar_arrive(&h_full[b]);
+        }
+        float* stage = reinterpret_cast<float*>(sW) + (size_t)(q * 32) * TC_LDS;
+        mbar_wait(&acc2_full, 0);
+        tc_fence_after();
+        epi_tmem_to_stage<TC_BN>(tmem_acc2, q, lane, stage);
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, stage, m0 + q * 32, lane);
+        else epi_rows_store(p, stage, m0 + q * 32, 0, split, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace mmt

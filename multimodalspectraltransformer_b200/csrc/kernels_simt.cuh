@@ -678,17 +678,42 @@ struct SampleParams {
     float* logits;           // [T][N][V] (forced / unit test) or nullptr
     StepCtl ctl;             // ctl.step may be nullptr (stand-alone use, t = 0)
     int advance;             // 1: the last CTA increments *ctl.step
+    // optional prologue (fused decoder path): x <- LN(x + pbias + sum_s part[s]) -- the last layer's FFN2 + norm3
+    const float* part; int splits; int64_t part_stride;
+    const float* pbias; const float* pgamma; const float* pbeta; float eps;
 };
 
 __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ SampleParams p) {
     __shared__ float Ws[VOCAB_MAX * (D + 1)];
     __shared__ __align__(16) float xs[8][D];
-    const int t = p.ctl.step ? *p.ctl.step : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < p.V * D; i += blockDim.x) Ws[(i / D) * (D + 1) + (i % D)] = p.W[i];
+    // fc_out weights -> padded smem rows (independent of the step: issued before anything else)
+    for (int i = threadIdx.x; i < p.V * (D / 4); i += blockDim.x) {
+        const float4 w = *reinterpret_cast<const float4*>(p.W + (int64_t)i * 4);
+        float* dst = Ws + (i / (D / 4)) * (D + 1) + (i % (D / 4)) * 4;
+        dst[0] = w.x; dst[1] = w.y; dst[2] = w.z; dst[3] = w.w;
+    }
+    const int t = p.ctl.step ? *p.ctl.step : 0;
     const int64_t n = (int64_t)blockIdx.x * 8 + warp;
-    if (n < p.N) *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+    if (n < p.N) {
+        float4 v = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+        if (p.part) {
+            float4 s = *reinterpret_cast<const float4*>(p.pbias + lane * 4);
+            for (int k0 = 0; k0 < p.splits; k0 += 8) {     // 8 partials in flight per pass, fixed summation order
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    q[u] = (k0 + u < p.splits) ? *reinterpret_cast<const float4*>(p.part + (int64_t)(k0 + u) * p.part_stride + n * D + lane * 4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { s.x += q[u].x; s.y += q[u].y; s.z += q[u].z; s.w += q[u].w; }
+            }
+            v = ln_row(make_float4(v.x + s.x, v.y + s.y, v.z + s.z, v.w + s.w), p.pgamma, p.pbeta, p.eps, lane);
+        }
+        *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = v;
+    }
     __syncthreads();
+    int picked_nonpad = 0;
     if (n < p.N) {
         const int v0 = lane, v1 = lane + 32;
         float a0 = 0.f, a1 = 0.f;
@@ -739,18 +764,21 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
             if (lane == 0) {
                 if (p.tokens) p.tokens[(int64_t)t * p.ldn + n] = bi;
                 if (p.probs) p.probs[(int64_t)t * p.ldn + n] = bp;
-                if (p.ctl.nonpad && bi != 0) atomicAdd(p.ctl.nonpad + t, 1);
+                picked_nonpad = (bi != 0);
             }
         }
     }
-    if (p.advance) {
-        __syncthreads();
+    if (p.advance || p.ctl.nonpad) {
+        const int cta_nonpad = __syncthreads_count(picked_nonpad);   // one atomic per CTA, not per sequence
         if (threadIdx.x == 0) {
-            __threadfence();
-            int done = atomicAdd(p.ctl.done_ctas, 1);
-            if (done == (int)gridDim.x - 1) {
-                *p.ctl.done_ctas = 0;
-                *p.ctl.step = t + 1;
+            if (p.ctl.nonpad && cta_nonpad) atomicAdd(p.ctl.nonpad + t, cta_nonpad);
+            if (p.advance) {
+                __threadfence();
+                int done = atomicAdd(p.ctl.done_ctas, 1);
+                if (done == (int)gridDim.x - 1) {
+                    *p.ctl.done_ctas = 0;
+                    *p.ctl.step = t + 1;
+                }
             }
         }
     }

@@ -109,3 +109,32 @@ def test_multinomial_bf16_candidates():
     torch.manual_seed(11)
     tok2, _ = s["M"].multinomial_sequence_multi(s["model"], memory, mask, STOI, cfg, n_candidates=32)
     assert torch.equal(tok, tok2)        # deterministic for a fixed seed
+
+
+@pytest.mark.parametrize("M,F,splits", [(256, 2048, 1), (256, 2048, 16), (256, 2048, 32), (77, 2048, 8), (1000, 2048, 1),
+                                         (4097, 2048, 1), (130, 512, 2), (128, 64, 1)])
+def test_ffn_fused_tcgen05(M, F, splits):
+    """Fused FFN kernel == fp64 evaluation of the same contract: bf16(x) . (W1_hi + W1_lo), bias, ReLU, hidden
+    rounded to bf16, . (W2_hi + W2_lo), + b2 + x (fp32 residual), LayerNorm."""
+    s = setup()
+    g = torch.Generator().manual_seed(M * 3 + F + splits)
+    x = torch.randn(M, 128, generator=g).cuda()
+    w1 = (torch.randn(F, 128, generator=g) / 128 ** 0.5).cuda()
+    b1 = (0.1 * torch.randn(F, generator=g)).cuda()
+    w2 = (torch.randn(128, F, generator=g) / F ** 0.5).cuda()
+    b2 = (0.1 * torch.randn(128, generator=g)).cuda()
+    gamma = (1 + 0.1 * torch.randn(128, generator=g)).cuda()
+    beta = (0.1 * torch.randn(128, generator=g)).cuda()
+    out = s["eng"].ffn(x, w1, b1, w2, b2, gamma, beta, splits=splits)
+
+    def two_term(w):
+        hi = w.bfloat16()
+        return hi.double() + (w - hi.float()).bfloat16().double()
+    h = torch.relu(x.bfloat16().double() @ two_term(w1).T + b1.double())
+    h = h.float().bfloat16().double()
+    y = x.double() + h @ two_term(w2).T + b2.double()
+    ref = torch.nn.functional.layer_norm(y, (128,), gamma.double(), beta.double(), 1e-5)
+    # the hidden activation is rounded to bf16 from an fp32 accumulator whose last bits depend on the
+    # accumulation order: a handful of elements may round the other way (1 bf16 ulp of h ~ 4e-3 * |h|)
+    torch.testing.assert_close(out.double(), ref, atol=3e-3, rtol=1e-3)
+    assert float((out.double() - ref).abs().mean()) < 2e-4
