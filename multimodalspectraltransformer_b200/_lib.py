@@ -94,14 +94,20 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        build()
+    path = os.environ.get("MMT_B200_LIB")      # A/B experiments: load another build of the same ABI
+    if path:
+        if not os.path.exists(path):
+            raise RuntimeError(f"MMT_B200_LIB={path} does not exist")
     else:
-        try:
+        path = LIB_PATH
+        if not os.path.exists(LIB_PATH):
             build()
-        except RuntimeError:
-            pass  # no nvcc on this box: use the shipped .so
-    L = C.CDLL(LIB_PATH)
+        else:
+            try:
+                build()
+            except RuntimeError:
+                pass  # no nvcc on this box: use the shipped .so
+    L = C.CDLL(path)
     vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
     D = C.POINTER(ModelDesc)
     L.mmt_abi_version.restype = i32

@@ -37,6 +37,32 @@ __device__ __forceinline__ float4 ln_row(float4 v, const float* gamma, const flo
     return make_float4(dx * rstd * ga.x + be.x, dy * rstd * ga.y + be.y, dz * rstd * ga.z + be.z, dw * rstd * ga.w + be.w);
 }
 
+// One key / value row of a head (8 elements) in the KV caches: fp32 in the fp32 check mode, bf16 in
+// the tensor-core mode (halves the HBM stream that bounds the decode step).  `Raw` is what one lane
+// loads (kept un-converted while the loads are in flight), `unpack` widens it to fp32.
+template <typename T> struct KvRow;
+template <> struct KvRow<float> {
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw ld(const float* p) {
+        Raw r; r.a = reinterpret_cast<const float4*>(p)[0]; r.b = reinterpret_cast<const float4*>(p)[1]; return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+        v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+    }
+    static __device__ __forceinline__ void st(float* p, float x) { *p = x; }
+};
+template <> struct KvRow<__nv_bfloat16> {
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw ld(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+        v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+        v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float x) { *p = __float2bfloat16_rn(x); }
+};
+
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace mmt

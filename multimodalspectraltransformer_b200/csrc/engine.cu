@@ -566,8 +566,9 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
 // ---------------------------------------------------------------------------
 struct DecBuffers {
     float *x, *qkv, *att, *part, *qc, *h;
-    float* kv_pool; int* block_table;
-    float* cross_kv;
+    char* kv_pool; int* block_table;   // paged self-attention cache, 6 pools of kv_esz-byte elements
+    char* cross_kv;                    // projected memory [layer][K|V][head][row][dh], kv_esz-byte elements
+    size_t kv_esz;                     // 4 (fp32 check mode) | 2 (bf16 tensor-core mode)
     int *nk, *row_start; int64_t* row_off; float* kbias_c;
     int* ctl;   // [0] step, [1] done_ctas, [8..8+max_len) nonpad counts
     // bf16 operand copies (tensor-core mode)
@@ -584,10 +585,11 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     b.part = a.get<float>(Nw * D * (Nw <= 2048 ? MAX_SPLITS : 1));   // split partials only exist for small waves
     b.qc = a.get<float>(Nw * D);
     b.h = a.get<float>(bf16 ? 0 : Nw * d.d_ff);
-    b.kv_pool = a.get<float>((size_t)L * Nw * pps * 2 * PAGE_TOKENS * D);
+    b.kv_esz = bf16 ? 2 : 4;
+    b.kv_pool = a.get<char>((size_t)L * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz);
     b.block_table = a.get<int>(Nw * pps);
     int64_t R = (int64_t)Bmw * S;
-    b.cross_kv = a.get<float>((size_t)L * 2 * R * D);
+    b.cross_kv = a.get<char>((size_t)L * 2 * R * D * b.kv_esz);
     b.nk = a.get<int>(Bmw);
     b.row_start = a.get<int>(Bmw);
     b.row_off = a.get<int64_t>(R);
@@ -635,7 +637,7 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
         for (int l = 0; l < d.n_dec_layers; ++l) {
             TcGemmParams p = tc_params((int)R, 2 * D, D);
             p.bias = e->dec[l].ca_in_b + D;
-            p.out_f32 = b.cross_kv + (size_t)l * 2 * R * D;
+            p.out_b16 = reinterpret_cast<__nv_bfloat16*>(b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz);
             p.head_major = 1; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
             MMT_TRY(launch_tc(e, p, b.mem16, D, e->Wb(e->dec[l].ca_in_w + (int64_t)D * D), TC_EPI_STORE, s, e->Wlo(e->dec[l].ca_in_w + (int64_t)D * D)));
         }
@@ -646,7 +648,7 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
         p.g[0].A = a.d_memory + (int64_t)b0 * a.stride_b; p.g[0].a_row_off = b.row_off; p.g[0].lda = 0;
         p.g[0].W = e->dec[l].ca_in_w + (int64_t)D * D;     // rows D..3D of in_proj: K then V
         p.g[0].bias = e->dec[l].ca_in_b + D;
-        p.g[0].C = b.cross_kv + (size_t)l * 2 * R * D; p.g[0].M = (int)R;
+        p.g[0].C = reinterpret_cast<float*>(b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz); p.g[0].M = (int)R;
         p.out_mode = GEMM_OUT_HEADMAJOR; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
         MMT_TRY(launch_gemm(e, p, 1, (int)R, s));
     }
@@ -700,7 +702,16 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     const bool fused = e->fused_decode_rows > 0 && Nw <= e->fused_decode_rows;
     int ffn_splits = 1;
     if (fused) {
-        if (dh != 8) MMT_FAIL("decoder head dim must be 8");
+        if (dh != 8 || H != DA_H) MMT_FAIL("decoder must have 16 heads of dim 8");
+        if (!e->da_dbg && getenv("MMT_DA_DEBUG")) {
+            MMT_CUDA(cudaMallocManaged(&e->da_dbg, 4096 * 16 * sizeof(long long)));
+            memset(e->da_dbg, 0, 4096 * 16 * sizeof(long long));
+        }
+        if (!e->da_ready) {
+            MMT_CUDA(cudaFuncSetAttribute(decode_attn<8, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
+            MMT_CUDA(cudaFuncSetAttribute(decode_attn<8, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
+            e->da_ready = true;
+        }
         const unsigned blocks = (unsigned)((Nw + DA_R - 1) / DA_R);
         // bf16: F/64 = 32 chunks over (splits x M/128) CTAs -- enough splits to cover the SMs
         ffn_splits = pick_splits(M, D, d.d_ff);
@@ -719,18 +730,21 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 q.pbias = pw.l2_b; q.pgamma = pw.n3_w; q.pbeta = pw.n3_b;
             }
             q.in_w = w.in_w; q.in_b = w.in_b; q.out_w = w.out_w; q.out_b = w.out_b; q.n1_w = w.n1_w; q.n1_b = w.n1_b;
-            q.kv_pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D; q.block_table = b.block_table; q.pps = pps;
+            q.kv_pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz; q.block_table = b.block_table; q.pps = pps;
             q.step = step;
             q.cq_w = w.ca_in_w; q.cq_b = w.ca_in_b; q.co_w = w.ca_out_w; q.co_b = w.ca_out_b; q.n2_w = w.n2_w; q.n2_b = w.n2_b;
-            q.ckv = b.cross_kv + (size_t)l * 2 * R * D; q.rows_total = R;
+            q.ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz; q.rows_total = R;
             q.nk = b.nk; q.row_start = b.row_start; q.kbias_c = b.kbias_c; q.n_cand = a.n_cand;
-            q.x2 = b.x; q.x2_16 = bf16 ? b.x16 : nullptr; q.M = Nw; q.H = H; q.scale = scale; q.eps = 1e-5f;
+            q.x2 = b.x; q.x2_16 = bf16 ? b.x16 : nullptr; q.M = Nw; q.scale = scale; q.eps = 1e-5f;
+            q.dbg = (e->da_dbg && l == 3) ? e->da_dbg : nullptr;
             prof_pre(e, s);
-            decode_attn<8><<<blocks, DA_THREADS, 0, s>>>(q);
+            if (bf16) decode_attn<8, __nv_bfloat16><<<blocks, DA_THREADS, DA_SMEM_BYTES, s>>>(q);
+            else decode_attn<8, float><<<blocks, DA_THREADS, DA_SMEM_BYTES, s>>>(q);
             MMT_TRY(check_launch(e, "decode_attn", s));
             if (bf16) {
                 FfnParams f = ffn_params(M, d.d_ff);
                 f.b1 = w.l1_b; f.splits = ffn_splits; f.out_f32 = b.part; f.part_stride = Nw * D;
+                f.dbg = (e->da_dbg && l == 3) ? e->da_dbg + 2048 * 16 : nullptr;
                 MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s));
             } else {
                 MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
@@ -747,12 +761,13 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         if (dh != 8) MMT_FAIL("decoder head dim must be 8");
         for (int l = 0; l < d.n_dec_layers; ++l) {
             const LayerW& w = e->dec[l];
-            float* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D;
-            const float* ckv = b.cross_kv + (size_t)l * 2 * R * D;
+            char* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz;
+            const char* ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz;
             if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
             else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
             prof_pre(e, s);
-            decode_self_attention<8><<<attn_blocks, 256, 0, s>>>(b.qkv, pool, b.block_table, pps, Nw, H, scale, step, bf16 ? nullptr : b.att, b.att16);
+            if (bf16) decode_self_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), b.block_table, pps, Nw, H, scale, step, nullptr, b.att16);
+            else decode_self_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_self_attention", s));
             if (bf16) {
                 MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
@@ -763,7 +778,8 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
             }
             prof_pre(e, s);
-            decode_cross_attention<8><<<attn_blocks, 256, 0, s>>>(b.qc, ckv, R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, bf16 ? nullptr : b.att, b.att16);
+            if (bf16) decode_cross_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, nullptr, b.att16);
+            else decode_cross_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const float*>(ckv), R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_cross_attention", s));
             if (bf16) {
                 MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
@@ -889,6 +905,21 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1)
         for (int q = 0; q < r.T; ++q) if (nonpad_total[q] == 0) { steps_done = q + 1; break; }
     if (h_steps) *h_steps = steps_done;
+    if (e->da_dbg) {   // MMT_DA_DEBUG: phase timestamps (SM cycles) of the last decode_attn launch of layer 3
+        MMT_CUDA(cudaStreamSynchronize(s));
+        const int blocks = (int)std::min<int64_t>(4096, (std::min<int64_t>(N_total, max_wave_seqs) + DA_R - 1) / DA_R);
+        for (int bshow : {0, blocks / 2, blocks - 1}) {
+            fprintf(stderr, "decode_attn phases, CTA %d:", bshow);
+            for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", e->da_dbg[bshow * 16 + i] - e->da_dbg[bshow * 16 + i - 1]);
+            fprintf(stderr, "  total %lld\n", e->da_dbg[bshow * 16 + 10] - e->da_dbg[bshow * 16]);
+        }
+        for (int bshow : {0, 33}) {
+            const long long* d = e->da_dbg + (2048 + bshow) * 16;
+            fprintf(stderr, "ffn_fused phases, CTA %d:", bshow);
+            for (int i = 1; i <= 7; ++i) fprintf(stderr, " %lld", d[i] - d[i - 1]);
+            fprintf(stderr, "  total %lld\n", d[7] - d[0]);
+        }
+    }
     return 0;
 }
 

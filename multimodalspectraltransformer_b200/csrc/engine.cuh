@@ -118,6 +118,8 @@ struct mmt_engine {
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     cudaStream_t cap_stream = nullptr; // capture-only stream (the caller's stream may be the legacy default stream)
+    long long* da_dbg = nullptr;       // MMT_DA_DEBUG phase timestamps (managed memory)
+    bool da_ready = false;             // decode_attn shared-memory attribute set
     bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)
     int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)
     // per-kernel-class device timing (mmt_profile_enable / mmt_profile_report)

@@ -10,18 +10,22 @@
 //                 x2 = LN2(x1 + W_o^cross att + b)      (fp32 + bf16 operand copy for the FFN)
 //
 // The per-step working set (cross K/V of every sequence, 40+ MB per layer) streams through L2 and
-// evicts the weights between steps, so every dependent phase would pay a DRAM round trip.  The kernel
-// therefore starts by prefetching into L2 (no registers held): its slice of this layer's weights
-// (all CTAs together cover them once) and the cross-attention K/V rows its own warps will read in
-// the second half -- the HBM stream of the cross attention overlaps the self-attention phases.
+// evicts the weights between steps, so every dependent global access pays a DRAM round trip and the
+// kernel is a chain of such round trips.  It is organised to keep that chain short:
+//   * weights never pass through registers: the 192 KB QKV matrix is pulled into shared memory by
+//     bulk async copies (cp.async.bulk + mbarrier) issued before anything else, and the three
+//     128x128 matrices of the later phases replace it while the self-attention runs;
+//   * the cross-attention K/V rows a warp will read in the second half are prefetched into L2 at
+//     kernel start (no registers held), so that HBM stream overlaps the self-attention phases;
+//   * one warp per (row, head): every per-warp index / page-table load is issued up front.
 //
 // Arithmetic is fp32 in both precision modes (these projections are 20 % of the decoder's weights
 // and the larger share of the bf16 logit error, DESIGN.md "bf16 numerics").
 //
 // Shape of the work: the kernels are pure latency chains (L2 / HBM round trips), so a CTA is a full
 // 1024-thread SM's worth of warps for DA_R rows: one warp per (row, head) in the attention phases,
-// and the 128-wide matrix-vector products split K over the lanes of a warp (coalesced 512 B weight
-// rows straight from L2) with 16 outputs per warp pass, finished by a shuffle reduce-scatter.
+// and the 128-wide matrix-vector products split K over the lanes of a warp (conflict-free 512 B
+// weight rows in shared memory) with 16 outputs per warp pass, finished by a shuffle reduce-scatter.
 #pragma once
 #include "common.cuh"
 
@@ -30,6 +34,13 @@ namespace mmt {
 constexpr int DA_R = 2;            // sequences per CTA
 constexpr int DA_WARPS = 32;
 constexpr int DA_THREADS = DA_WARPS * 32;
+constexpr int DA_H = 16;           // decoder heads (config_V8 num_heads): one warp per (row, head)
+static_assert(DA_R * DA_H == DA_WARPS, "one warp per (row, head)");
+// dynamic shared memory: weight buffer + small parameter vectors
+constexpr int DA_W_FLOATS = 3 * D * D;                      // in_proj (384x128); later out_w | cq_w | co_w
+enum { DA_P_INB = 0, DA_P_OUTB = 3 * D, DA_P_N1W = 4 * D, DA_P_N1B = 5 * D, DA_P_CQB = 6 * D, DA_P_COB = 7 * D,
+       DA_P_N2W = 8 * D, DA_P_N2B = 9 * D, DA_P_PB = 10 * D, DA_P_PG = 11 * D, DA_P_PBETA = 12 * D, DA_P_FLOATS = 13 * D };
+constexpr int DA_SMEM_BYTES = (DA_W_FLOATS + DA_P_FLOATS) * 4 + 128;
 
 // v[0..15] per lane -> every lane returns sum over the 32 lanes of v[(lane >> 1) & 15]
 // (reduce-scatter butterfly: 8 + 4 + 2 + 1 + 1 shuffles)
@@ -49,28 +60,24 @@ __device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
 }
 
 // out[r][n] = bias[n] + W[n,:] . xs[r,:]   for n in [0, n_out), all DA_R rows; W row-major [n_out][128]
-// in global memory.  Warps take groups of 16 outputs round-robin.
-__device__ __forceinline__ void gemv_rows(const float* __restrict__ W, const float* __restrict__ bias, int n_out,
+// and bias in SHARED memory.  Warps take groups of 16 outputs round-robin.
+__device__ __forceinline__ void gemv_rows(const float* W, const float* bias, int n_out,
                                           const float (*xs)[D], float* out, int ldo, int warp, int lane) {
     float4 xr[DA_R];
 #pragma unroll
     for (int r = 0; r < DA_R; ++r) xr[r] = *reinterpret_cast<const float4*>(&xs[r][4 * lane]);
     for (int n0 = warp * 16; n0 < n_out; n0 += DA_WARPS * 16) {
         float acc[DA_R][16];
-        const float4* wp = reinterpret_cast<const float4*>(W + (int64_t)n0 * D) + lane;
+        const float4* wp = reinterpret_cast<const float4*>(W + n0 * D) + lane;
 #pragma unroll
-        for (int jb = 0; jb < 16; jb += 4) {
-            float4 w[4];
+        for (int j = 0; j < 16; ++j) {
+            const float4 w = wp[j * (D / 4)];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = __ldg(wp + (int64_t)(jb + j) * (D / 4));
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int r = 0; r < DA_R; ++r)
-                    acc[r][jb + j] = fmaf(w[j].w, xr[r].w, fmaf(w[j].z, xr[r].z, fmaf(w[j].y, xr[r].y, w[j].x * xr[r].x)));
+            for (int r = 0; r < DA_R; ++r)
+                acc[r][j] = fmaf(w.w, xr[r].w, fmaf(w.z, xr[r].z, fmaf(w.y, xr[r].y, w.x * xr[r].x)));
         }
         const int n = n0 + ((lane >> 1) & 15);
-        const float b = bias ? bias[n] : 0.f;
+        const float b = bias[n];
 #pragma unroll
         for (int r = 0; r < DA_R; ++r) {
             const float v = reduce_scatter16(acc[r], lane) + b;
@@ -81,13 +88,33 @@ __device__ __forceinline__ void gemv_rows(const float* __restrict__ W, const flo
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// every CTA prefetches its 1/gridDim share of a weight matrix (64-byte granules), so that the grid
-// as a whole pulls the matrix into L2 exactly once
-__device__ __forceinline__ void prefetch_slice(const float* w, int n_floats) {
-    const int granules = n_floats / 16;
-    const int per = (granules + gridDim.x - 1) / gridDim.x;
-    const int g0 = blockIdx.x * per;
-    for (int g = g0 + threadIdx.x; g < min(g0 + per, granules); g += blockDim.x) prefetch_l2(w + (int64_t)g * 16);
+// ---- bulk async copy global -> shared, completion on an mbarrier (same primitives as kernels_tc.cuh)
+__device__ __forceinline__ uint32_t da_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void da_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(da_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void da_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(da_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void da_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(da_smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) { printf("mmt: decode_attn mbarrier wait timed out\n"); __trap(); }
+    }
+}
+__device__ __forceinline__ void da_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(da_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(da_smem_u32(bar)) : "memory");
+}
+// copy `floats` fp32 in pieces of at most 16 KB
+__device__ __forceinline__ void da_bulk_matrix(float* dst, const float* src, int floats, uint64_t* bar) {
+    for (int o = 0; o < floats; o += 4096) da_bulk_g2s(dst + o, src + o, (uint32_t)min(4096, floats - o) * 4u, bar);
 }
 
 struct DecAttnParams {
@@ -99,19 +126,25 @@ struct DecAttnParams {
     const float* pbias; const float* pgamma; const float* pbeta;     //   x = LN3(x_in + pbias + sum_s part[s])
     // ---- self-attention block
     const float *in_w, *in_b, *out_w, *out_b, *n1_w, *n1_b;
-    float* kv_pool; const int* block_table; int pps;                 // paged self-attention cache of this layer
+    void* kv_pool; const int* block_table; int pps;                  // paged self-attention cache of this layer (KVT elements)
     const int* step;
     // ---- cross-attention block
     const float *cq_w, *cq_b, *co_w, *co_b, *n2_w, *n2_b;
-    const float* ckv; int64_t rows_total;      // projected memory of this layer, head-major [2][H][rows_total][DH]
+    const void* ckv; int64_t rows_total;       // projected memory of this layer, head-major [2][H][rows_total][DH] (KVT elements)
     const int* nk; const int* row_start; const float* kbias_c; int n_cand;
     float* x2; __nv_bfloat16* x2_16;           // out [M][D] fp32 (+ bf16 operand copy for the FFN, optional)
-    int64_t M; int H; float scale; float eps;
+    int64_t M; float scale; float eps;
+    long long* dbg;                            // optional [gridDim.x][16] phase timestamps (MMT_DA_DEBUG)
 };
 
-template <int DH>
+template <int DH, typename KVT>
 __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_constant__ DecAttnParams p) {
-    static_assert(DH == 8, "two float4 per key row");
+    static_assert(DH == 8 && DH * DA_H == D, "8-element key rows, 16 heads");
+    typedef KvRow<KVT> KV;
+    extern __shared__ __align__(128) uint8_t da_smem[];
+    float* Wbuf = reinterpret_cast<float*>(da_smem);
+    float* Ps = Wbuf + DA_W_FLOATS;
+    __shared__ __align__(8) uint64_t bars[4];      // 0: in_w + vectors, 1: out_w, 2: cq_w, 3: co_w
     __shared__ __align__(16) float xs[DA_R][D];
     __shared__ __align__(16) float qkv[DA_R][3 * D];
     __shared__ __align__(16) float att[DA_R][D];
@@ -119,34 +152,73 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     __shared__ __align__(16) float psum[DA_WARPS][D];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t)blockIdx.x * DA_R;
+    const int r = warp / DA_H, h = warp % DA_H;      // this warp's (row, head) in the attention phases
+    const int64_t n = row0 + r;
+    const bool live = n < p.M;
+#define DA_STAMP(i) do { if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+    DA_STAMP(0);
 
-    // ---- L2 prefetch: weights of this layer (grid-wide, once) and this CTA's cross-attention K/V rows
-    prefetch_slice(p.in_w, 3 * D * D);
-    prefetch_slice(p.out_w, D * D);
-    prefetch_slice(p.cq_w, D * D);
-    prefetch_slice(p.co_w, D * D);
-    for (int pair = warp; pair < DA_R * p.H; pair += DA_WARPS) {
-        const int r = pair / p.H, h = pair % p.H;
-        const int64_t n = row0 + r;
-        if (n >= p.M) continue;
-        const int64_t b = n / p.n_cand;
-        const int cnt = p.nk[b];
-        const int64_t r0 = p.row_start[b];
-        const float* Kh = p.ckv + ((int64_t)(0 * p.H + h) * p.rows_total + r0) * DH;
-        const float* Vh = p.ckv + ((int64_t)(1 * p.H + h) * p.rows_total + r0) * DH;
-        for (int g = lane; g * 16 < cnt * DH; g += 32) { prefetch_l2(Kh + g * 16); prefetch_l2(Vh + g * 16); }
+    // ---- weights of the first phase + every small vector: bulk async copies, issued before anything else
+    // (one copy per lane of warp 0: a single thread issuing ~25 copies costs microseconds)
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < 4; ++i) da_mbar_init(&bars[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t vec_bytes = (uint32_t)(3 * D + 7 * D + (p.part ? 3 * D : 0)) * 4u;
+            da_mbar_expect_tx(&bars[0], (uint32_t)DA_W_FLOATS * 4u + vec_bytes);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // every CTA reads the same matrix in the same order: requests for one line from many SMs that
+            // arrive close together are merged by L2 (measured: a per-CTA rotated order is 2x slower)
+            for (int piece = 0; piece < 12; ++piece)
+                da_bulk_g2s(Wbuf + piece * 4096, p.in_w + piece * 4096, 4096 * 4, &bars[0]);
+        } else if (lane >= 12) {
+            const float* src = nullptr; int dst = 0, nf = D;
+            switch (lane) {
+                case 12: src = p.in_b; dst = DA_P_INB; nf = 3 * D; break;
+                case 13: src = p.out_b; dst = DA_P_OUTB; break;
+                case 14: src = p.n1_w; dst = DA_P_N1W; break;
+                case 15: src = p.n1_b; dst = DA_P_N1B; break;
+                case 16: src = p.cq_b; dst = DA_P_CQB; break;
+                case 17: src = p.co_b; dst = DA_P_COB; break;
+                case 18: src = p.n2_w; dst = DA_P_N2W; break;
+                case 19: src = p.n2_b; dst = DA_P_N2B; break;
+                case 20: if (p.part) { src = p.pbias; dst = DA_P_PB; } break;
+                case 21: if (p.part) { src = p.pgamma; dst = DA_P_PG; } break;
+                case 22: if (p.part) { src = p.pbeta; dst = DA_P_PBETA; } break;
+                default: break;
+            }
+            if (src) da_bulk_g2s(Ps + dst, src, (uint32_t)nf * 4u, &bars[0]);
+        }
     }
+    // ---- per-warp indices, issued up front: cross-attention key range, self-attention page table
+    int cnt = 0;
+    int64_t r0 = 0;
+    int my_page = 0;
+    if (live) {
+        const int64_t b = n / p.n_cand;
+        cnt = p.nk[b];
+        r0 = p.row_start[b];
+        my_page = (lane < p.pps) ? p.block_table[n * p.pps + lane] : 0;
+    }
+    const KVT* Kc = reinterpret_cast<const KVT*>(p.ckv) + ((int64_t)(0 * DA_H + h) * p.rows_total + r0) * DH;
+    const KVT* Vc = reinterpret_cast<const KVT*>(p.ckv) + ((int64_t)(1 * DA_H + h) * p.rows_total + r0) * DH;
+    constexpr int PF = 64 / (int)sizeof(KVT);     // elements per 64-byte prefetch granule
     const int t = *p.step;
+    // L2 prefetch of this warp's cross-attention K/V rows (64-byte granules; consumed in the second half)
+    for (int g = lane; g * PF < cnt * DH; g += 32) { prefetch_l2(Kc + g * PF); prefetch_l2(Vc + g * PF); }
+    DA_STAMP(1);
 
     // ---- prologue: layer input
     if (p.tokens) {
         if (warp < DA_R) {
-            const int64_t n = row0 + warp;
+            const int64_t nn = row0 + warp;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < p.M) {
+            if (nn < p.M) {
                 int64_t tok;
-                if (p.tok_shift) tok = (t == 0) ? p.sos : p.tokens[(int64_t)(t - 1) * p.ldn + n];
-                else tok = p.tokens[(int64_t)t * p.ldn + n];
+                if (p.tok_shift) tok = (t == 0) ? p.sos : p.tokens[(int64_t)(t - 1) * p.ldn + nn];
+                else tok = p.tokens[(int64_t)t * p.ldn + nn];
                 if (tok < 0 || tok >= p.vocab) tok = 0;
                 const float4 a = *reinterpret_cast<const float4*>(p.E_tok + tok * D + lane * 4);
                 const float4 b = *reinterpret_cast<const float4*>(p.E_pos + (int64_t)t * D + lane * 4);
@@ -154,59 +226,77 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             }
             *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = v;
         }
+        __syncthreads();
+        da_mbar_wait(&bars[0], 0);
     } else {
         // x = LN3(x_in + pbias + sum_s part[s]): the partial sums are spread over all warps (one L2
         // round trip), reduced through shared memory in a fixed order (deterministic)
-        const int r = warp % DA_R, k0 = warp / DA_R;
-        const int64_t n = row0 + r;
+        const int pr = warp % DA_R, k0 = warp / DA_R;
+        const int64_t nn = row0 + pr;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < p.M && p.part) {
-            for (int k = k0; k < p.splits; k += DA_WARPS / DA_R) {
-                const float4 q = *reinterpret_cast<const float4*>(p.part + (int64_t)k * p.part_stride + n * D + lane * 4);
-                s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+        float4 xin = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nn < p.M) {
+            if (warp < DA_R) xin = *reinterpret_cast<const float4*>(p.x_in + nn * D + lane * 4);
+            if (p.part) {
+                float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+                if (k0 < p.splits) q0 = *reinterpret_cast<const float4*>(p.part + (int64_t)k0 * p.part_stride + nn * D + lane * 4);
+                if (k0 + DA_WARPS / DA_R < p.splits)
+                    q1 = *reinterpret_cast<const float4*>(p.part + (int64_t)(k0 + DA_WARPS / DA_R) * p.part_stride + nn * D + lane * 4);
+                s = make_float4(q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, q0.w + q1.w);
+                for (int k = k0 + 2 * (DA_WARPS / DA_R); k < p.splits; k += DA_WARPS / DA_R) {
+                    const float4 q = *reinterpret_cast<const float4*>(p.part + (int64_t)k * p.part_stride + nn * D + lane * 4);
+                    s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+                }
             }
         }
         *reinterpret_cast<float4*>(&psum[warp][lane * 4]) = s;
         __syncthreads();
+        da_mbar_wait(&bars[0], 0);
         if (warp < DA_R) {
-            const int64_t n2 = row0 + warp;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n2 < p.M) {
-                v = *reinterpret_cast<const float4*>(p.x_in + n2 * D + lane * 4);
-                if (p.part) {
-                    float4 a = *reinterpret_cast<const float4*>(p.pbias + lane * 4);
+            float4 v = xin;     // warp < DA_R => pr == warp
+            if (p.part && row0 + warp < p.M) {
+                float4 a = *reinterpret_cast<const float4*>(Ps + DA_P_PB + lane * 4);
 #pragma unroll
-                    for (int k = 0; k < DA_WARPS / DA_R; ++k) {
-                        const float4 q = *reinterpret_cast<const float4*>(&psum[k * DA_R + warp][lane * 4]);
-                        a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
-                    }
-                    v = ln_row(make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w), p.pgamma, p.pbeta, p.eps, lane);
+                for (int k = 0; k < DA_WARPS / DA_R; ++k) {
+                    const float4 q = *reinterpret_cast<const float4*>(&psum[k * DA_R + warp][lane * 4]);
+                    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
                 }
+                v = ln_row(make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w), Ps + DA_P_PG, Ps + DA_P_PBETA, p.eps, lane);
             }
             *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = v;
         }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- QKV projection (384 outputs)
-    gemv_rows(p.in_w, p.in_b, 3 * D, xs, &qkv[0][0], 3 * D, warp, lane);
+    DA_STAMP(2);
+    // ---- QKV projection (384 outputs) from shared memory
+    gemv_rows(Wbuf, Ps + DA_P_INB, 3 * D, xs, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
+    DA_STAMP(3);
+    // the QKV matrix is dead: pull the three 128x128 matrices of the later phases into its place
+    if (warp == 0) {
+        if (lane < 3) da_mbar_expect_tx(&bars[1 + lane], D * D * 4);
+        __syncwarp();
+        if (lane == 0) {   // 3 matrices x 4 pieces of 16 KB, in order of use
+            for (int m = 0; m < 3; ++m) {
+                const float* src = (m == 0 ? p.out_w : (m == 1 ? p.cq_w : p.co_w));
+                for (int piece = 0; piece < 4; ++piece)
+                    da_bulk_g2s(Wbuf + m * D * D + piece * 4096, src + piece * 4096, 4096 * 4, &bars[1 + m]);
+            }
+        }
+    }
 
     // ---- KV append + causal self-attention: one warp per (row, head)
-    constexpr int PAGE_FLOATS = 2 * PAGE_TOKENS * D;
-    for (int pair = warp; pair < DA_R * p.H; pair += DA_WARPS) {
-        const int r = pair / p.H, h = pair % p.H;
-        const int64_t n = row0 + r;
-        if (n >= p.M) continue;
-        // page ids of this sequence: lane i holds page i (max_len 128 / PAGE_TOKENS 16 = 8 pages)
-        const int my_page = (lane < p.pps) ? p.block_table[n * p.pps + lane] : 0;
+    constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
+    KVT* const pool = reinterpret_cast<KVT*>(p.kv_pool);
+    if (live) {
         const float* row = &qkv[r][h * DH];
         {
             const int pg = __shfl_sync(0xffffffffu, my_page, t / PAGE_TOKENS);
             if (lane < 2 * DH) {
                 const int kv = lane / DH, d = lane % DH;
-                float* page = p.kv_pool + (int64_t)pg * PAGE_FLOATS;
-                page[((kv * p.H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + d] = row[(1 + kv) * D + d];
+                KVT* page = pool + (int64_t)pg * PAGE_ELEMS;
+                KV::st(page + ((kv * DA_H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + d, row[(1 + kv) * D + d]);
             }
         }
         __syncwarp();
@@ -216,23 +306,27 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         constexpr int MAXK = 4;   // max_len 128 / 32
         float s[MAXK];
         float m = MMT_NEG_INF;
+        typename KV::Raw kraw[MAXK];
+#pragma unroll
+        for (int i = 0; i < MAXK; ++i) {     // all K rows of this lane in flight together; V rows prefetched to L2
+            const int j = lane + i * 32;
+            const int pg = __shfl_sync(0xffffffffu, my_page, (j / PAGE_TOKENS) & 31);
+            if (j <= t) {
+                const KVT* page = pool + (int64_t)pg * PAGE_ELEMS;
+                kraw[i] = KV::ld(page + ((0 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
+                prefetch_l2(page + ((1 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < MAXK; ++i) {
             const int j = lane + i * 32;
-            const int pg = __shfl_sync(0xffffffffu, my_page, (j / PAGE_TOKENS) & 31);
             s[i] = MMT_NEG_INF;
             if (j <= t) {
-                const float* page = p.kv_pool + (int64_t)pg * PAGE_FLOATS;
-                const float4* k = reinterpret_cast<const float4*>(page + ((0 * p.H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
-                const float4* v = reinterpret_cast<const float4*>(page + ((1 * p.H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
-                prefetch_l2(v);
+                float k[DH];
+                KV::unpack(kraw[i], k);
                 float a = 0.f;
 #pragma unroll
-                for (int d4 = 0; d4 < DH / 4; ++d4) {
-                    const float4 kk = k[d4];
-                    a = fmaf(q[d4 * 4], kk.x, a); a = fmaf(q[d4 * 4 + 1], kk.y, a);
-                    a = fmaf(q[d4 * 4 + 2], kk.z, a); a = fmaf(q[d4 * 4 + 3], kk.w, a);
-                }
+                for (int d = 0; d < DH; ++d) a = fmaf(q[d], k[d], a);
                 s[i] = a;
                 m = fmaxf(m, a);
             }
@@ -246,16 +340,20 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             const int j = lane + i * 32;
             const int pg = __shfl_sync(0xffffffffu, my_page, (j / PAGE_TOKENS) & 31);
             if (j <= t) {
+                const KVT* page = pool + (int64_t)pg * PAGE_ELEMS;
+                kraw[i] = KV::ld(page + ((1 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXK; ++i) {
+            const int j = lane + i * 32;
+            if (j <= t) {
                 const float e = expf(s[i] - m);
                 l += e;
-                const float* page = p.kv_pool + (int64_t)pg * PAGE_FLOATS;
-                const float4* v = reinterpret_cast<const float4*>(page + ((1 * p.H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
+                float v[DH];
+                KV::unpack(kraw[i], v);
 #pragma unroll
-                for (int d4 = 0; d4 < DH / 4; ++d4) {
-                    const float4 vv = v[d4];
-                    acc[d4 * 4] = fmaf(e, vv.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(e, vv.y, acc[d4 * 4 + 1]);
-                    acc[d4 * 4 + 2] = fmaf(e, vv.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(e, vv.w, acc[d4 * 4 + 3]);
-                }
+                for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, v[d], acc[d]);
             }
         }
         l = warp_sum(l);
@@ -267,34 +365,34 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
             att[r][h * DH + lane] = v / l;
         }
+    } else if (lane < DH) {
+        att[r][h * DH + lane] = 0.f;
     }
     __syncthreads();
+    DA_STAMP(4);
 
     // ---- out-projection -> qkv[r][0..127] (reused as scratch), then LN1
-    gemv_rows(p.out_w, p.out_b, D, att, &qkv[0][0], 3 * D, warp, lane);
+    da_mbar_wait(&bars[1], 0);
+    DA_STAMP(5);
+    gemv_rows(Wbuf, Ps + DA_P_OUTB, D, att, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
     if (warp < DA_R) {
         const float4 a = *reinterpret_cast<const float4*>(&xs[warp][lane * 4]);
         const float4 y = *reinterpret_cast<const float4*>(&qkv[warp][lane * 4]);
         *reinterpret_cast<float4*>(&x1s[warp][lane * 4]) =
-            ln_row(make_float4(a.x + y.x, a.y + y.y, a.z + y.z, a.w + y.w), p.n1_w, p.n1_b, p.eps, lane);
+            ln_row(make_float4(a.x + y.x, a.y + y.y, a.z + y.z, a.w + y.w), Ps + DA_P_N1W, Ps + DA_P_N1B, p.eps, lane);
     }
     __syncthreads();
 
+    DA_STAMP(6);
     // ---- cross-attention query projection -> xs (the layer input is no longer needed)
-    gemv_rows(p.cq_w, p.cq_b, D, x1s, &xs[0][0], D, warp, lane);
+    da_mbar_wait(&bars[2], 0);
+    gemv_rows(Wbuf + D * D, Ps + DA_P_CQB, D, x1s, &xs[0][0], D, warp, lane);
     __syncthreads();
+    DA_STAMP(7);
 
     // ---- cross-attention over the projected memory: one warp per (row, head)
-    for (int pair = warp; pair < DA_R * p.H; pair += DA_WARPS) {
-        const int r = pair / p.H, h = pair % p.H;
-        const int64_t n = row0 + r;
-        if (n >= p.M) continue;
-        const int64_t b = n / p.n_cand;
-        const int cnt = p.nk[b];
-        const int64_t r0 = p.row_start[b];
-        const float4* Kh = reinterpret_cast<const float4*>(p.ckv + ((int64_t)(0 * p.H + h) * p.rows_total + r0) * DH);
-        const float4* Vh = reinterpret_cast<const float4*>(p.ckv + ((int64_t)(1 * p.H + h) * p.rows_total + r0) * DH);
+    if (live) {
         const float* bias = p.kbias_c + r0;
         float q[DH], acc[DH];
 #pragma unroll
@@ -305,15 +403,13 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             const int j1 = j0 + 32;
             const bool has1 = j1 < cnt;
             const int j1c = has1 ? j1 : j0;
-            const float4 ka0 = Kh[(int64_t)j0 * 2], kb0 = Kh[(int64_t)j0 * 2 + 1];
-            const float4 ka1 = Kh[(int64_t)j1c * 2], kb1 = Kh[(int64_t)j1c * 2 + 1];
-            const float4 va0 = Vh[(int64_t)j0 * 2], vb0 = Vh[(int64_t)j0 * 2 + 1];
-            const float4 va1 = Vh[(int64_t)j1c * 2], vb1 = Vh[(int64_t)j1c * 2 + 1];
+            const typename KV::Raw rk0 = KV::ld(Kc + (int64_t)j0 * DH), rk1 = KV::ld(Kc + (int64_t)j1c * DH);
+            const typename KV::Raw rv0 = KV::ld(Vc + (int64_t)j0 * DH), rv1 = KV::ld(Vc + (int64_t)j1c * DH);
             float s0 = bias[j0], s1 = has1 ? bias[j1] : MMT_NEG_INF;
-            s0 = fmaf(q[0], ka0.x, s0); s0 = fmaf(q[1], ka0.y, s0); s0 = fmaf(q[2], ka0.z, s0); s0 = fmaf(q[3], ka0.w, s0);
-            s0 = fmaf(q[4], kb0.x, s0); s0 = fmaf(q[5], kb0.y, s0); s0 = fmaf(q[6], kb0.z, s0); s0 = fmaf(q[7], kb0.w, s0);
-            s1 = fmaf(q[0], ka1.x, s1); s1 = fmaf(q[1], ka1.y, s1); s1 = fmaf(q[2], ka1.z, s1); s1 = fmaf(q[3], ka1.w, s1);
-            s1 = fmaf(q[4], kb1.x, s1); s1 = fmaf(q[5], kb1.y, s1); s1 = fmaf(q[6], kb1.z, s1); s1 = fmaf(q[7], kb1.w, s1);
+            float k0[DH], k1[DH];
+            KV::unpack(rk0, k0); KV::unpack(rk1, k1);
+#pragma unroll
+            for (int d = 0; d < DH; ++d) { s0 = fmaf(q[d], k0[d], s0); s1 = fmaf(q[d], k1[d], s1); }
             const float mn = fmaxf(m, fmaxf(s0, s1));
             if (mn > m) {
                 const float corr = expf(m - mn);   // m = -inf on the first pass -> 0
@@ -324,10 +420,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             }
             const float e0 = expf(s0 - m), e1 = has1 ? expf(s1 - m) : 0.f;
             l += e0 + e1;
-            acc[0] = fmaf(e0, va0.x, acc[0]); acc[1] = fmaf(e0, va0.y, acc[1]); acc[2] = fmaf(e0, va0.z, acc[2]); acc[3] = fmaf(e0, va0.w, acc[3]);
-            acc[4] = fmaf(e0, vb0.x, acc[4]); acc[5] = fmaf(e0, vb0.y, acc[5]); acc[6] = fmaf(e0, vb0.z, acc[6]); acc[7] = fmaf(e0, vb0.w, acc[7]);
-            acc[0] = fmaf(e1, va1.x, acc[0]); acc[1] = fmaf(e1, va1.y, acc[1]); acc[2] = fmaf(e1, va1.z, acc[2]); acc[3] = fmaf(e1, va1.w, acc[3]);
-            acc[4] = fmaf(e1, vb1.x, acc[4]); acc[5] = fmaf(e1, vb1.y, acc[5]); acc[6] = fmaf(e1, vb1.z, acc[6]); acc[7] = fmaf(e1, vb1.w, acc[7]);
+            float v0[DH], v1[DH];
+            KV::unpack(rv0, v0); KV::unpack(rv1, v1);
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] = fmaf(e1, v1[d], fmaf(e0, v0[d], acc[d]));
         }
         const float Mx = warp_max(m);
         const float corr = (m == MMT_NEG_INF) ? 0.f : expf(m - Mx);
@@ -342,24 +438,29 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         }
     }
     __syncthreads();
+    DA_STAMP(8);
 
     // ---- cross out-projection -> qkv scratch, then LN2 -> x2
-    gemv_rows(p.co_w, p.co_b, D, att, &qkv[0][0], 3 * D, warp, lane);
+    da_mbar_wait(&bars[3], 0);
+    gemv_rows(Wbuf + 2 * D * D, Ps + DA_P_COB, D, att, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
+    DA_STAMP(9);
     if (warp < DA_R) {
-        const int64_t n = row0 + warp;
-        if (n < p.M) {
+        const int64_t nn = row0 + warp;
+        if (nn < p.M) {
             const float4 a = *reinterpret_cast<const float4*>(&x1s[warp][lane * 4]);
             const float4 y = *reinterpret_cast<const float4*>(&qkv[warp][lane * 4]);
-            const float4 o = ln_row(make_float4(a.x + y.x, a.y + y.y, a.z + y.z, a.w + y.w), p.n2_w, p.n2_b, p.eps, lane);
-            *reinterpret_cast<float4*>(p.x2 + n * D + lane * 4) = o;
+            const float4 o = ln_row(make_float4(a.x + y.x, a.y + y.y, a.z + y.z, a.w + y.w), Ps + DA_P_N2W, Ps + DA_P_N2B, p.eps, lane);
+            *reinterpret_cast<float4*>(p.x2 + nn * D + lane * 4) = o;
             if (p.x2_16) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                *reinterpret_cast<uint2*>(p.x2_16 + n * D + lane * 4) =
+                *reinterpret_cast<uint2*>(p.x2_16 + nn * D + lane * 4) =
                     make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
             }
         }
     }
+    DA_STAMP(10);
+#undef DA_STAMP
 }
 
 }  // namespace mmt

@@ -52,6 +52,7 @@ struct FfnParams {
     int head_major, hm_heads, hm_dh; int64_t hm_rows;   // unused (0); keeps the shared epilogue templates happy
     const float* res; const float* gamma; const float* beta; float eps;
     int S_in; int64_t stride_b, stride_s, off;
+    long long* dbg;                  // optional [CTA][16] phase timestamps (MMT_DA_DEBUG)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     __shared__ __align__(8) uint64_t x_full, w_full[2], w_empty[2], acc1_full[2], h_full[2], h_empty[2], acc2_full;
     __shared__ uint32_t tmem_slot;
 
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space
     uint8_t* sX = smem;
     uint8_t* sH = smem + FF_OFF_H;
     uint8_t* sW = smem + FF_OFF_W;
@@ -73,6 +74,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     const int split = blockIdx.x, m0 = blockIdx.y * TC_BM;
     const int n = (p.F / FF_CH) / p.splits;      // chunks of this CTA (host guarantees divisibility, n >= 1)
     const int c0 = split * n;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+#define FF_STAMP(i) do { if (p.dbg) p.dbg[cta * 16 + (i)] = clock64(); } while (0)
+    if (threadIdx.x == 64) FF_STAMP(0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW1); tma_prefetch_desc(&p.tmW2);
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t tmem_acc2 = tmem_base + 128;
+    if (threadIdx.x == 64) FF_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             const int b = i & 1;
             mbar_wait(&acc1_full[b], ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
+            if (threadIdx.x == 64 && i == 0) FF_STAMP(2);
             uint32_t pk[FF_CH / 2];
 #pragma unroll
             for (int c = 0; c < FF_CH / 32; ++c) {
@@ -196,16 +202,22 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             tc_fence_before();
             mbar_arrive(&h_full[b]);
+            if (threadIdx.x == 64 && i == 0) FF_STAMP(3);
         }
         float* stage = reinterpret_cast<float*>(sW) + (size_t)(q * 32) * TC_LDS;
         mbar_wait(&acc2_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) FF_STAMP(4);
         epi_tmem_to_stage<TC_BN>(tmem_acc2, q, lane, stage);
+        if (threadIdx.x == 64) FF_STAMP(5);
         if (EPI == TC_EPI_LN) epi_rows_ln(p, stage, m0 + q * 32, lane);
         else epi_rows_store(p, stage, m0 + q * 32, 0, split, lane);
+        if (threadIdx.x == 64) FF_STAMP(6);
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 64) FF_STAMP(7);
+#undef FF_STAMP
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);

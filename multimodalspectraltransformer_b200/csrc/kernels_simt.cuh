@@ -524,25 +524,27 @@ __global__ void __launch_bounds__(128) decode_embed(const int64_t* tokens, int t
 
 // Causal self-attention of the new position over the paged KV cache; one warp per
 // (sequence, head).  Appends this step's K,V to the cache first.
-// page layout: [2 (K,V)][H][PAGE_TOKENS][DH] floats.
-template <int DH>
-__global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, float* kv_pool, const int* block_table,
+// page layout: [2 (K,V)][H][PAGE_TOKENS][DH] elements of KVT (fp32 check mode / bf16 tensor-core mode).
+template <int DH, typename KVT>
+__global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, KVT* kv_pool, const int* block_table,
                                                              int pages_per_seq, int64_t N, int H, float scale,
                                                              const int* step, float* out, __nv_bfloat16* out16) {
+    static_assert(DH == 8, "8-element key rows");
+    typedef KvRow<KVT> KV;
     const int t = *step;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= N * H) return;
     const int lane = threadIdx.x & 31;
     const int64_t n = w / H;
     const int h = (int)(w % H);
-    constexpr int PAGE_FLOATS = 2 * PAGE_TOKENS * D;
+    constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
     const int* bt = block_table + n * pages_per_seq;
     const float* row = qkv + n * (3 * D) + h * DH;
     // append K,V of position t
     if (lane < 2 * DH) {
         int kv = lane / DH, d = lane % DH;
-        float* page = kv_pool + (int64_t)bt[t / PAGE_TOKENS] * PAGE_FLOATS;
-        page[((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + d] = row[(1 + kv) * D + d];
+        KVT* page = kv_pool + (int64_t)bt[t / PAGE_TOKENS] * PAGE_ELEMS;
+        KV::st(page + ((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + d, row[(1 + kv) * D + d]);
     }
     __syncwarp();
     float q[DH];
@@ -557,8 +559,9 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, f
         int j = lane + i * 32;
         s[i] = MMT_NEG_INF;
         if (j <= t) {
-            const float* page = kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_FLOATS;
-            const float* k = page + ((0 * H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH;
+            const KVT* page = kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_ELEMS;
+            float k[DH];
+            KV::unpack(KV::ld(page + ((0 * H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH), k);
             float a = 0.f;
 #pragma unroll
             for (int d = 0; d < DH; ++d) a = fmaf(q[d], k[d], a);
@@ -576,8 +579,9 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, f
         if (j <= t) {
             float e = expf(s[i] - m);
             l += e;
-            const float* page = kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_FLOATS;
-            const float* v = page + ((1 * H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH;
+            const KVT* page = kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_ELEMS;
+            float v[DH];
+            KV::unpack(KV::ld(page + ((1 * H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH), v);
 #pragma unroll
             for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, v[d], acc[d]);
         }
@@ -595,12 +599,14 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, f
 }
 
 // Cross-attention of the new position over the (compacted) projected memory;
-// one warp per (sequence, head).  K/V layout: [2][H][rows_total][DH] (head-major).
-template <int DH>
-__global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in, const float* kv, int64_t rows_total,
+// one warp per (sequence, head).  K/V layout: [2][H][rows_total][DH] (head-major) of KVT.
+template <int DH, typename KVT>
+__global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in, const KVT* kv, int64_t rows_total,
                                                               const int* nk, const int* row_start, const float* kbias_c,
                                                               int n_cand, int64_t N, int H, float scale, float* out,
                                                               __nv_bfloat16* out16) {
+    static_assert(DH == 8, "8-element key rows");
+    typedef KvRow<KVT> KV;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= N * H) return;
     const int lane = threadIdx.x & 31;
@@ -609,22 +615,20 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
     const int64_t b = n / n_cand;
     const int cnt = nk[b];
     const int64_t r0 = row_start[b];
-    const float* Kh = kv + ((int64_t)(0 * H + h) * rows_total + r0) * DH;
-    const float* Vh = kv + ((int64_t)(1 * H + h) * rows_total + r0) * DH;
+    const KVT* Kh = kv + ((int64_t)(0 * H + h) * rows_total + r0) * DH;
+    const KVT* Vh = kv + ((int64_t)(1 * H + h) * rows_total + r0) * DH;
     const float* bias = kbias_c + r0;
     float q[DH], acc[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) { q[d] = q_in[n * D + h * DH + d] * scale; acc[d] = 0.f; }
     float m = MMT_NEG_INF, l = 0.f;
     for (int j = lane; j < cnt; j += 32) {
+        const typename KV::Raw rk = KV::ld(Kh + (int64_t)j * DH), rv = KV::ld(Vh + (int64_t)j * DH);
         float s = bias[j];
-        const float4* kp = reinterpret_cast<const float4*>(Kh + (int64_t)j * DH);
+        float k[DH];
+        KV::unpack(rk, k);
 #pragma unroll
-        for (int d4 = 0; d4 < DH / 4; ++d4) {
-            float4 k = kp[d4];
-            s = fmaf(q[d4 * 4], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
-            s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
-        }
+        for (int d = 0; d < DH; ++d) s = fmaf(q[d], k[d], s);
         if (s > m) {
             float corr = expf(m - s);
             l *= corr;
@@ -634,13 +638,10 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
         }
         float e = expf(s - m);
         l += e;
-        const float4* vp = reinterpret_cast<const float4*>(Vh + (int64_t)j * DH);
+        float v[DH];
+        KV::unpack(rv, v);
 #pragma unroll
-        for (int d4 = 0; d4 < DH / 4; ++d4) {
-            float4 v = vp[d4];
-            acc[d4 * 4] = fmaf(e, v.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(e, v.y, acc[d4 * 4 + 1]);
-            acc[d4 * 4 + 2] = fmaf(e, v.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(e, v.w, acc[d4 * 4 + 3]);
-        }
+        for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, v[d], acc[d]);
     }
     // merge the 32 per-lane partial softmaxes
     float M = warp_max(m);

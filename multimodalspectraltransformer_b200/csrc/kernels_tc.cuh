@@ -180,6 +180,25 @@ __device__ __forceinline__ void warp_sum_ilp(float (&s)[EPI_ILP]) {
     }
 }
 
+// Output row map r -> (r / S_in) * stride_b + (r % S_in) * stride_s + off, stepped row by row (one
+// integer division per warp instead of one per row: the epilogue is instruction-bound otherwise).
+struct RowStep {
+    int rs, S_in; int64_t cur, stride_s, wrap;     // wrap = stride_b - S_in * stride_s: added when rs wraps
+    template <class P>
+    __device__ __forceinline__ RowStep(const P& p, int r) {
+        S_in = p.S_in; stride_s = p.stride_s; wrap = p.stride_b - (int64_t)p.S_in * p.stride_s;
+        const int rb = r / S_in;
+        rs = r - rb * S_in;
+        cur = (int64_t)rb * p.stride_b + (int64_t)rs * p.stride_s + p.off;
+    }
+    __device__ __forceinline__ int64_t next() {     // returns the mapped row, then advances by one input row
+        const int64_t o = cur;
+        cur += stride_s;
+        if (++rs == S_in) { rs = 0; cur += wrap; }
+        return o;
+    }
+};
+
 // out[map(r)] = LN(stage[r] + bias + res[r]) * gamma + beta for the warp's 32 rows (N == 128)
 template <class P>
 __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int lane) {
@@ -189,14 +208,21 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
     const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
     const float4 be = *reinterpret_cast<const float4*>(p.beta + col);
     const int rows = min(32, p.M - row0);
+    if (rows <= 0) return;
+    const float* res = p.res + (int64_t)row0 * D + col;
+    float* const out32 = p.out_f32 ? p.out_f32 + col : nullptr;
+    __nv_bfloat16* const out16 = p.out_b16 ? p.out_b16 + col : nullptr;
+    const int64_t ld32 = p.ld_f32, ld16 = p.ld_b16;
+    const float eps = p.eps;
+    RowStep map(p, row0);
     for (int i0 = 0; i0 < rows; i0 += EPI_ILP) {
         float4 v[EPI_ILP];
         float s[EPI_ILP];
 #pragma unroll
         for (int u = 0; u < EPI_ILP; ++u) {
             const bool ok = i0 + u < rows;
-            const float4 rs = ok ? *reinterpret_cast<const float4*>(p.res + (int64_t)(row0 + i0 + u) * D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 a = *reinterpret_cast<const float4*>(stage + (size_t)((i0 + u) & 31) * TC_LDS + col);
+            const float4 rs = ok ? *reinterpret_cast<const float4*>(res + (int64_t)(i0 + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = *reinterpret_cast<const float4*>(stage + ((i0 + u) & 31) * TC_LDS + col);
             v[u] = make_float4(a.x + bias.x + rs.x, a.y + bias.y + rs.y, a.z + bias.z + rs.z, a.w + bias.w + rs.w);
             s[u] = v[u].x + v[u].y + v[u].z + v[u].w;
         }
@@ -211,12 +237,11 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
 #pragma unroll
         for (int u = 0; u < EPI_ILP; ++u) {
             if (i0 + u < rows) {
-                const int r = row0 + i0 + u;
-                const float rstd = rsqrtf(s[u] * (1.0f / D) + p.eps);
+                const float rstd = rsqrtf(s[u] * (1.0f / D) + eps);
                 const float4 o = make_float4(v[u].x * rstd * ga.x + be.x, v[u].y * rstd * ga.y + be.y, v[u].z * rstd * ga.z + be.z, v[u].w * rstd * ga.w + be.w);
-                const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow * p.ld_f32 + col) = o;
-                if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(o);
+                const int64_t orow = map.next();
+                if (out32) *reinterpret_cast<float4*>(out32 + orow * ld32) = o;
+                if (out16) *reinterpret_cast<uint2*>(out16 + orow * ld16) = pack_bf16x4(o);
             }
         }
     }
@@ -227,32 +252,40 @@ template <class P>
 __device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, int row0, int n0, int split, int lane) {
     const int col = n0 + lane * 4;
     if (col >= p.N) return;
+    const int rows = min(32, p.M - row0);
+    if (rows <= 0) return;
     const bool raw = p.splits > 1;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias && !raw) bias = *reinterpret_cast<const float4*>(p.bias + col);
     const bool relu = p.act == 1 && !raw;
-    float* out32 = p.out_f32 ? p.out_f32 + (int64_t)split * p.part_stride : nullptr;
-    const int rows = min(32, p.M - row0);
-    int kvh = 0, hd = 0;
-    if (p.head_major) { const int kv = col / D, cc = col % D; kvh = kv * p.hm_heads + cc / p.hm_dh; hd = cc % p.hm_dh; }
-    for (int i0 = 0; i0 < rows; i0 += EPI_ILP) {
-        float4 v[EPI_ILP];
-#pragma unroll
-        for (int u = 0; u < EPI_ILP; ++u) v[u] = *reinterpret_cast<const float4*>(stage + (size_t)((i0 + u) & 31) * TC_LDS + lane * 4);
-#pragma unroll
-        for (int u = 0; u < EPI_ILP; ++u) {
-            if (i0 + u >= rows) continue;
-            const int r = row0 + i0 + u;
-            float4 o = make_float4(v[u].x + bias.x, v[u].y + bias.y, v[u].z + bias.z, v[u].w + bias.w);
-            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (p.head_major) {
-                *reinterpret_cast<float4*>(out32 + ((int64_t)kvh * p.hm_rows + r) * p.hm_dh + hd) = o;
-            } else {
-                const int64_t orow = (int64_t)(r / p.S_in) * p.stride_b + (int64_t)(r % p.S_in) * p.stride_s + p.off;
-                if (out32) *reinterpret_cast<float4*>(out32 + orow * p.ld_f32 + col) = o;
-                if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + orow * p.ld_b16 + col) = pack_bf16x4(o);
-            }
+    const float* st = stage + lane * 4;
+    if (p.head_major) {
+        const int kv = col / D, cc = col % D;
+        const int kvh = kv * p.hm_heads + cc / p.hm_dh, hd = cc % p.hm_dh;
+        float* out32 = p.out_f32 ? p.out_f32 + ((int64_t)kvh * p.hm_rows + row0) * p.hm_dh + hd : nullptr;
+        __nv_bfloat16* out16 = p.out_b16 ? p.out_b16 + ((int64_t)kvh * p.hm_rows + row0) * p.hm_dh + hd : nullptr;
+        const int dh = p.hm_dh;
+#pragma unroll 4
+        for (int i = 0; i < rows; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS);
+            const float4 o = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+            if (out32) *reinterpret_cast<float4*>(out32 + (int64_t)i * dh) = o;
+            if (out16) *reinterpret_cast<uint2*>(out16 + (int64_t)i * dh) = pack_bf16x4(o);
         }
+        return;
+    }
+    float* const out32 = p.out_f32 ? p.out_f32 + (int64_t)split * p.part_stride + col : nullptr;
+    __nv_bfloat16* const out16 = p.out_b16 ? p.out_b16 + col : nullptr;
+    const int64_t ld32 = p.ld_f32, ld16 = p.ld_b16;
+    RowStep map(p, row0);
+#pragma unroll 4
+    for (int i = 0; i < rows; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS);
+        float4 o = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        const int64_t orow = map.next();
+        if (out32) *reinterpret_cast<float4*>(out32 + orow * ld32) = o;
+        if (out16) *reinterpret_cast<uint2*>(out16 + orow * ld16) = pack_bf16x4(o);
     }
 }
 
@@ -265,7 +298,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_slot;
 
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space: LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
     const int split = blockIdx.z;
