@@ -165,7 +165,7 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = os.environ.get("MMT_DEFAULT_PRECISION", "fp32")
+        precision = os.environ.get("MMT_DEFAULT_PRECISION", "bf16")      # BASELINE.json configs[1]: bf16 greedy decode
     cfg = M.default_config(device=str(dev), precision=precision, max_len=MAX_LEN)
     torch.manual_seed(0)
     model = M.MultimodalTransformer(cfg).eval()
@@ -246,14 +246,17 @@ def main():
     pk = peaks()
     total_ms = sum(v["ms"] for v in prof.values())
     dom = max(prof, key=lambda k: prof[k]["ms"])
-    esz = 4 if precision == "fp32" else 2
+    esz = 4 if precision == "fp32" else 2       # KV-cache element size (bf16 caches in the tensor-core mode)
     n_valid = int((~mask.bool()).sum().item()) if mask.dtype == torch.bool else mask.numel()
     N = B_PER_GPU
+    kv_cross = n_valid * 2 * 128 * esz + n_valid * 4                  # K and V rows of the un-masked memory keys (+ key bias)
+    kv_self = N * ((MAX_LEN + 1) / 2) * 2 * 128 * esz                 # mean over steps of the self-attention cache read
+    attn_w = (3 * 128 * 128 + 3 * 128 * 128 + 13 * 128) * 4           # in_proj, out_proj, cross q / out proj, vectors (read once)
     alg_bytes = {
-        # K and V rows of the un-masked memory keys + q in / out, per launch (one layer, one step)
-        "decode_cross_attention": n_valid * 2 * 128 * esz + n_valid * 4 + N * 128 * 4 * 2,
-        # mean over steps of the self-attention cache read + append + q in / out
-        "decode_self_attention": N * ((MAX_LEN + 1) / 2) * 2 * 128 * esz + N * 3 * 128 * 4 + N * 128 * 4,
+        # one decoder layer, one position: cross K/V + self K/V + weights + x in / x2 out (fp32 + bf16)
+        "decode_attn": kv_cross + kv_self + attn_w + N * 128 * (4 + 4 + 2),
+        "decode_cross_attention": kv_cross + N * 128 * 4 * 2,
+        "decode_self_attention": kv_self + N * 3 * 128 * 4 + N * 128 * 4,
         "bias_res_layernorm": None, "sample_tokens": None,
     }
     d = prof[dom]

@@ -26,6 +26,14 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may
+// start while its predecessor in the stream is still running.  pdl_launch_dependents() lets the successor be
+// scheduled; pdl_wait() blocks until the predecessor grid has completed and its writes are visible.  Everything a
+// kernel does before pdl_wait() must only touch data that is constant during the decode loop (weights, indices).
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // one warp, lane owns 4 consecutive columns of a 128-wide row: LayerNorm(v) * gamma + beta
 __device__ __forceinline__ float4 ln_row(float4 v, const float* gamma, const float* beta, float eps, int lane) {
     const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.0f / D);

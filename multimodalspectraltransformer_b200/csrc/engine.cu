@@ -43,6 +43,21 @@ static int check_launch(mmt_engine* e, const char* what, cudaStream_t s = nullpt
     return 0;
 }
 
+// Launch with (optionally) the programmatic-dependent-launch attribute: the kernel may be scheduled while its
+// predecessor in the stream drains; it synchronises on the predecessor itself with griddepcontrol.wait
+// (common.cuh pdl_wait).  Captured into the decode-step graph as a programmatic dependency edge.
+template <typename P>
+static void launch_kernel(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, const P& params) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, params);     // errors surface through cudaGetLastError() in check_launch
+}
+
 static int ensure_arena(mmt_engine* e, size_t bytes) {
     if (bytes <= e->arena_bytes) return 0;
     if (e->arena) { MMT_CUDA(cudaDeviceSynchronize()); MMT_CUDA(cudaFree(e->arena)); e->arena = nullptr; e->arena_bytes = 0; }
@@ -179,7 +194,7 @@ static FfnParams ffn_params(int M, int F) {
 // Fused FFN (kernels_ffn.cuh): X [M,128] bf16 (row pitch ldx); W1 [F,128] / W2 [128,F] as bf16 hi (+ lo) terms.
 // splits == 1 with epi == TC_EPI_LN: out = LN(res + b2 + FFN(X)); splits > 1: raw partials to out_f32.
 static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W1, const __nv_bfloat16* W1lo,
-                      const __nv_bfloat16* W2, const __nv_bfloat16* W2lo, int epi, cudaStream_t s) {
+                      const __nv_bfloat16* W2, const __nv_bfloat16* W2lo, int epi, cudaStream_t s, bool pdl = false) {
     if (p.M <= 0) return 0;
     MMT_TRY(tc_init(e));
     if (p.F % FF_CH || p.F > FF_MAX_F || p.F < FF_CH) MMT_FAIL("fused FFN needs d_ff % 64 == 0 and d_ff <= 2048");
@@ -197,8 +212,8 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
     }
     dim3 grid(p.splits, (p.M + TC_BM - 1) / TC_BM);
     prof_pre(e, s);
-    if (epi == TC_EPI_LN) ffn_fused_tc<TC_EPI_LN><<<grid, FF_THREADS, FF_SMEM_BYTES, s>>>(p);
-    else ffn_fused_tc<TC_EPI_STORE><<<grid, FF_THREADS, FF_SMEM_BYTES, s>>>(p);
+    if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN>, grid, dim3(FF_THREADS), FF_SMEM_BYTES, s, pdl, p);
+    else launch_kernel(ffn_fused_tc<TC_EPI_STORE>, grid, dim3(FF_THREADS), FF_SMEM_BYTES, s, pdl, p);
     return check_launch(e, "ffn_fused_tc", s, 4.0 * p.M * D * p.F);
 }
 
@@ -421,7 +436,20 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         } else {
             p.out_f32 = gr[i].X; p.out_b16 = gr[i].x16;
         }
+        if (getenv("MMT_DA_DEBUG") && ng == 1) {
+            if (!e->da_dbg) { MMT_CUDA(cudaMallocManaged(&e->da_dbg, 4096 * 16 * sizeof(long long))); memset(e->da_dbg, 0, 4096 * 16 * sizeof(long long)); }
+            p.dbg = e->da_dbg + 3000 * 16;
+        }
         MMT_TRY(launch_ffn(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), e->Wlo(gr[i].w->l1_w), e->Wb(gr[i].w->l2_w), e->Wlo(gr[i].w->l2_w), TC_EPI_LN, s));
+        if (p.dbg) {
+            MMT_CUDA(cudaStreamSynchronize(s));
+            for (int c : {0, 500}) {
+                const long long* d = e->da_dbg + (3000 + c) * 16;
+                fprintf(stderr, "enc ffn CTA %d: init %lld acc1wait %lld epi1 %lld | chunk cadence", c, d[1] - d[0], d[2] - d[1], d[3] - d[2]);
+                for (int k = 9; k < 16; ++k) fprintf(stderr, " %lld", d[k] - d[k - 1]);
+                fprintf(stderr, " | acc2->end %lld total %lld\n", d[7] - d[4], d[7] - d[0]);
+            }
+        }
     }
     return 0;
 }
@@ -700,6 +728,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     // (kernels_decode.cuh); the previous layer's FFN2 split-K partials + norm3 are folded into the
     // next kernel's prologue (the sampler's for the last layer).
     const bool fused = e->fused_decode_rows > 0 && Nw <= e->fused_decode_rows;
+    const bool pdl = fused && e->use_pdl && !e->profiling;
     int ffn_splits = 1;
     if (fused) {
         if (dh != 8 || H != DA_H) MMT_FAIL("decoder must have 16 heads of dim 8");
@@ -738,14 +767,14 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             q.x2 = b.x; q.x2_16 = bf16 ? b.x16 : nullptr; q.M = Nw; q.scale = scale; q.eps = 1e-5f;
             q.dbg = (e->da_dbg && l == 3) ? e->da_dbg : nullptr;
             prof_pre(e, s);
-            if (bf16) decode_attn<8, __nv_bfloat16><<<blocks, DA_THREADS, DA_SMEM_BYTES, s>>>(q);
-            else decode_attn<8, float><<<blocks, DA_THREADS, DA_SMEM_BYTES, s>>>(q);
+            if (bf16) launch_kernel(decode_attn<8, __nv_bfloat16>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl, q);
+            else launch_kernel(decode_attn<8, float>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl, q);
             MMT_TRY(check_launch(e, "decode_attn", s));
             if (bf16) {
                 FfnParams f = ffn_params(M, d.d_ff);
                 f.b1 = w.l1_b; f.splits = ffn_splits; f.out_f32 = b.part; f.part_stride = Nw * D;
                 f.dbg = (e->da_dbg && l == 3) ? e->da_dbg + 2048 * 16 : nullptr;
-                MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s));
+                MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s, pdl));
             } else {
                 MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
                 MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, ffn_splits));
@@ -824,7 +853,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         sp.pbias = pw.l2_b; sp.pgamma = pw.n3_w; sp.pbeta = pw.n3_b; sp.eps = 1e-5f;
     }
     prof_pre(e, s);
-    sample_tokens<<<(unsigned)((Nw + 7) / 8), 256, 0, s>>>(sp);
+    launch_kernel(sample_tokens, dim3((unsigned)((Nw + 7) / 8)), dim3(256), 0, s, pdl, sp);
     MMT_TRY(check_launch(e, "sample_tokens", s));
     return 0;
 }
@@ -981,6 +1010,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     e->desc = *desc; e->device = device; e->sm_count = prop.multiProcessorCount; e->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
     e->reg = build_registry(*desc);
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
+    if (getenv("MMT_NO_PDL")) e->use_pdl = false;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };

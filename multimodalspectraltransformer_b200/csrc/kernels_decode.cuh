@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     const bool live = n < p.M;
 #define DA_STAMP(i) do { if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + (i)] = clock64(); } while (0)
     DA_STAMP(0);
+    pdl_launch_dependents();
 
     // ---- weights of the first phase + every small vector: bulk async copies, issued before anything else
     // (one copy per lane of warp 0: a single thread issuing ~25 copies costs microseconds)
@@ -205,9 +206,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     const KVT* Kc = reinterpret_cast<const KVT*>(p.ckv) + ((int64_t)(0 * DA_H + h) * p.rows_total + r0) * DH;
     const KVT* Vc = reinterpret_cast<const KVT*>(p.ckv) + ((int64_t)(1 * DA_H + h) * p.rows_total + r0) * DH;
     constexpr int PF = 64 / (int)sizeof(KVT);     // elements per 64-byte prefetch granule
-    const int t = *p.step;
     // L2 prefetch of this warp's cross-attention K/V rows (64-byte granules; consumed in the second half)
     for (int g = lane; g * PF < cnt * DH; g += 32) { prefetch_l2(Kc + g * PF); prefetch_l2(Vc + g * PF); }
+    // ---- everything above reads only decode-loop constants; from here on the previous kernel's results are needed
+    pdl_wait();
+    const int t = *p.step;
     DA_STAMP(1);
 
     // ---- prologue: layer input

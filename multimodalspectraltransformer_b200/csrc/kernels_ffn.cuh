@@ -10,7 +10,10 @@
 //   GEMM2   acc2 (TMEM, 128 cols)     += H[c&1] . W2[:, c]^T      tcgen05.mma 128x128x16, K = 64
 //
 // software-pipelined so that GEMM1 of chunk c+1 runs on the tensor core while the epilogue warps
-// convert chunk c (acc1 and H are double-buffered; the W1/W2 chunk ring has two TMA stages).
+// convert chunk c (acc1 and H are double-buffered).  W1 and W2 chunks travel through two independent
+// two-stage TMA rings fed by two producer lanes: a W1 slot is free as soon as GEMM1 of its chunk retires,
+// so the next chunks' weights are always in flight while the tensor core works (one shared ring would hold
+// every slot until GEMM2 and expose the TMA latency once per chunk).
 // Weights are the two-term bf16 split W_hi + W_lo (kernels_tc.cuh): every MMA pass runs twice.
 //
 // grid = (splits, ceil(M/128)).  splits == 1: the epilogue is bias + residual + LayerNorm over the
@@ -18,24 +21,28 @@
 // than M/128): each CTA handles F/64/splits chunks and writes a raw fp32 partial; the consumer
 // (decode_attn_self / sample_tokens prologue, or bias_res_layernorm) reduces them in a fixed order.
 //
-// warp 0: TMA producer (one lane) | warp 1: MMA issuer (one lane) + TMEM alloc (256 cols) | warps 2-5: epilogue
+// warp 0: TMA producers (two lanes) | warp 1: MMA issuer (one lane) + TMEM alloc (256 cols) | warps 2-9: epilogue
+// (two epilogue warps per TMEM lane quarter: the acc1 -> H conversion paces the chunk loop otherwise)
 #pragma once
 #include "kernels_tc.cuh"
 
 namespace mmt {
 
 constexpr int FF_CH = 64;                                  // hidden columns per chunk
-constexpr int FF_THREADS = 192;
+constexpr int FF_THREADS = TC_THREADS;                     // 2 + 8 epilogue warps
 constexpr int FF_X_BYTES = 2 * TC_SLAB_BYTES;              // X: two K slabs of [128 rows x 64]
 constexpr int FF_H_BYTES = TC_SLAB_BYTES;                  // one H buffer: [128 rows x 64] bf16
 constexpr int FF_W1_SLAB = FF_CH * TC_BK * 2;              // 8 KB: [64 rows x 64 K]
-constexpr int FF_STAGE_BYTES = 4 * FF_W1_SLAB + 2 * TC_SLAB_BYTES;   // W1 hi(2 slabs) + lo(2) + W2 hi + W2 lo = 64 KB
+constexpr int FF_W1_STAGE = 4 * FF_W1_SLAB;                // W1 chunk: hi (2 K slabs) + lo (2 K slabs) = 32 KB
+constexpr int FF_W2_STAGE = 2 * TC_SLAB_BYTES;             // W2 chunk: hi + lo slabs of [128 rows x 64 K] = 32 KB
+constexpr int FF_STAGE_BYTES = FF_W1_STAGE + FF_W2_STAGE;
 constexpr int FF_OFF_H = FF_X_BYTES;
-constexpr int FF_OFF_W = FF_OFF_H + 2 * FF_H_BYTES;
+constexpr int FF_OFF_W = FF_OFF_H + 2 * FF_H_BYTES;        // W1 ring (2 stages), then W2 ring (2 stages)
+constexpr int FF_OFF_W2 = FF_OFF_W + 2 * FF_W1_STAGE;
 constexpr int FF_OFF_B1 = FF_OFF_W + 2 * FF_STAGE_BYTES;   // 192 KB
 constexpr int FF_MAX_F = 2048;
 constexpr int FF_SMEM_BYTES = FF_OFF_B1 + FF_MAX_F * 4 + 1024;
-static_assert(2 * FF_STAGE_BYTES >= TC_STAGING_BYTES, "final staging tile aliases the weight ring");
+static_assert(2 * FF_STAGE_BYTES >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
 
 struct FfnParams {
     CUtensorMap tmX;                 // X  [M,128] bf16, box {64,128}
@@ -62,13 +69,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int EPI>
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t x_full, w_full[2], w_empty[2], acc1_full[2], h_full[2], h_empty[2], acc2_full;
+    __shared__ __align__(8) uint64_t x_full, w1_full[2], w1_empty[2], w2_full[2], w2_empty[2], acc1_full[2], h_full[2], h_empty[2], acc2_full;
     __shared__ uint32_t tmem_slot;
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space
     uint8_t* sX = smem;
     uint8_t* sH = smem + FF_OFF_H;
-    uint8_t* sW = smem + FF_OFF_W;
+    uint8_t* sW = smem + FF_OFF_W;       // W1 ring; also the final staging tile
+    uint8_t* sW2 = smem + FF_OFF_W2;
     float* b1s = reinterpret_cast<float*>(smem + FF_OFF_B1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, m0 = blockIdx.y * TC_BM;
@@ -77,20 +85,22 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
 #define FF_STAMP(i) do { if (p.dbg) p.dbg[cta * 16 + (i)] = clock64(); } while (0)
     if (threadIdx.x == 64) FF_STAMP(0);
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW1); tma_prefetch_desc(&p.tmW2);
         if (p.wsplit) { tma_prefetch_desc(&p.tmW1lo); tma_prefetch_desc(&p.tmW2lo); }
         mbar_init(&x_full, 1); mbar_init(&acc2_full, 1);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); mbar_init(&acc1_full[s], 1);
-            mbar_init(&h_full[s], 128); mbar_init(&h_empty[s], 1);
+            mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1);
+            mbar_init(&acc1_full[s], 1);
+            mbar_init(&h_full[s], TC_EPI_WARPS * 32); mbar_init(&h_empty[s], 1);
         }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, 256);
     if (warp >= 2)
-        for (int i = threadIdx.x - 64; i < n * FF_CH; i += 128) b1s[i] = p.b1[c0 * FF_CH + i];
+        for (int i = threadIdx.x - 64; i < n * FF_CH; i += TC_EPI_WARPS * 32) b1s[i] = p.b1[c0 * FF_CH + i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -99,23 +109,39 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     if (threadIdx.x == 64) FF_STAMP(1);
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(&x_full, FF_X_BYTES);
-            tma_load_2d(sX, &p.tmX, &x_full, 0, m0);
-            tma_load_2d(sX + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0);
+        if (lane == 0) {                  // W1 ring (decode-loop constants only: runs ahead of the PDL wait)
             for (int i = 0; i < n; ++i) {
                 const int s = i & 1, c = c0 + i;
-                mbar_wait(&w_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&w_full[s], p.wsplit ? FF_STAGE_BYTES : FF_STAGE_BYTES / 2);
-                uint8_t* w = sW + (size_t)s * FF_STAGE_BYTES;
-                tma_load_2d(w, &p.tmW1, &w_full[s], 0, c * FF_CH);
-                tma_load_2d(w + FF_W1_SLAB, &p.tmW1, &w_full[s], TC_BK, c * FF_CH);
-                tma_load_2d(w + 4 * FF_W1_SLAB, &p.tmW2, &w_full[s], c * FF_CH, 0);
+                mbar_wait(&w1_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&w1_full[s], p.wsplit ? FF_W1_STAGE : FF_W1_STAGE / 2);
+                uint8_t* w = sW + (size_t)s * FF_W1_STAGE;
+                tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
+                tma_load_2d(w + FF_W1_SLAB, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
                 if (p.wsplit) {
-                    tma_load_2d(w + 2 * FF_W1_SLAB, &p.tmW1lo, &w_full[s], 0, c * FF_CH);
-                    tma_load_2d(w + 3 * FF_W1_SLAB, &p.tmW1lo, &w_full[s], TC_BK, c * FF_CH);
-                    tma_load_2d(w + 4 * FF_W1_SLAB + TC_SLAB_BYTES, &p.tmW2lo, &w_full[s], c * FF_CH, 0);
+                    tma_load_2d(w + 2 * FF_W1_SLAB, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
+                    tma_load_2d(w + 3 * FF_W1_SLAB, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
                 }
+            }
+        } else if (lane == 1) {           // W2 ring, and X once the producer of X has finished (PDL)
+            for (int i = 0; i < n; ++i) {
+                const int s = i & 1, c = c0 + i;
+                if (i == min(n, 2)) {
+                    pdl_wait();
+                    mbar_arrive_expect_tx(&x_full, FF_X_BYTES);
+                    tma_load_2d(sX, &p.tmX, &x_full, 0, m0);
+                    tma_load_2d(sX + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0);
+                }
+                mbar_wait(&w2_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&w2_full[s], p.wsplit ? FF_W2_STAGE : FF_W2_STAGE / 2);
+                uint8_t* w = sW2 + (size_t)s * FF_W2_STAGE;
+                tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
+                if (p.wsplit) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
+            }
+            if (n <= 2) {                 // short loops never reached the in-loop wait
+                pdl_wait();
+                mbar_arrive_expect_tx(&x_full, FF_X_BYTES);
+                tma_load_2d(sX, &p.tmX, &x_full, 0, m0);
+                tma_load_2d(sX + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0);
             }
         }
     } else if (warp == 1) {
@@ -126,10 +152,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             // acc2 += H[j&1] . W2[:, chunk j]^T
             auto gemm2 = [&](int j) {
                 const int b = j & 1;
+                mbar_wait(&w2_full[b], ((uint32_t)j >> 1) & 1u);
                 mbar_wait(&h_full[b], ((uint32_t)j >> 1) & 1u);
                 tc_fence_after();
                 const uint64_t adesc = umma_desc_sw128(smem_u32(sH + (size_t)b * FF_H_BYTES));
-                const uint32_t w2 = smem_u32(sW + (size_t)b * FF_STAGE_BYTES + 4 * FF_W1_SLAB);
+                const uint32_t w2 = smem_u32(sW2 + (size_t)b * FF_W2_STAGE);
                 const uint64_t bdesc = umma_desc_sw128(w2);
 #pragma unroll
                 for (int k = 0; k < FF_CH / 16; ++k)
@@ -140,15 +167,15 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                     for (int k = 0; k < FF_CH / 16; ++k)
                         umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc2 + (uint64_t)(2 * k), idesc2, 1u);
                 }
-                umma_commit(&w_empty[b]);      // weight stage b reusable
+                umma_commit(&w2_empty[b]);     // W2 stage b reusable
                 umma_commit(&h_empty[b]);      // H buffer b reusable
             };
             mbar_wait(&x_full, 0);
             for (int i = 0; i < n; ++i) {
                 const int s = i & 1;
-                mbar_wait(&w_full[s], ((uint32_t)i >> 1) & 1u);
+                mbar_wait(&w1_full[s], ((uint32_t)i >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t w1 = smem_u32(sW + (size_t)s * FF_STAGE_BYTES);
+                const uint32_t w1 = smem_u32(sW + (size_t)s * FF_W1_STAGE);
                 const uint32_t acc1 = tmem_base + (uint32_t)(s * FF_CH);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
@@ -165,53 +192,60 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                     }
                 }
                 umma_commit(&acc1_full[s]);
+                umma_commit(&w1_empty[s]);     // W1 stage s reusable as soon as this GEMM1 retires
                 if (i > 0) gemm2(i - 1);
             }
             gemm2(n - 1);
             umma_commit(&acc2_full);
         }
     } else {
-        // ---------------- epilogue warps: warp (id % 4) owns TMEM lanes [32*(id%4), +32); thread = row
-        const int q = warp & 3;
+        // ---------------- epilogue warps: warp (id % 4) owns TMEM lanes [32*(id%4), +32); thread = row;
+        // the two warps of a quarter split the chunk's 64 columns
+        const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         for (int i = 0; i < n; ++i) {
             const int b = i & 1;
             mbar_wait(&acc1_full[b], ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
             if (threadIdx.x == 64 && i == 0) FF_STAMP(2);
-            uint32_t pk[FF_CH / 2];
-#pragma unroll
-            for (int c = 0; c < FF_CH / 32; ++c) {
+            uint32_t pk[16];
+            {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * FF_CH + c * 32), r);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * FF_CH + hf * 32), r);
                 tmem_ld_wait();
-                const float* bb = b1s + i * FF_CH + c * 32;
+                const float* bb = b1s + i * FF_CH + hf * 32;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float lo = fmaxf(__uint_as_float(r[2 * j]) + bb[2 * j], 0.f);
                     const float hi = fmaxf(__uint_as_float(r[2 * j + 1]) + bb[2 * j + 1], 0.f);
                     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-                    pk[c * 16 + j] = *reinterpret_cast<uint32_t*>(&v);
+                    pk[j] = *reinterpret_cast<uint32_t*>(&v);
                 }
             }
             mbar_wait(&h_empty[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
             uint8_t* hrow = sH + (size_t)b * FF_H_BYTES + (size_t)row * 128;
 #pragma unroll
-            for (int cj = 0; cj < 8; ++cj)      // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
-                *reinterpret_cast<uint4*>(hrow + ((cj ^ (row & 7)) << 4)) = make_uint4(pk[4 * cj], pk[4 * cj + 1], pk[4 * cj + 2], pk[4 * cj + 3]);
+            for (int c4 = 0; c4 < 4; ++c4) {    // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
+                const int cj = hf * 4 + c4;
+                *reinterpret_cast<uint4*>(hrow + ((cj ^ (row & 7)) << 4)) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             tc_fence_before();
             mbar_arrive(&h_full[b]);
             if (threadIdx.x == 64 && i == 0) FF_STAMP(3);
+            if (threadIdx.x == 64 && i >= 8 && i < 16) FF_STAMP(i);     // steady-state chunk cadence
         }
-        float* stage = reinterpret_cast<float*>(sW) + (size_t)(q * 32) * TC_LDS;
+        float* stage_q = reinterpret_cast<float*>(sW) + (q * 32) * TC_LDS;
+        pdl_wait();                            // (already satisfied: acc2 depends on X) orders the stores below explicitly
         mbar_wait(&acc2_full, 0);
         tc_fence_after();
         if (threadIdx.x == 64) FF_STAMP(4);
-        epi_tmem_to_stage<TC_BN>(tmem_acc2, q, lane, stage);
+        epi_tmem_to_stage<TC_BN>(tmem_acc2, q, hf, lane, stage_q);
+        epi_bar_sync();
         if (threadIdx.x == 64) FF_STAMP(5);
-        if (EPI == TC_EPI_LN) epi_rows_ln(p, stage, m0 + q * 32, lane);
-        else epi_rows_store(p, stage, m0 + q * 32, 0, split, lane);
+        const float* st = stage_q + (hf * 16) * TC_LDS;
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane);
+        else epi_rows_store(p, st, m0 + q * 32 + hf * 16, 16, 0, split, lane);
         if (threadIdx.x == 64) FF_STAMP(6);
     }
     tc_fence_before();

@@ -688,12 +688,14 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
     __shared__ float Ws[VOCAB_MAX * (D + 1)];
     __shared__ __align__(16) float xs[8][D];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     // fc_out weights -> padded smem rows (independent of the step: issued before anything else)
     for (int i = threadIdx.x; i < p.V * (D / 4); i += blockDim.x) {
         const float4 w = *reinterpret_cast<const float4*>(p.W + (int64_t)i * 4);
         float* dst = Ws + (i / (D / 4)) * (D + 1) + (i % (D / 4)) * 4;
         dst[0] = w.x; dst[1] = w.y; dst[2] = w.z; dst[3] = w.w;
     }
+    pdl_wait();
     const int t = p.ctl.step ? *p.ctl.step : 0;
     const int64_t n = (int64_t)blockIdx.x * 8 + warp;
     if (n < p.N) {

@@ -8,10 +8,12 @@
 // twice per K slab on the same A slab, which removes the weight-rounding error (the dominant
 // term of the bf16 logit error, DESIGN.md "bf16 numerics") for no extra HBM traffic.
 //
-// One CTA = one 128x128 output tile (UMMA 128x128x16, cta_group::1), 6 warps:
+// One CTA = one 128x128 output tile (UMMA 128x128x16, cta_group::1), 10 warps:
 //   warp 0     TMA producer   (one lane): K slabs of 64 elements (=128 B swizzle rows)
 //   warp 1     MMA issuer     (one lane) + TMEM allocation (128 columns)
-//   warps 2-5  epilogue: TMEM -> registers -> padded smem tile -> coalesced global I/O
+//   warps 2-9  epilogue: TMEM -> registers -> padded smem tile -> coalesced global I/O
+//              (two warps per TMEM lane quarter: with one warp per scheduler the epilogue is a pure
+//              latency chain and paces the whole kernel)
 // Several CTAs are resident per SM (68 KB smem at K=128), so one tile's epilogue overlaps
 // the TMA/MMA of its neighbours without a persistent scheduler.
 #pragma once
@@ -27,7 +29,8 @@ constexpr int TC_STAGE_BYTES = 2 * TC_SLAB_BYTES;          // A slab + W slab
 constexpr int TC_STAGE_BYTES_WSPLIT = 3 * TC_SLAB_BYTES;   // A slab + W_hi slab + W_lo slab
 constexpr int TC_LDS = TC_BN + 4;                          // padded fp32 staging row (conflict-free float4)
 constexpr int TC_STAGING_BYTES = TC_BM * TC_LDS * 4;       // 67,584 B
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + TC_EPI_WARPS * 32;
 constexpr int TC_MAX_STAGES = 4;
 
 enum { TC_EPI_STORE = 0, TC_EPI_LN = 1 };
@@ -156,21 +159,25 @@ __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
 // independent rows overlap (a single row's chain is ~500 cycles of pure latency).
 constexpr int EPI_ILP = 8;
 
+// Epilogue warp e = warp - 2 owns TMEM lane quarter q = warp % 4 (hardware rule) and half hf = e / 4:
+// it moves the hf-th half of the accumulator columns of its 32 rows into the staging tile, and after
+// epi_bar_sync() processes rows [16*hf, 16*hf + 16) of the quarter.
 template <int NCOLS>
-__device__ __forceinline__ void epi_tmem_to_stage(uint32_t tmem_acc, int q, int lane, float* stage) {
+__device__ __forceinline__ void epi_tmem_to_stage(uint32_t tmem_acc, int q, int hf, int lane, float* stage_q) {
 #pragma unroll
-    for (int c = 0; c < NCOLS / 32; ++c) {
+    for (int cc = 0; cc < NCOLS / 64; ++cc) {
+        const int c = hf * (NCOLS / 64) + cc;
         uint32_t r[32];
         tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
-        float* dst = stage + (size_t)lane * TC_LDS + c * 32;
+        float* dst = stage_q + lane * TC_LDS + c * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(dst + 4 * j) =
                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     }
-    __syncwarp();
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory"); }
 
 __device__ __forceinline__ void warp_sum_ilp(float (&s)[EPI_ILP]) {
 #pragma unroll
@@ -201,13 +208,13 @@ struct RowStep {
 
 // out[map(r)] = LN(stage[r] + bias + res[r]) * gamma + beta for the warp's 32 rows (N == 128)
 template <class P>
-__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int lane) {
+__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int nrows, int lane) {
     const int col = lane * 4;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + col);
     const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
     const float4 be = *reinterpret_cast<const float4*>(p.beta + col);
-    const int rows = min(32, p.M - row0);
+    const int rows = min(nrows, p.M - row0);
     if (rows <= 0) return;
     const float* res = p.res + (int64_t)row0 * D + col;
     float* const out32 = p.out_f32 ? p.out_f32 + col : nullptr;
@@ -222,7 +229,7 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
         for (int u = 0; u < EPI_ILP; ++u) {
             const bool ok = i0 + u < rows;
             const float4 rs = ok ? *reinterpret_cast<const float4*>(res + (int64_t)(i0 + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 a = *reinterpret_cast<const float4*>(stage + ((i0 + u) & 31) * TC_LDS + col);
+            const float4 a = *reinterpret_cast<const float4*>(stage + (i0 + u) * TC_LDS + col);
             v[u] = make_float4(a.x + bias.x + rs.x, a.y + bias.y + rs.y, a.z + bias.z + rs.z, a.w + bias.w + rs.w);
             s[u] = v[u].x + v[u].y + v[u].z + v[u].w;
         }
@@ -249,10 +256,10 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
 
 // out[map(r)][n0 + ...] = act(stage[r] + bias) for the warp's 32 rows; split > 0 partials are raw sums
 template <class P>
-__device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, int row0, int n0, int split, int lane) {
+__device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, int row0, int nrows, int n0, int split, int lane) {
     const int col = n0 + lane * 4;
     if (col >= p.N) return;
-    const int rows = min(32, p.M - row0);
+    const int rows = min(nrows, p.M - row0);
     if (rows <= 0) return;
     const bool raw = p.splits > 1;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -362,14 +369,16 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
             umma_commit(&tmem_full_bar);               // accumulator complete
         }
     } else {
-        // ---------------- epilogue: 4 warps, warp (id % 4) owns TMEM lanes [32*(id%4), +32)
-        const int q = warp & 3;
-        float* stage = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * TC_LDS;
+        // ---------------- epilogue: 8 warps, warp (id % 4) owns TMEM lanes [32*(id%4), +32), two warps per quarter
+        const int q = warp & 3, hf = (warp - 2) >> 2;
+        float* stage_q = reinterpret_cast<float*>(smem) + (q * 32) * TC_LDS;
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
-        epi_tmem_to_stage<TC_BN>(tmem_base, q, lane, stage);
-        if (EPI == TC_EPI_LN) epi_rows_ln(p, stage, m0 + q * 32, lane);
-        else epi_rows_store(p, stage, m0 + q * 32, n0, split, lane);
+        epi_tmem_to_stage<TC_BN>(tmem_base, q, hf, lane, stage_q);
+        epi_bar_sync();
+        const float* st = stage_q + (hf * 16) * TC_LDS;
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane);
+        else epi_rows_store(p, st, m0 + q * 32 + hf * 16, 16, n0, split, lane);
     }
     tc_fence_before();
     __syncthreads();
