@@ -12,6 +12,7 @@ namespace mmt {
 constexpr int D = 128;            // d_model (config_V8 hidden_size); the kernels are specialised for it
 constexpr int VOCAB_MAX = 64;     // out_size 43 <= 64 (two values per lane in the sampler)
 constexpr int PAGE_TOKENS = 16;   // tokens per self-attention KV page
+constexpr int CP_SMAX = 200;      // row stride of the ragged-encoder index maps (>= longest modality sequence, 193)
 
 #define MMT_NEG_INF (-INFINITY)
 

@@ -5,6 +5,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_decode.cuh"
 #include "kernels_ffn.cuh"
+#include "kernels_compact.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -317,6 +318,8 @@ struct EncGroupRun {
     float* out; int64_t stride_b, stride_s, off;
     // tensor-core mode: bf16 copies of X / attention output / FFN hidden, bf16 copy of `out`
     __nv_bfloat16 *x16, *att16, *h16, *out16;
+    // ragged encoder (kernels_compact.cuh): per-sequence row ranges, key-list stride, explicit output rows
+    const int *row_start, *cnt; int kstride; const int* out_rows;
 };
 
 static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
@@ -332,7 +335,10 @@ static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         AttnParams p;
         memset(&p, 0, sizeof(p));
         p.scale = 1.0f / sqrtf((float)dh);
-        for (int i = 0; i < ng; ++i) { p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = gr[i].att; p.g[i].S = gr[i].S; }
+        for (int i = 0; i < ng; ++i) {
+            p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = gr[i].att; p.g[i].S = gr[i].S;
+            p.g[i].row_start = gr[i].row_start; p.g[i].cnt = gr[i].cnt; p.g[i].kstride = gr[i].kstride;
+        }
         dim3 grid(heads, Bc, ng);
         size_t smem = (size_t)maxS * (2 * dh + 1) * sizeof(float);
         int threads = maxS > 256 ? 256 : 128;
@@ -379,7 +385,7 @@ static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
             LnGroup& g = q.g[i];
             g.part = gr[i].part; g.bias = gr[i].w->l2_b; g.res = gr[i].X; g.gamma = gr[i].w->n2_w; g.beta = gr[i].w->n2_b;
             g.out = gr[i].out ? gr[i].out : gr[i].X; g.M = gr[i].rows;
-            if (gr[i].out) { g.S_in = gr[i].S; g.stride_b = gr[i].stride_b; g.stride_s = gr[i].stride_s; g.off = gr[i].off; }
+            if (gr[i].out) { g.S_in = gr[i].S; g.stride_b = gr[i].stride_b; g.stride_s = gr[i].stride_s; g.off = gr[i].off; g.out_rows = gr[i].out_rows; }
             else { g.S_in = gr[i].rows > 0 ? gr[i].rows : 1; g.stride_b = 0; g.stride_s = 1; g.off = 0; }
         }
         MMT_TRY(launch_ln(e, q, ng, maxM, s));
@@ -402,7 +408,10 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         AttnParams p;
         memset(&p, 0, sizeof(p));
         p.scale = 1.0f / sqrtf((float)dh);
-        for (int i = 0; i < ng; ++i) { p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = nullptr; p.g[i].out16 = gr[i].att16; p.g[i].S = gr[i].S; }
+        for (int i = 0; i < ng; ++i) {
+            p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = nullptr; p.g[i].out16 = gr[i].att16; p.g[i].S = gr[i].S;
+            p.g[i].row_start = gr[i].row_start; p.g[i].cnt = gr[i].cnt; p.g[i].kstride = gr[i].kstride;
+        }
         dim3 grid(heads, Bc, ng);
         size_t smem = (size_t)maxS * (2 * dh + 1) * sizeof(float);
         int threads = maxS > 256 ? 256 : 128;
@@ -432,24 +441,204 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         p.b1 = gr[i].w->l1_b; p.bias = gr[i].w->l2_b; p.res = gr[i].X; p.gamma = gr[i].w->n2_w; p.beta = gr[i].w->n2_b;
         if (gr[i].out || gr[i].out16) {
             p.out_f32 = gr[i].out; p.out_b16 = gr[i].out16;
-            p.S_in = gr[i].S; p.stride_b = gr[i].stride_b; p.stride_s = gr[i].stride_s; p.off = gr[i].off;
+            p.S_in = gr[i].S; p.stride_b = gr[i].stride_b; p.stride_s = gr[i].stride_s; p.off = gr[i].off; p.out_rows = gr[i].out_rows;
         } else {
             p.out_f32 = gr[i].X; p.out_b16 = gr[i].x16;
         }
-        if (getenv("MMT_DA_DEBUG") && ng == 1) {
-            if (!e->da_dbg) { MMT_CUDA(cudaMallocManaged(&e->da_dbg, 4096 * 16 * sizeof(long long))); memset(e->da_dbg, 0, 4096 * 16 * sizeof(long long)); }
-            p.dbg = e->da_dbg + 3000 * 16;
-        }
         MMT_TRY(launch_ffn(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), e->Wlo(gr[i].w->l1_w), e->Wb(gr[i].w->l2_w), e->Wlo(gr[i].w->l2_w), TC_EPI_LN, s));
-        if (p.dbg) {
-            MMT_CUDA(cudaStreamSynchronize(s));
-            for (int c : {0, 500}) {
-                const long long* d = e->da_dbg + (3000 + c) * 16;
-                fprintf(stderr, "enc ffn CTA %d: init %lld acc1wait %lld epi1 %lld | chunk cadence", c, d[1] - d[0], d[2] - d[1], d[3] - d[2]);
-                for (int k = 9; k < 16; ++k) fprintf(stderr, " %lld", d[k] - d[k - 1]);
-                fprintf(stderr, " | acc2->end %lld total %lld\n", d[7] - d[4], d[7] - d[0]);
-            }
+    }
+    return 0;
+}
+
+// Ragged encoder (kernels_compact.cuh): the same computation on the distinct token rows only.  Returns 0 on
+// success, 1 on error, 2 when the batch does not qualify (padded rows with differing raw inputs) and the caller
+// must take the dense path.
+static int encode_chunk_compact(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, int B_total, const ModeLayout& L,
+                                float* d_memory, float* d_embedding_src, float* d_key_bias, uint8_t* d_pad_mask, bool bf16, cudaStream_t s) {
+    const mmt_model_desc& d = e->desc;
+    const int P = d.pad_points;
+    int maxS = 0;
+    for (int m = 0; m < 5; ++m) maxS = std::max(maxS, L.S_m[m]);
+    if (maxS > CP_SMAX) return 2;
+    // ---- workspace (activation buffers sized for the dense row counts: upper bounds known without a sync)
+    Arena a;
+    struct { int *cnt, *nkeys, *d2c, *kidx, *flag, *row_start, *cstart, *moff, *nk_c, *ccnt, *totals, *out_rows, *kidx_c; } ix;
+    float *X[5], *Xc, *ir_emb, *QKV, *ATT, *PART, *H, *key_bias_l; uint8_t* pad_mask_l;
+    __nv_bfloat16 *X16[5], *Xc16, *ATT16;
+    const int64_t R = (int64_t)Bc * L.S_total;
+    auto plan = [&]() {
+        ix.cnt = a.get<int>(5 * Bc); ix.nkeys = a.get<int>(5 * Bc);
+        ix.d2c = a.get<int>((size_t)5 * Bc * CP_SMAX); ix.kidx = a.get<int>((size_t)5 * Bc * CP_SMAX);
+        ix.flag = a.get<int>(1); ix.row_start = a.get<int>(5 * (Bc + 1)); ix.cstart = a.get<int>(Bc + 1);
+        ix.moff = a.get<int>(5 * Bc); ix.nk_c = a.get<int>(Bc); ix.ccnt = a.get<int>(Bc); ix.totals = a.get<int>(8);
+        ix.out_rows = a.get<int>((size_t)5 * Bc * maxS); ix.kidx_c = a.get<int>(R);
+        int64_t rows_mod = 0;
+        for (int m = 0; m < 5; ++m) { X[m] = a.get<float>((size_t)Bc * L.S_m[m] * D); rows_mod += (int64_t)Bc * L.S_m[m]; }
+        const int64_t rmax = std::max(rows_mod, R);
+        Xc = a.get<float>(R * D);
+        ir_emb = a.get<float>((size_t)Bc * D);
+        QKV = a.get<float>(rmax * 3 * D);
+        key_bias_l = d_key_bias ? nullptr : a.get<float>(R);
+        pad_mask_l = d_pad_mask ? nullptr : a.get<uint8_t>(R);
+        if (bf16) {
+            ATT = PART = H = nullptr;
+            for (int m = 0; m < 5; ++m) X16[m] = a.get<__nv_bfloat16>((size_t)Bc * L.S_m[m] * D);
+            Xc16 = a.get<__nv_bfloat16>(R * D);
+            ATT16 = a.get<__nv_bfloat16>(rmax * D);
+        } else {
+            ATT = a.get<float>(rmax * D); PART = a.get<float>(rmax * D); H = a.get<float>(rmax * d.d_ff);
+            for (int m = 0; m < 5; ++m) X16[m] = nullptr;
+            Xc16 = ATT16 = nullptr;
         }
+    };
+    a.plan = true; plan();
+    MMT_TRY(ensure_arena(e, a.off));
+    a.plan = false; a.base = e->arena; a.cap = e->arena_bytes; a.off = 0; plan();
+    float* key_bias = d_key_bias ? d_key_bias + (int64_t)b0 * L.S_total : key_bias_l;
+    uint8_t* pad_mask = d_pad_mask ? d_pad_mask + (int64_t)b0 * L.S_total : pad_mask_l;
+
+    const float* srcs[4] = {in.d_src_1H, in.d_src_13C, in.d_src_HSQC, in.d_src_COSY};
+    const float* masks[4] = {in.d_mask_1H, in.d_mask_13C, in.d_mask_HSQC, in.d_mask_COSY};
+    for (int m = 0; m < 4; ++m) if (!srcs[m] || !masks[m]) MMT_FAIL("spectra pointer missing for a modality in training_mode");
+    if (!in.d_src_IR) MMT_FAIL("src_IR missing");
+    if (L.has_MF && (!in.d_src_MF || !in.d_mask_MF)) MMT_FAIL("src_MF / mask_MF missing");
+    if (L.has_MS && (!in.d_src_MS || !in.d_mask_MS)) MMT_FAIL("src_MS / mask_MS missing");
+    if (L.has_MW && !in.d_trg_MW) MMT_FAIL("trg_MW missing");
+
+    // ---- index maps, then one small device-to-host read of the row totals
+    {
+        MMT_CUDA(cudaMemsetAsync(ix.flag, 0, sizeof(int), s));
+        CompactParams p;
+        memset(&p, 0, sizeof(p));
+        for (int m = 0; m < 4; ++m) {
+            const int cols = (m == 1) ? 1 : 2;
+            p.mask[m] = masks[m] + (int64_t)b0 * P; p.src[m] = srcs[m] + (int64_t)b0 * P * cols; p.cols[m] = cols;
+        }
+        if (L.has_MF) { p.mask_MF = in.d_mask_MF + (int64_t)b0 * P; p.src_MF = in.d_src_MF + (int64_t)b0 * P; }
+        if (L.has_MS) { p.mask_MS = in.d_mask_MS + (int64_t)b0 * P; p.src_MS = in.d_src_MS + (int64_t)b0 * P; }
+        for (int m = 0; m < 5; ++m) { p.present[m] = 1; p.n_x[m] = L.n_x[m]; }
+        p.has_MF = L.has_MF; p.has_MS = L.has_MS; p.has_MW = L.has_MW; p.P = P; p.B = Bc;
+        p.cnt = ix.cnt; p.nkeys = ix.nkeys; p.d2c = ix.d2c; p.kidx = ix.kidx; p.flag = ix.flag;
+        prof_pre(e, s);
+        compact_index<<<dim3(Bc, 5), 32, 0, s>>>(p);
+        MMT_TRY(check_launch(e, "compact_index", s));
+        CompactScanParams q;
+        q.cnt = ix.cnt; q.nkeys = ix.nkeys; q.B = Bc; q.row_start = ix.row_start; q.cstart = ix.cstart; q.moff = ix.moff;
+        q.nk_c = ix.nk_c; q.ccnt = ix.ccnt; q.totals = ix.totals; q.flag = ix.flag;
+        prof_pre(e, s);
+        compact_scan<<<1, 256, 0, s>>>(q);
+        MMT_TRY(check_launch(e, "compact_scan", s));
+        CompactCrossParams c;
+        c.cnt = ix.cnt; c.nkeys = ix.nkeys; c.kidx = ix.kidx; c.row_start = ix.row_start; c.cstart = ix.cstart; c.moff = ix.moff; c.B = Bc;
+        c.out_rows = ix.out_rows; c.out_rows_stride = (int64_t)Bc * maxS; c.kidx_c = ix.kidx_c; c.kc_stride = L.S_total;
+        prof_pre(e, s);
+        compact_cross_index<<<Bc, 32, 0, s>>>(c);
+        MMT_TRY(check_launch(e, "compact_cross_index", s));
+        MMT_CUDA(cudaMemcpyAsync(e->h_pinned, ix.totals, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MMT_CUDA(cudaStreamSynchronize(s));
+    }
+    int rows_m[5];
+    for (int m = 0; m < 5; ++m) rows_m[m] = e->h_pinned[m];
+    const int rows_c = e->h_pinned[5];
+    if (e->h_pinned[6] != 0) return 2;
+
+    // ---- IR projection 1000 -> 128 (+ReLU)
+    {
+        GemmParams p = gemm_params(D, d.ir_bins, D, 1);
+        p.g[0].A = in.d_src_IR + (int64_t)b0 * d.ir_bins; p.g[0].lda = d.ir_bins;
+        p.g[0].W = e->W(std::string(kEmbedKeys[4]) + ".weight"); p.g[0].bias = e->W(std::string(kEmbedKeys[4]) + ".bias");
+        p.g[0].C = ir_emb; p.g[0].M = Bc;
+        MMT_TRY(launch_gemm(e, p, 1, Bc, s));
+    }
+    {   // embed: dense key bias / pad mask / embedding_src outputs, compact X rows
+        EmbedParams p;
+        memset(&p, 0, sizeof(p));
+        const float* esrc[5] = {srcs[0], srcs[1], srcs[2], srcs[3], ir_emb};
+        for (int m = 0; m < 5; ++m) {
+            EmbedGroup& g = p.g[m];
+            g.present = 1; g.kind = (m == 4) ? 2 : (m == 1 ? 1 : 0);
+            g.S_m = L.S_m[m]; g.n_x = L.n_x[m]; g.off = L.off[m]; g.blank_is_ir = (m == 4);
+            if (m < 4) {
+                const int cols = (m == 1) ? 1 : 2;
+                g.src = esrc[m] + (int64_t)b0 * P * cols; g.mask = masks[m] + (int64_t)b0 * P;
+                g.W = e->W(std::string(kEmbedKeys[m]) + ".weight"); g.b = e->W(std::string(kEmbedKeys[m]) + ".bias");
+            } else {
+                g.src = ir_emb;
+            }
+            g.X = X[m]; g.kbias = nullptr;
+            g.d2c = ix.d2c + (size_t)m * Bc * CP_SMAX; g.row_start = ix.row_start + m * (Bc + 1);
+        }
+        p.has_MF = L.has_MF; p.has_MS = L.has_MS; p.has_MW = L.has_MW;
+        if (L.has_MF) { p.src_MF = in.d_src_MF + (int64_t)b0 * P; p.mask_MF = in.d_mask_MF + (int64_t)b0 * P; p.E_MF = e->W("linear_embedding_MF.embedding.weight"); p.mf_vocab = d.mf_vocab; }
+        if (L.has_MS) { p.src_MS = in.d_src_MS + (int64_t)b0 * P; p.mask_MS = in.d_mask_MS + (int64_t)b0 * P; p.E_MS = e->W("linear_embedding_MS.embedding.weight"); p.ms_vocab = d.ms_vocab; }
+        if (L.has_MW) {
+            p.trg_MW = in.d_trg_MW + b0;
+            p.W_MW = e->W("linear_embedding_MW.linear_spec_embedding_MW.weight");
+            p.b_MW = e->W("linear_embedding_MW.linear_spec_embedding_MW.bias");
+        }
+        p.B = Bc; p.S_total = L.S_total; p.P = P; p.float_mask = 0;
+        p.cross_X = Xc; p.key_bias = key_bias; p.pad_mask = pad_mask;
+        p.embedding_src = d_embedding_src; p.B_total = B_total; p.b0 = b0;
+        prof_pre(e, s);
+        embed_tokens<<<dim3(Bc, 5), 128, 0, s>>>(p);
+        MMT_TRY(check_launch(e, "embed_tokens", s));
+    }
+    if (bf16)
+        for (int m = 0; m < 5; ++m) {
+            prof_pre(e, s);
+            pack_rows_bf16<<<(unsigned)((rows_m[m] + 7) / 8), 256, 0, s>>>(X[m], nullptr, D, rows_m[m], X16[m]);
+            MMT_TRY(check_launch(e, "pack_rows_bf16", s));
+        }
+    // ---- five modality encoders on their compact rows
+    {
+        EncGroupRun gr[5];
+        int64_t row_off = 0;
+        for (int m = 0; m < 5; ++m) {
+            EncGroupRun& g = gr[m];
+            memset(&g, 0, sizeof(g));
+            g.X = X[m]; g.rows = rows_m[m]; g.S = L.S_m[m];
+            g.kbias = nullptr; g.kidx = ix.kidx + (size_t)m * Bc * CP_SMAX; g.nk = ix.nkeys + m * Bc;
+            g.row_start = ix.row_start + m * (Bc + 1); g.cnt = ix.cnt + m * Bc; g.kstride = CP_SMAX;
+            g.qkv = QKV + row_off * 3 * D;
+            if (bf16) { g.x16 = X16[m]; g.att16 = ATT16 + row_off * D; }
+            else { g.att = ATT + row_off * D; g.part = PART + row_off * D; g.h = H + row_off * d.d_ff; }
+            row_off += g.rows;
+        }
+        for (int l = 0; l < d.n_enc_layers; ++l) {
+            for (int m = 0; m < 5; ++m) {
+                gr[m].w = &e->enc[m][l];
+                if (l == d.n_enc_layers - 1) {   // last layer scatters into the spectrum-major cross buffer
+                    gr[m].out = Xc; gr[m].out16 = Xc16; gr[m].out_rows = ix.out_rows + (size_t)m * Bc * maxS;
+                    gr[m].stride_b = 0; gr[m].stride_s = 1; gr[m].off = 0;
+                }
+            }
+            if (bf16) MMT_TRY(encoder_layer_bf16(e, gr, 5, Bc, d.n_heads, d.d_ff, s));
+            else MMT_TRY(encoder_layer_fp32(e, gr, 5, Bc, d.n_heads, d.d_ff, s));
+        }
+    }
+    // ---- encoder_cross on the concatenated compact rows
+    {
+        EncGroupRun g;
+        memset(&g, 0, sizeof(g));
+        g.X = Xc; g.rows = rows_c; g.S = L.S_total; g.kbias = nullptr; g.kidx = ix.kidx_c; g.nk = ix.nk_c;
+        g.row_start = ix.cstart; g.cnt = ix.ccnt; g.kstride = L.S_total;
+        g.qkv = QKV; g.att = ATT; g.part = PART; g.h = H;
+        g.x16 = Xc16; g.att16 = ATT16;
+        for (int l = 0; l < d.n_enc_layers; ++l) {
+            g.w = &e->enc[5][l];
+            if (bf16) MMT_TRY(encoder_layer_bf16(e, &g, 1, Bc, d.n_heads_cross, d.d_ff, s));
+            else MMT_TRY(encoder_layer_fp32(e, &g, 1, Bc, d.n_heads_cross, d.d_ff, s));
+        }
+    }
+    {   // replicate the padded rows while writing the sequence-first (S, B, 128) memory
+        ExpandParams p;
+        memset(&p, 0, sizeof(p));
+        p.Y = Xc; p.cstart = ix.cstart; p.moff = ix.moff; p.d2c = ix.d2c; p.B = Bc; p.S_total = L.S_total;
+        for (int m = 0; m < 5; ++m) { p.off[m] = L.off[m]; p.S_m[m] = L.S_m[m]; }
+        p.memory = d_memory; p.B_total = B_total; p.b0 = b0;
+        prof_pre(e, s);
+        expand_memory<<<(unsigned)((R + 7) / 8), 256, 0, s>>>(p);
+        MMT_TRY(check_launch(e, "expand_memory", s));
     }
     return 0;
 }
@@ -1011,6 +1200,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     e->reg = build_registry(*desc);
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
     if (getenv("MMT_NO_PDL")) e->use_pdl = false;
+    if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };
@@ -1069,7 +1259,12 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
     const int chunk = 256;
     for (int b0 = 0; b0 < B; b0 += chunk) {
         int Bc = std::min(chunk, B - b0);
-        MMT_TRY(encode_chunk(e, *in, b0, Bc, B, mode_bits, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, precision == MMT_PREC_BF16, s));
+        // ragged path: all five spectra in training_mode (bool key-padding masks everywhere)
+        int rc = 2;
+        if (e->use_compact && !L.float_mask && L.present[4])
+            rc = encode_chunk_compact(e, *in, b0, Bc, B, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, precision == MMT_PREC_BF16, s);
+        if (rc == 1) return 1;
+        if (rc == 2) MMT_TRY(encode_chunk(e, *in, b0, Bc, B, mode_bits, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, precision == MMT_PREC_BF16, s));
     }
     if (d_fingerprint || d_avg_memory) {
         Arena a;

@@ -117,6 +117,7 @@ struct mmt_engine {
     int64_t launches = 0;
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
+    bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     bool use_pdl = true;               // programmatic dependent launch between the kernels of a fused decode step (MMT_NO_PDL=1 disables)
     cudaStream_t cap_stream = nullptr; // capture-only stream (the caller's stream may be the legacy default stream)
     long long* da_dbg = nullptr;       // MMT_DA_DEBUG phase timestamps (managed memory)

@@ -59,6 +59,7 @@ struct FfnParams {
     int head_major, hm_heads, hm_dh; int64_t hm_rows;   // unused (0); keeps the shared epilogue templates happy
     const float* res; const float* gamma; const float* beta; float eps;
     int S_in; int64_t stride_b, stride_s, off;
+    const int* out_rows;             // optional explicit output rows (LayerNorm epilogue, ragged encoder)
     long long* dbg;                  // optional [CTA][16] phase timestamps (MMT_DA_DEBUG)
 };
 

@@ -198,6 +198,7 @@ struct LnGroup {
     const int* M_dev;
     int M;
     int S_in; int64_t stride_b, stride_s, off;
+    const int* out_rows;       // optional explicit output row per input row (ragged encoder), overrides the affine map
 };
 struct LnParams { LnGroup g[GEMM_MAX_GROUPS]; int splits; int64_t part_stride; float eps; };
 
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256) bias_res_layernorm(const __grid_constant_
     float4 ga = *reinterpret_cast<const float4*>(g.gamma + c);
     float4 be = *reinterpret_cast<const float4*>(g.beta + c);
     float4 o = make_float4(dx * rstd * ga.x + be.x, dy * rstd * ga.y + be.y, dz * rstd * ga.z + be.z, dw * rstd * ga.w + be.w);
-    int64_t orow = (int64_t)(r / g.S_in) * g.stride_b + (int64_t)(r % g.S_in) * g.stride_s + g.off;
+    int64_t orow = g.out_rows ? (int64_t)g.out_rows[r] : (int64_t)(r / g.S_in) * g.stride_b + (int64_t)(r % g.S_in) * g.stride_s + g.off;
     *reinterpret_cast<float4*>(g.out + orow * D + c) = o;
     if (g.out_bf16) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
@@ -254,6 +255,8 @@ struct EmbedGroup {
     int n_x;                 // leading spectrum tokens (64 or 1)
     int off;                 // row offset inside the concatenated memory
     int blank_is_ir;         // blank IR gets a bool False mask (bias 0), others float ones (+1)
+    // ragged encoder (kernels_compact.cuh): X row of token (b, s) is row_start[b] + d2c[b][s]; kbias is not written
+    const int* d2c; const int* row_start;
 };
 struct EmbedParams {
     EmbedGroup g[5];
@@ -326,11 +329,12 @@ __global__ void __launch_bounds__(128) embed_tokens(const __grid_constant__ Embe
             }
         }
         v = fmaxf(v, 0.f);
-        g.X[((int64_t)b * g.S_m + s) * D + d] = v;
+        if (g.d2c) g.X[((int64_t)g.row_start[b] + g.d2c[(int64_t)b * CP_SMAX + s]) * D + d] = v;   // padded tokens of a segment share one row (same value)
+        else g.X[((int64_t)b * g.S_m + s) * D + d] = v;
         int srow = g.off + s;
         if (p.embedding_src) p.embedding_src[((int64_t)srow * B + bo) * D + d] = v;
         if (d == 0) {
-            g.kbias[(int64_t)b * g.S_m + s] = pad ? MMT_NEG_INF : 0.f;
+            if (g.kbias) g.kbias[(int64_t)b * g.S_m + s] = pad ? MMT_NEG_INF : 0.f;
             p.key_bias[(int64_t)b * p.S_total + srow] = p.float_mask ? (pad ? 1.f : 0.f) : (pad ? MMT_NEG_INF : 0.f);
             p.pad_mask[(int64_t)b * p.S_total + srow] = pad ? 1 : 0;
         }
@@ -369,6 +373,9 @@ struct AttnGroup {
     float* out;          // [B*S][D] fp32 (or nullptr)
     __nv_bfloat16* out16;  // [B*S][D] bf16 operand copy for the tensor-core out-projection (or nullptr)
     int S;
+    // ragged encoder: sequence b owns rows [row_start[b], row_start[b] + cnt[b]); kidx rows are kstride apart;
+    // every listed key is attendable with bias 0 (kbias == nullptr)
+    const int* row_start; const int* cnt; int kstride;
 };
 struct AttnParams { AttnGroup g[GEMM_MAX_GROUPS]; float scale; };
 
@@ -377,20 +384,23 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
     extern __shared__ __align__(16) float smem[];
     const AttnGroup& g = p.g[blockIdx.z];
     const int h = blockIdx.x, b = blockIdx.y;
-    const int S = g.S;
+    const int S = g.cnt ? g.cnt[b] : g.S;            // query rows of this sequence
+    const int Smax = g.S;                            // smem carve-up bound (host sizes smem for it)
+    const int kstride = g.cnt ? g.kstride : g.S;
+    const int64_t row0 = g.row_start ? (int64_t)g.row_start[b] : (int64_t)b * g.S;
     const int nk = g.nk[b];
-    float* Ks = smem;                 // [nk][DH]
-    float* Vs = Ks + (size_t)S * DH;  // [nk][DH]
-    float* bs = Vs + (size_t)S * DH;  // [nk]
-    const float* base = g.qkv + (int64_t)b * S * (3 * D);
+    float* Ks = smem;                    // [nk][DH]
+    float* Vs = Ks + (size_t)Smax * DH;  // [nk][DH]
+    float* bs = Vs + (size_t)Smax * DH;  // [nk]
+    const float* base = g.qkv + row0 * (3 * D);
     constexpr int V4 = DH / 4;
     for (int i = threadIdx.x; i < nk * V4; i += blockDim.x) {
         int jj = i / V4, q4 = i % V4;
-        int j = g.kidx[(int64_t)b * S + jj];
+        int j = g.kidx[(int64_t)b * kstride + jj];
         const float* row = base + (int64_t)j * (3 * D) + h * DH + q4 * 4;
         *reinterpret_cast<float4*>(Ks + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + D);
         *reinterpret_cast<float4*>(Vs + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + 2 * D);
-        if (q4 == 0) bs[jj] = g.kbias[(int64_t)b * S + j];
+        if (q4 == 0) bs[jj] = g.kbias ? g.kbias[(int64_t)b * g.S + j] : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
@@ -430,14 +440,14 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
         }
         float inv = 1.0f / l;
         if (g.out) {
-            float* orow = g.out + ((int64_t)b * S + i) * D + h * DH;
+            float* orow = g.out + (row0 + i) * D + h * DH;
 #pragma unroll
             for (int d4 = 0; d4 < V4; ++d4)
                 *reinterpret_cast<float4*>(orow + d4 * 4) =
                     make_float4(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv, acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
         }
         if (g.out16) {
-            __nv_bfloat16* orow = g.out16 + ((int64_t)b * S + i) * D + h * DH;
+            __nv_bfloat16* orow = g.out16 + (row0 + i) * D + h * DH;
 #pragma unroll
             for (int d4 = 0; d4 < V4; ++d4) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv);

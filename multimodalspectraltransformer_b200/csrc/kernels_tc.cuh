@@ -54,6 +54,7 @@ struct TcGemmParams {
     const float* res; const float* gamma; const float* beta; float eps;
     // output row map (in rows): (r / S_in) * stride_b + (r % S_in) * stride_s + off
     int S_in; int64_t stride_b, stride_s, off;
+    const int* out_rows;      // optional explicit output row per input row (ragged encoder), overrides the affine map
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -246,7 +247,7 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
             if (i0 + u < rows) {
                 const float rstd = rsqrtf(s[u] * (1.0f / D) + eps);
                 const float4 o = make_float4(v[u].x * rstd * ga.x + be.x, v[u].y * rstd * ga.y + be.y, v[u].z * rstd * ga.z + be.z, v[u].w * rstd * ga.w + be.w);
-                const int64_t orow = map.next();
+                const int64_t orow = p.out_rows ? (int64_t)p.out_rows[row0 + i0 + u] : map.next();
                 if (out32) *reinterpret_cast<float4*>(out32 + orow * ld32) = o;
                 if (out16) *reinterpret_cast<uint2*>(out16 + orow * ld16) = pack_bf16x4(o);
             }
