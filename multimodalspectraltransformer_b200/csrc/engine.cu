@@ -1083,37 +1083,59 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         MMT_TRY(check_launch(e, "init_block_table", s));
         MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, bf16, s));
         // One decode step is the same kernel sequence at every position (the step counter lives on
-        // the device), so it is captured once per wave into a CUDA graph and replayed max_len times.
+        // the device), so a group of U consecutive steps is captured once per wave into a CUDA graph
+        // (programmatic-dependent-launch edges included) and replayed T / U times.
+        int U = 1;
+        for (int u = 2; u <= 16; ++u) if (r.T % u == 0) U = u;
         cudaGraphExec_t exec = nullptr;
-        int64_t launches_per_step = 0;
+        int64_t launches_per_group = 0;
         if (e->use_graph && !e->profiling) {
             if (bf16) MMT_TRY(tc_init(e));
             if (!e->cap_stream) MMT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
             const int64_t l0 = e->launches;
             MMT_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed));
-            const int rc = decode_step(e, r, n0, Nw, Bmw, b, bf16, e->cap_stream);
+            int rc = 0;
+            for (int u = 0; u < U && !rc; ++u) rc = decode_step(e, r, n0, Nw, Bmw, b, bf16, e->cap_stream);
             cudaGraph_t graph = nullptr;
             cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
-            launches_per_step = e->launches - l0;
+            launches_per_group = e->launches - l0;
             e->launches = l0;
             if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
             if (ce != cudaSuccess) MMT_FAIL(std::string("decode step capture failed: ") + cudaGetErrorString(ce));
             ce = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) MMT_FAIL(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+        } else {
+            U = 1;
         }
         struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { if (x) cudaGraphExecDestroy(x); } } guard{exec};
-        for (int t = 0; t < r.T; ++t) {
-            if (exec) { MMT_CUDA(cudaGraphLaunch(exec, s)); e->launches += launches_per_step; }
+        // greedy early exit (validate_generate_MMT_v15_4.py:763): the per-step non-PAD counts are polled one
+        // group behind the launches, so the host never drains the stream inside the loop
+        if (early) for (int i = 0; i < 2; ++i) if (!e->poll_ev[i]) MMT_CUDA(cudaEventCreateWithFlags(&e->poll_ev[i], cudaEventDisableTiming));
+        const int poll_every = (16 / U) * U > 0 ? std::max(U, (16 / U) * U) : U;    // steps between polls (multiple of U, ~16)
+        int n_polls = 0, checked_polls = 0;
+        bool stop = false;
+        auto check_poll = [&](int k) -> int {       // inspect poll k (covers steps < (k+1)*poll_every, capped at T)
+            MMT_CUDA(cudaEventSynchronize(e->poll_ev[k & 1]));
+            const int upto = std::min(r.T, (k + 1) * poll_every);
+            const int32_t* cnt = e->h_pinned + (k & 1) * 256;
+            for (int q = 0; q < upto; ++q) if (cnt[q] == 0) { steps_done = q + 1; stop = true; break; }
+            return 0;
+        };
+        for (int t = 0; t < r.T && !stop; t += U) {
+            if (exec) { MMT_CUDA(cudaGraphLaunch(exec, s)); e->launches += launches_per_group; }
             else MMT_TRY(decode_step(e, r, n0, Nw, Bmw, b, bf16, s));
-            if (early && ((t + 1) % 16 == 0 || t + 1 == r.T) ) {
-                MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
-                MMT_CUDA(cudaStreamSynchronize(s));
-                bool stop = false;
-                for (int q = 0; q <= t; ++q) if (e->h_pinned[q] == 0) { steps_done = q + 1; stop = true; break; }
+            const int done = t + U;
+            if (early && (done % poll_every == 0 || done == r.T)) {
+                if (n_polls - checked_polls >= 2) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
                 if (stop) break;
+                MMT_CUDA(cudaMemcpyAsync(e->h_pinned + (n_polls & 1) * 256, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
+                MMT_CUDA(cudaEventRecord(e->poll_ev[n_polls & 1], s));
+                ++n_polls;
+                if (n_polls - checked_polls >= 2) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
             }
         }
+        while (early && !stop && checked_polls < n_polls) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
         if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1) {
             MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
             MMT_CUDA(cudaStreamSynchronize(s));
@@ -1231,6 +1253,7 @@ void mmt_destroy(mmt_engine* e) {
     if (e->arena) cudaFree(e->arena);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    for (int i = 0; i < 2; ++i) if (e->poll_ev[i]) cudaEventDestroy(e->poll_ev[i]);
     delete e;
 }
 

@@ -123,6 +123,7 @@ struct mmt_engine {
     long long* da_dbg = nullptr;       // MMT_DA_DEBUG phase timestamps (managed memory)
     bool da_ready = false;             // decode_attn shared-memory attribute set
     bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};   // early-exit polls, one group behind the launches
     int32_t* h_pinned = nullptr;       // small pinned staging buffer (early-exit poll)
     // per-kernel-class device timing (mmt_profile_enable / mmt_profile_report)
     struct ProfRecord { const char* name; cudaEvent_t a, b; double work; };

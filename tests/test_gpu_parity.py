@@ -294,3 +294,59 @@ def test_errors_are_loud():
         s["M"].run_model(s["model"], data, cpu_cfg)
     with pytest.raises(TypeError):
         s["M"].run_model(s["model"], data, cfg_for(training_mode="IR_MF_MW"))
+
+
+# --------------------------------------------------------------------------- ragged encoder
+def _dense_engine():
+    """A second engine over the same weights with the ragged encoder disabled (MMT_DENSE_ENCODER is read at creation)."""
+    import os
+    s = setup()
+    if "eng_dense" not in _S:
+        from multimodalspectraltransformer_b200.engine import Engine
+        os.environ["MMT_DENSE_ENCODER"] = "1"
+        try:
+            _S["eng_dense"] = Engine(s["model"].state_dict(), s["cfg"], "cuda")
+        finally:
+            del os.environ["MMT_DENSE_ENCODER"]
+    return _S["eng_dense"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("peaks", ["realistic", "max"])
+def test_ragged_encoder_equals_dense_encoder(precision, peaks):
+    """Computing each distinct token row once == running all 582 padded rows: same memory, mask and
+    fingerprint; padded rows of a segment are exact replicas."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    data = {k: v.cuda() for k, v in synthetic.make_spectra(9, seed=77, peaks=peaks).items()}
+    mode = "1H_13C_HSQC_COSY_IR_MF_MW"
+    mem_r, pad_r, kb_r, fp_r, avg_r, emb_r = s["eng"].encode(data, mode, precision, want_embedding_src=True)
+    mem_d, pad_d, kb_d, fp_d, avg_d, emb_d = _dense_engine().encode(data, mode, precision, want_embedding_src=True)
+    assert torch.equal(pad_r, pad_d) and torch.equal(kb_r, kb_d) and torch.equal(emb_r, emb_d)
+    tol = 1e-5 if precision == "fp32" else 2e-5      # row-local arithmetic is position independent; allow reassociation
+    torch.testing.assert_close(mem_r, mem_d, atol=tol, rtol=0)
+    torch.testing.assert_close(fp_r, fp_d, atol=1e-4, rtol=0)
+    # every padded peak row of a spectrum equals the first padded row of its segment, bit for bit
+    m1 = data["mask_1H"][0] != 0
+    if int(m1.sum()) > 1:
+        rows = mem_r[:64, 0][m1]
+        assert torch.equal(rows, rows[:1].expand_as(rows))
+
+
+def test_ragged_encoder_falls_back_when_padding_hides_data():
+    """A caller may leave non-zero data under the mask: padded rows then differ as queries, the ragged path must
+    notice (device-side flag) and the dense path must produce the reference's result."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    host = synthetic.make_spectra(3, seed=5)
+    pad = host["mask_1H"] != 0
+    host["src_1H"] = host["src_1H"].clone()
+    host["src_1H"][pad] = torch.rand(int(pad.sum()), 2)            # junk under the mask
+    cfg = cfg_for()
+    memory, mask, *_ = s["M"].run_model(s["model"], host, cfg)
+    with torch.no_grad():
+        omem, omask, ofp, _ = s["O"].encode(s["P"], host, s["O"].default_config())
+    assert torch.equal(mask.cpu(), omask)
+    np.testing.assert_allclose(memory.cpu().numpy(), omem.numpy(), atol=5e-5, rtol=0)
+    rows = memory[:64, 0][pad[0].cuda()]
+    assert not torch.equal(rows, rows[:1].expand_as(rows))        # the padded rows really are distinct here
