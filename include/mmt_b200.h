@@ -177,6 +177,12 @@ uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threa
 int32_t mmt_pack_tokens_u8(const int64_t* d_tokens, int64_t n, uint8_t* d_out, void* stream);
 int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, void* stream);
 
+/* Replaces the per-element .item() scans of tensor_to_smiles / tensor_to_smiles_and_prob(_2)
+ * (helper_functions_pl_v15_4.py:255-301, 390-419): d_len[n] = position of the first `eos` id in column n
+ * of d_tokens (T,N) i64, or T if the sequence never emits it.  The host then slices tokens / probabilities
+ * and joins the strings after ONE device-to-host copy. */
+int32_t mmt_first_eos(const int64_t* d_tokens, int32_t T, int64_t N, int32_t eos, int32_t* d_len, void* stream);
+
 /* ---- building blocks exported for unit parity tests --------------------------- */
 
 /* fused fc_out + softmax(logits/T) + greedy|multinomial pick on hidden states

@@ -1343,6 +1343,14 @@ int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, 
     return 0;
 }
 
+int32_t mmt_first_eos(const int64_t* d_tokens, int32_t T, int64_t N, int32_t eos, int32_t* d_len, void* stream) {
+    if (!d_tokens || !d_len) MMT_FAIL("null argument");
+    if (N <= 0 || T <= 0) return 0;
+    first_eos_scan<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_tokens, T, N, eos, d_len);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature, int32_t sampling,
                    uint64_t philox_seed, uint64_t philox_offset, int64_t seq_index_base, int64_t N_total,
                    int32_t rng_sm_count, int32_t rng_max_threads_per_sm,

@@ -797,6 +797,18 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
     }
 }
 
+// len[n] = index of the first `eos` in column n of tokens (T, N), or T when there is none
+// (the truncation rule of helper_functions_pl_v15_4.py:272-301, 390-419).  One thread per sequence; rows are
+// contiguous over n, so every step of the scan is a coalesced read.
+__global__ void first_eos_scan(const int64_t* tokens, int T, int64_t N, int eos, int32_t* len) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    int L = T;
+    for (int t = 0; t < T; ++t)
+        if (tokens[(int64_t)t * N + n] == eos) { L = t; break; }
+    len[n] = L;
+}
+
 __global__ void pack_tokens_u8(const int64_t* in, int64_t n, uint8_t* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint8_t)in[i];
