@@ -118,11 +118,17 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    v, tokens, sec, threads = cpu_reference_tokens_per_s(REF_SAMPLE_SPECTRA, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    precision = args.precision if args.precision != "auto" else os.environ.get("MMT_DEFAULT_PRECISION", "bf16")
+    v, tokens, sec, threads = cpu_reference_tokens_per_s(REF_SAMPLE_SPECTRA, steps=max(1, args.steps), warmup=min(args.warmup, 1), threads=ncores)
     sample = f"{REF_SAMPLE_SPECTRA} of the {B_PER_GPU} spectra x {MAX_LEN} steps per step (greedy, fp32, oracle port of the reference loop)"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(1, "fp32"),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(max(1, args.gpus), precision),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -59,6 +59,9 @@ template <> struct KvRow<float> {
         v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
     }
     static __device__ __forceinline__ void st(float* p, float x) { *p = x; }
+    static __device__ __forceinline__ Raw pack(const float* x) {      // the row as the cache will hold it
+        Raw r; r.a = make_float4(x[0], x[1], x[2], x[3]); r.b = make_float4(x[4], x[5], x[6], x[7]); return r;
+    }
 };
 template <> struct KvRow<__nv_bfloat16> {
     typedef uint4 Raw;
@@ -70,6 +73,14 @@ template <> struct KvRow<__nv_bfloat16> {
         v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
     }
     static __device__ __forceinline__ void st(__nv_bfloat16* p, float x) { *p = __float2bfloat16_rn(x); }
+    static __device__ __forceinline__ Raw pack(const float* x) {      // the row as the cache will hold it (same rounding as st)
+        Raw r;
+        __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(x[4], x[5]), d = __floats2bfloat162_rn(x[6], x[7]);
+        r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+        r.z = *reinterpret_cast<uint32_t*>(&c); r.w = *reinterpret_cast<uint32_t*>(&d);
+        return r;
+    }
 };
 
 __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

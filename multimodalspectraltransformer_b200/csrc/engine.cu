@@ -855,7 +855,7 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
             TcGemmParams p = tc_params((int)R, 2 * D, D);
             p.bias = e->dec[l].ca_in_b + D;
             p.out_b16 = reinterpret_cast<__nv_bfloat16*>(b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz);
-            p.head_major = 1; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
+            p.head_major = 1; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = a.S;
             MMT_TRY(launch_tc(e, p, b.mem16, D, e->Wb(e->dec[l].ca_in_w + (int64_t)D * D), TC_EPI_STORE, s, e->Wlo(e->dec[l].ca_in_w + (int64_t)D * D)));
         }
         return 0;
@@ -866,7 +866,7 @@ static int decode_prepare_wave(mmt_engine* e, const mmt_decode_args& a, int b0, 
         p.g[0].W = e->dec[l].ca_in_w + (int64_t)D * D;     // rows D..3D of in_proj: K then V
         p.g[0].bias = e->dec[l].ca_in_b + D;
         p.g[0].C = reinterpret_cast<float*>(b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz); p.g[0].M = (int)R;
-        p.out_mode = GEMM_OUT_HEADMAJOR; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = R;
+        p.out_mode = GEMM_OUT_HEADMAJOR; p.hm_heads = d.n_heads; p.hm_dh = dh; p.hm_rows = a.S;
         MMT_TRY(launch_gemm(e, p, 1, (int)R, s));
     }
     return 0;
@@ -951,7 +951,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             q.kv_pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz; q.block_table = b.block_table; q.pps = pps;
             q.step = step;
             q.cq_w = w.ca_in_w; q.cq_b = w.ca_in_b; q.co_w = w.ca_out_w; q.co_b = w.ca_out_b; q.n2_w = w.n2_w; q.n2_b = w.n2_b;
-            q.ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz; q.rows_total = R;
+            q.ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz; q.rows_total = a.S;
             q.nk = b.nk; q.row_start = b.row_start; q.kbias_c = b.kbias_c; q.n_cand = a.n_cand;
             q.x2 = b.x; q.x2_16 = bf16 ? b.x16 : nullptr; q.M = Nw; q.scale = scale; q.eps = 1e-5f;
             q.dbg = (e->da_dbg && l == 3) ? e->da_dbg : nullptr;
@@ -996,8 +996,8 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
             }
             prof_pre(e, s);
-            if (bf16) decode_cross_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, nullptr, b.att16);
-            else decode_cross_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const float*>(ckv), R, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, b.att, b.att16);
+            if (bf16) decode_cross_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, nullptr, b.att16);
+            else decode_cross_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const float*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_cross_attention", s));
             if (bf16) {
                 MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
@@ -1062,45 +1062,81 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
     if (a.precision != MMT_PREC_FP32 && a.precision != MMT_PREC_BF16) MMT_FAIL("decode: bad precision");
     const bool bf16 = a.precision == MMT_PREC_BF16;
+    // Lanes: a small wave is a latency chain of ~13 dependent kernels per position that leaves most of the GPU
+    // idle, so the wave's spectra are split into independent lanes whose chains run concurrently (parallel
+    // branches of the same CUDA graph, own KV pools / step counters); every sequence is independent.
+    constexpr int MAX_LANES = 4;
+    int NL = 1;
+    {
+        const int64_t Nwave = (int64_t)Bm_wave * a.n_cand;
+        const bool fused = e->fused_decode_rows > 0 && Nwave <= e->fused_decode_rows;
+        if (fused && e->use_graph && !e->profiling) {
+            NL = std::min(std::min(e->decode_lanes, MAX_LANES), Bm_wave);
+            while (NL > 1 && Nwave / NL < 32) --NL;
+        }
+    }
+    const int Bm_lane = (Bm_wave + NL - 1) / NL;
     Arena ar;
-    DecBuffers b;
+    DecBuffers lb[MAX_LANES];
     ar.plan = true;
-    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b, bf16);
+    for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16);
     MMT_TRY(ensure_arena(e, ar.off));
     ar.plan = false; ar.base = e->arena; ar.cap = e->arena_bytes; ar.off = 0;
-    plan_decoder(ar, d, (int64_t)Bm_wave * a.n_cand, Bm_wave, a.S, a.max_len, b, bf16);
+    for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16);
     const int pps = (a.max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
     const bool early = (r.mode == 0) && a.stop_on_all_pad && n_waves == 1;
     int steps_done = r.T;
     std::vector<int64_t> nonpad_total(r.T, 0);
     for (int wv = 0; wv < n_waves; ++wv) {
-        const int b0 = wv * Bm_wave;
-        const int Bmw = std::min(Bm_wave, a.Bm - b0);
-        const int64_t Nw = (int64_t)Bmw * a.n_cand, n0 = (int64_t)b0 * a.n_cand;
-        MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
-        prof_pre(e, s);
-        init_block_table<<<(unsigned)((Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, Nw * pps);
-        MMT_TRY(check_launch(e, "init_block_table", s));
-        MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, bf16, s));
+        const int wb0 = wv * Bm_wave;
+        const int Bmw = std::min(Bm_wave, a.Bm - wb0);
+        struct Lane { int b0, Bm; int64_t n0, Nw; } lane[MAX_LANES];
+        int nl = 0;
+        for (int i = 0; i < NL; ++i) {
+            const int lo = std::min(i * Bm_lane, Bmw), hi = std::min(lo + Bm_lane, Bmw);
+            if (hi > lo) { lane[nl].b0 = wb0 + lo; lane[nl].Bm = hi - lo; lane[nl].n0 = (int64_t)(wb0 + lo) * a.n_cand; lane[nl].Nw = (int64_t)(hi - lo) * a.n_cand; ++nl; }
+        }
+        for (int i = 0; i < nl; ++i) {
+            DecBuffers& b = lb[i];
+            MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
+            prof_pre(e, s);
+            init_block_table<<<(unsigned)((lane[i].Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, lane[i].Nw * pps);
+            MMT_TRY(check_launch(e, "init_block_table", s));
+            MMT_TRY(decode_prepare_wave(e, a, lane[i].b0, lane[i].Bm, b, bf16, s));
+        }
         // One decode step is the same kernel sequence at every position (the step counter lives on
-        // the device), so a group of U consecutive steps is captured once per wave into a CUDA graph
-        // (programmatic-dependent-launch edges included) and replayed T / U times.
+        // the device), so a group of U consecutive steps of every lane is captured once per wave into a CUDA
+        // graph (programmatic-dependent-launch edges included) and replayed T / U times.
         int U = 1;
         for (int u = 2; u <= 16; ++u) if (r.T % u == 0) U = u;
         cudaGraphExec_t exec = nullptr;
         int64_t launches_per_group = 0;
         if (e->use_graph && !e->profiling) {
             if (bf16) MMT_TRY(tc_init(e));
-            if (!e->cap_stream) MMT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < nl; ++i) {
+                if (!e->cap_stream[i]) MMT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream[i], cudaStreamNonBlocking));
+                if (!e->lane_ev[i]) MMT_CUDA(cudaEventCreateWithFlags(&e->lane_ev[i], cudaEventDisableTiming));
+            }
             const int64_t l0 = e->launches;
-            MMT_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeRelaxed));
+            MMT_CUDA(cudaStreamBeginCapture(e->cap_stream[0], cudaStreamCaptureModeRelaxed));
             int rc = 0;
-            for (int u = 0; u < U && !rc; ++u) rc = decode_step(e, r, n0, Nw, Bmw, b, bf16, e->cap_stream);
+            cudaError_t fe = cudaSuccess;
+            if (nl > 1) {                                 // fork the other lanes' branches off the capture origin
+                fe = cudaEventRecord(e->lane_ev[0], e->cap_stream[0]);
+                for (int i = 1; i < nl && fe == cudaSuccess; ++i) fe = cudaStreamWaitEvent(e->cap_stream[i], e->lane_ev[0], 0);
+            }
+            for (int u = 0; u < U && !rc && fe == cudaSuccess; ++u)
+                for (int i = 0; i < nl && !rc; ++i) rc = decode_step(e, r, lane[i].n0, lane[i].Nw, lane[i].Bm, lb[i], bf16, e->cap_stream[i]);
+            for (int i = 1; i < nl && fe == cudaSuccess; ++i) {   // join
+                fe = cudaEventRecord(e->lane_ev[i], e->cap_stream[i]);
+                if (fe == cudaSuccess) fe = cudaStreamWaitEvent(e->cap_stream[0], e->lane_ev[i], 0);
+            }
             cudaGraph_t graph = nullptr;
-            cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+            cudaError_t ce = cudaStreamEndCapture(e->cap_stream[0], &graph);
             launches_per_group = e->launches - l0;
             e->launches = l0;
             if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+            if (fe != cudaSuccess) { if (graph) cudaGraphDestroy(graph); MMT_FAIL(std::string("decode lane fork/join failed: ") + cudaGetErrorString(fe)); }
             if (ce != cudaSuccess) MMT_FAIL(std::string("decode step capture failed: ") + cudaGetErrorString(ce));
             ce = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
@@ -1118,18 +1154,23 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         auto check_poll = [&](int k) -> int {       // inspect poll k (covers steps < (k+1)*poll_every, capped at T)
             MMT_CUDA(cudaEventSynchronize(e->poll_ev[k & 1]));
             const int upto = std::min(r.T, (k + 1) * poll_every);
-            const int32_t* cnt = e->h_pinned + (k & 1) * 256;
-            for (int q = 0; q < upto; ++q) if (cnt[q] == 0) { steps_done = q + 1; stop = true; break; }
+            const int32_t* cnt = e->h_pinned + (k & 1) * 512;
+            for (int q = 0; q < upto; ++q) {
+                int tot = 0;
+                for (int i = 0; i < nl; ++i) tot += cnt[i * 128 + q];
+                if (tot == 0) { steps_done = q + 1; stop = true; break; }
+            }
             return 0;
         };
         for (int t = 0; t < r.T && !stop; t += U) {
             if (exec) { MMT_CUDA(cudaGraphLaunch(exec, s)); e->launches += launches_per_group; }
-            else MMT_TRY(decode_step(e, r, n0, Nw, Bmw, b, bf16, s));
+            else for (int i = 0; i < nl; ++i) MMT_TRY(decode_step(e, r, lane[i].n0, lane[i].Nw, lane[i].Bm, lb[i], bf16, s));
             const int done = t + U;
             if (early && (done % poll_every == 0 || done == r.T)) {
                 if (n_polls - checked_polls >= 2) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
                 if (stop) break;
-                MMT_CUDA(cudaMemcpyAsync(e->h_pinned + (n_polls & 1) * 256, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
+                for (int i = 0; i < nl; ++i)
+                    MMT_CUDA(cudaMemcpyAsync(e->h_pinned + (n_polls & 1) * 512 + i * 128, lb[i].ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
                 MMT_CUDA(cudaEventRecord(e->poll_ev[n_polls & 1], s));
                 ++n_polls;
                 if (n_polls - checked_polls >= 2) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
@@ -1137,9 +1178,10 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         }
         while (early && !stop && checked_polls < n_polls) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
         if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1) {
-            MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
+            for (int i = 0; i < nl; ++i)
+                MMT_CUDA(cudaMemcpyAsync(e->h_pinned + i * 128, lb[i].ctl + 8, r.T * sizeof(int), cudaMemcpyDeviceToHost, s));
             MMT_CUDA(cudaStreamSynchronize(s));
-            for (int q = 0; q < r.T; ++q) nonpad_total[q] += e->h_pinned[q];
+            for (int i = 0; i < nl; ++i) for (int q = 0; q < r.T; ++q) nonpad_total[q] += e->h_pinned[i * 128 + q];
         }
     }
     if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1)
@@ -1152,6 +1194,11 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
             fprintf(stderr, "decode_attn phases, CTA %d:", bshow);
             for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", e->da_dbg[bshow * 16 + i] - e->da_dbg[bshow * 16 + i - 1]);
             fprintf(stderr, "  total %lld\n", e->da_dbg[bshow * 16 + 10] - e->da_dbg[bshow * 16]);
+        }
+        for (int bshow : {1, blocks / 2}) {
+            const long long* d = e->da_dbg + (1024 + bshow) * 16;
+            fprintf(stderr, "decode_attn warp 5, CTA %d: self [K+scores %lld | V+acc %lld | reduce %lld | sync %lld]  cross [loop %lld | reduce %lld | sync %lld]\n", bshow,
+                    d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[6] - d[5], d[7] - d[6], d[8] - d[7]);
         }
         for (int bshow : {0, 33}) {
             const long long* d = e->da_dbg + (2048 + bshow) * 16;
@@ -1222,6 +1269,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     e->reg = build_registry(*desc);
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
     if (getenv("MMT_NO_PDL")) e->use_pdl = false;
+    if (const char* v = getenv("MMT_DECODE_LANES")) e->decode_lanes = std::max(1, atoi(v));
     if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
@@ -1252,7 +1300,7 @@ void mmt_destroy(mmt_engine* e) {
     if (e->w16lo) cudaFree(e->w16lo);
     if (e->arena) cudaFree(e->arena);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
-    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    for (int i = 0; i < 4; ++i) { if (e->cap_stream[i]) cudaStreamDestroy(e->cap_stream[i]); if (e->lane_ev[i]) cudaEventDestroy(e->lane_ev[i]); }
     for (int i = 0; i < 2; ++i) if (e->poll_ev[i]) cudaEventDestroy(e->poll_ev[i]);
     delete e;
 }

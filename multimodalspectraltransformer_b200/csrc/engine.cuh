@@ -119,7 +119,9 @@ struct mmt_engine {
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     bool use_pdl = true;               // programmatic dependent launch between the kernels of a fused decode step (MMT_NO_PDL=1 disables)
-    cudaStream_t cap_stream = nullptr; // capture-only stream (the caller's stream may be the legacy default stream)
+    cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only streams, one per decode lane (the caller's stream may be the legacy default stream)
+    cudaEvent_t lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};       // fork / join events of the lane branches
+    int decode_lanes = 2;              // concurrent lanes of a small decode wave (MMT_DECODE_LANES overrides)
     long long* da_dbg = nullptr;       // MMT_DA_DEBUG phase timestamps (managed memory)
     bool da_ready = false;             // decode_attn shared-memory attribute set
     bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)

@@ -130,7 +130,9 @@ struct DecAttnParams {
     const int* step;
     // ---- cross-attention block
     const float *cq_w, *cq_b, *co_w, *co_b, *n2_w, *n2_b;
-    const void* ckv; int64_t rows_total;       // projected memory of this layer, head-major [2][H][rows_total][DH] (KVT elements)
+    const void* ckv; int64_t rows_total;       // projected memory of this layer: [spectrum][K|V][H][rows_total][DH] (KVT elements),
+                                               // rows_total = rows reserved per spectrum; one contiguous block per spectrum keeps
+                                               // a CTA's K/V inside one or two 2 MB pages (32 head planes would thrash the TLB)
     const int* nk; const int* row_start; const float* kbias_c; int n_cand;
     float* x2; __nv_bfloat16* x2_16;           // out [M][D] fp32 (+ bf16 operand copy for the FFN, optional)
     int64_t M; float scale; float eps;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     const int64_t n = row0 + r;
     const bool live = n < p.M;
 #define DA_STAMP(i) do { if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#define DA_STAMP2(i) do { if (p.dbg && threadIdx.x == 5 * 32) p.dbg[(1024 + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
     DA_STAMP(0);
     pdl_launch_dependents();
 
@@ -195,16 +198,16 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     }
     // ---- per-warp indices, issued up front: cross-attention key range, self-attention page table
     int cnt = 0;
-    int64_t r0 = 0;
+    int64_t r0 = 0, bmem = 0;
     int my_page = 0;
     if (live) {
-        const int64_t b = n / p.n_cand;
-        cnt = p.nk[b];
-        r0 = p.row_start[b];
+        bmem = n / p.n_cand;
+        cnt = p.nk[bmem];
+        r0 = p.row_start[bmem];
         my_page = (lane < p.pps) ? p.block_table[n * p.pps + lane] : 0;
     }
-    const KVT* Kc = reinterpret_cast<const KVT*>(p.ckv) + ((int64_t)(0 * DA_H + h) * p.rows_total + r0) * DH;
-    const KVT* Vc = reinterpret_cast<const KVT*>(p.ckv) + ((int64_t)(1 * DA_H + h) * p.rows_total + r0) * DH;
+    const KVT* Kc = reinterpret_cast<const KVT*>(p.ckv) + ((bmem * 2 + 0) * DA_H + h) * p.rows_total * DH;
+    const KVT* Vc = reinterpret_cast<const KVT*>(p.ckv) + ((bmem * 2 + 1) * DA_H + h) * p.rows_total * DH;
     constexpr int PF = 64 / (int)sizeof(KVT);     // elements per 64-byte prefetch granule
     // L2 prefetch of this warp's cross-attention K/V rows (64-byte granules; consumed in the second half)
     for (int g = lane; g * PF < cnt * DH; g += 32) { prefetch_l2(Kc + g * PF); prefetch_l2(Vc + g * PF); }
@@ -276,19 +279,19 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     gemv_rows(Wbuf, Ps + DA_P_INB, 3 * D, xs, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
     DA_STAMP(3);
-    // the QKV matrix is dead: pull the three 128x128 matrices of the later phases into its place
-    if (warp == 0) {
-        if (lane < 3) da_mbar_expect_tx(&bars[1 + lane], D * D * 4);
-        __syncwarp();
-        if (lane == 0) {   // 3 matrices x 4 pieces of 16 KB, in order of use
-            for (int m = 0; m < 3; ++m) {
-                const float* src = (m == 0 ? p.out_w : (m == 1 ? p.cq_w : p.co_w));
-                for (int piece = 0; piece < 4; ++piece)
-                    da_bulk_g2s(Wbuf + m * D * D + piece * 4096, src + piece * 4096, 4096 * 4, &bars[1 + m]);
-            }
-        }
-    }
-
+    // the QKV matrix is dead after the barrier above: the three 128x128 matrices of the later phases are pulled
+    // into its place (issued by warp 0 from inside the attention phase, see DA_ISSUE_ROUND2)
+#define DA_ISSUE_ROUND2() do {                                                                              \
+        if (warp == 0) {                                                                                    \
+            if (lane < 3) da_mbar_expect_tx(&bars[1 + lane], D * D * 4);                                    \
+            __syncwarp();                                                                                   \
+            if (lane < 12) {                                                                                \
+                const int m_ = lane >> 2, piece_ = lane & 3;                                                \
+                const float* src_ = (m_ == 0 ? p.out_w : (m_ == 1 ? p.cq_w : p.co_w)) + piece_ * 4096;      \
+                da_bulk_g2s(Wbuf + m_ * D * D + piece_ * 4096, src_, 4096 * 4, &bars[1 + m_]);              \
+            }                                                                                               \
+        }                                                                                                   \
+    } while (0)
     // ---- KV append + causal self-attention: one warp per (row, head)
     constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
     KVT* const pool = reinterpret_cast<KVT*>(p.kv_pool);
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             }
         }
         __syncwarp();
+        DA_STAMP2(0);
         float q[DH];
 #pragma unroll
         for (int d = 0; d < DH; ++d) q[d] = row[d] * p.scale;
@@ -314,12 +318,15 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         for (int i = 0; i < MAXK; ++i) {     // all K rows of this lane in flight together; V rows prefetched to L2
             const int j = lane + i * 32;
             const int pg = __shfl_sync(0xffffffffu, my_page, (j / PAGE_TOKENS) & 31);
-            if (j <= t) {
+            if (j < t) {
                 const KVT* page = pool + (int64_t)pg * PAGE_ELEMS;
                 kraw[i] = KV::ld(page + ((0 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
-                prefetch_l2(page + ((1 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
+                prefetch_l2(page + ((1 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);   // V row: an L2 hit by the time the softmax needs it
+            } else if (j == t) {
+                kraw[i] = KV::pack(row + D);      // this position's own K: straight from the projection (no global round trip)
             }
         }
+        DA_ISSUE_ROUND2();   // after this warp's K loads: the 192 KB of weights must not queue ahead of them on the SM's ingress
 #pragma unroll
         for (int i = 0; i < MAXK; ++i) {
             const int j = lane + i * 32;
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             }
         }
         m = warp_max(m);
+        DA_STAMP2(1);
         float l = 0.f, acc[DH];
 #pragma unroll
         for (int d = 0; d < DH; ++d) acc[d] = 0.f;
@@ -342,9 +350,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         for (int i = 0; i < MAXK; ++i) {
             const int j = lane + i * 32;
             const int pg = __shfl_sync(0xffffffffu, my_page, (j / PAGE_TOKENS) & 31);
-            if (j <= t) {
+            if (j < t) {
                 const KVT* page = pool + (int64_t)pg * PAGE_ELEMS;
                 kraw[i] = KV::ld(page + ((1 * DA_H + h) * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH);
+            } else if (j == t) {
+                kraw[i] = KV::pack(row + 2 * D);
             }
         }
 #pragma unroll
@@ -359,6 +369,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
                 for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, v[d], acc[d]);
             }
         }
+        DA_STAMP2(2);
         l = warp_sum(l);
 #pragma unroll
         for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d]);
@@ -368,10 +379,14 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
             att[r][h * DH + lane] = v / l;
         }
-    } else if (lane < DH) {
-        att[r][h * DH + lane] = 0.f;
+        DA_STAMP2(3);
+    } else {
+        DA_ISSUE_ROUND2();
+        if (lane < DH) att[r][h * DH + lane] = 0.f;
     }
+#undef DA_ISSUE_ROUND2
     __syncthreads();
+    DA_STAMP2(4);
     DA_STAMP(4);
 
     // ---- out-projection -> qkv[r][0..127] (reused as scratch), then LN1
@@ -401,6 +416,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
 #pragma unroll
         for (int d = 0; d < DH; ++d) { q[d] = xs[r][h * DH + d] * p.scale; acc[d] = 0.f; }
         float m = MMT_NEG_INF, l = 0.f;
+        DA_STAMP2(5);
         // two keys per lane per pass, K and V of both in flight together
         for (int j0 = lane; j0 < cnt; j0 += 64) {
             const int j1 = j0 + 32;
@@ -428,6 +444,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
 #pragma unroll
             for (int d = 0; d < DH; ++d) acc[d] = fmaf(e1, v1[d], fmaf(e0, v0[d], acc[d]));
         }
+        DA_STAMP2(6);
         const float Mx = warp_max(m);
         const float corr = (m == MMT_NEG_INF) ? 0.f : expf(m - Mx);
         l = warp_sum(l * corr);
@@ -439,8 +456,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
             att[r][h * DH + lane] = v / l;
         }
+        DA_STAMP2(7);
     }
     __syncthreads();
+    DA_STAMP2(8);
     DA_STAMP(8);
 
     // ---- cross out-projection -> qkv scratch, then LN2 -> x2
@@ -464,6 +483,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     }
     DA_STAMP(10);
 #undef DA_STAMP
+#undef DA_STAMP2
 }
 
 }  // namespace mmt

@@ -34,8 +34,8 @@ struct GemmParams {
     int64_t ldc;
     int act;               // 0 none, 1 relu
     int out_mode;          // GEMM_OUT_*
-    int hm_heads, hm_dh;   // head-major: C[((c/D)*heads + (c%D)/dh) * hm_rows + r][c%dh]
-    int64_t hm_rows;
+    int hm_heads, hm_dh;   // cross K/V layout, one block per spectrum: r = b*hm_rows + j ->
+    int64_t hm_rows;       //   C[(((b*2 + c/D)*heads + (c%D)/dh) * hm_rows + j) * dh + c%dh]
 };
 
 template <int BM, int BN, int TM, int TN>
@@ -178,7 +178,8 @@ gemm_nt_f32(const __grid_constant__ GemmParams p) {
             } else {
                 int kv = c / D, cc = c % D;
                 int h = cc / p.hm_dh, d = cc % p.hm_dh;
-                Cbase[(((int64_t)kv * p.hm_heads + h) * p.hm_rows + r) * p.hm_dh + d] = v;
+                const int bb = r / (int)p.hm_rows, jj = r - bb * (int)p.hm_rows;
+                Cbase[((((int64_t)bb * 2 + kv) * p.hm_heads + h) * p.hm_rows + jj) * p.hm_dh + d] = v;
             }
         }
     }
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, K
 }
 
 // Cross-attention of the new position over the (compacted) projected memory;
-// one warp per (sequence, head).  K/V layout: [2][H][rows_total][DH] (head-major) of KVT.
+// one warp per (sequence, head).  K/V layout: [spectrum][K|V][H][rows_total = rows per spectrum][DH] of KVT.
 template <int DH, typename KVT>
 __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in, const KVT* kv, int64_t rows_total,
                                                               const int* nk, const int* row_start, const float* kbias_c,
@@ -625,8 +626,10 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
     const int64_t b = n / n_cand;
     const int cnt = nk[b];
     const int64_t r0 = row_start[b];
-    const KVT* Kh = kv + ((int64_t)(0 * H + h) * rows_total + r0) * DH;
-    const KVT* Vh = kv + ((int64_t)(1 * H + h) * rows_total + r0) * DH;
+    // one contiguous K/V block per spectrum: [K|V][H][S][DH], S = rows reserved per spectrum (r0 = b * S)
+    const int64_t S = rows_total;
+    const KVT* Kh = kv + (((int64_t)b * 2 + 0) * H + h) * S * DH;
+    const KVT* Vh = kv + (((int64_t)b * 2 + 1) * H + h) * S * DH;
     const float* bias = kbias_c + r0;
     float q[DH], acc[DH];
 #pragma unroll

@@ -48,7 +48,8 @@ struct TcGemmParams {
     int act;                  // 0 none, 1 ReLU
     float* out_f32; int64_t ld_f32;            // optional fp32 output
     __nv_bfloat16* out_b16; int64_t ld_b16;    // optional bf16 output
-    // head-major fp32 output (cross-attention K/V): C[((c/128)*heads + (c%128)/dh) * hm_rows + r][c % dh]
+    // cross-attention K/V output, one contiguous block per memory (spectrum): row r = b * hm_rows + j, column c ->
+    // C[(((b * 2 + c/128) * heads + (c%128)/dh) * hm_rows + j) * dh + c % dh]   (hm_rows = memory rows per spectrum)
     int head_major, hm_heads, hm_dh; int64_t hm_rows;
     // LayerNorm epilogue (N == 128): out = LN(acc + bias + res[r]) * gamma + beta
     const float* res; const float* gamma; const float* beta; float eps;
@@ -269,16 +270,20 @@ __device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, i
     const float* st = stage + lane * 4;
     if (p.head_major) {
         const int kv = col / D, cc = col % D;
-        const int kvh = kv * p.hm_heads + cc / p.hm_dh, hd = cc % p.hm_dh;
-        float* out32 = p.out_f32 ? p.out_f32 + ((int64_t)kvh * p.hm_rows + row0) * p.hm_dh + hd : nullptr;
-        __nv_bfloat16* out16 = p.out_b16 ? p.out_b16 + ((int64_t)kvh * p.hm_rows + row0) * p.hm_dh + hd : nullptr;
-        const int dh = p.hm_dh;
+        const int h = cc / p.hm_dh, hd = cc % p.hm_dh, dh = p.hm_dh;
+        const int S = (int)p.hm_rows;
+        int b = row0 / S, j = row0 - b * S;
+        const int64_t plane = (int64_t)S * dh;                         // one (spectrum, K|V, head) plane
+        int64_t o = (((int64_t)b * 2 + kv) * p.hm_heads + h) * plane + (int64_t)j * dh + hd;
+        const int64_t wrap = 2 * (int64_t)p.hm_heads * plane - plane;   // from the end of one spectrum's plane to the next spectrum's
 #pragma unroll 4
         for (int i = 0; i < rows; ++i) {
             const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS);
-            const float4 o = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
-            if (out32) *reinterpret_cast<float4*>(out32 + (int64_t)i * dh) = o;
-            if (out16) *reinterpret_cast<uint2*>(out16 + (int64_t)i * dh) = pack_bf16x4(o);
+            const float4 v = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+            if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + o) = pack_bf16x4(v);
+            o += dh;
+            if (++j == S) { j = 0; o += wrap; }
         }
         return;
     }

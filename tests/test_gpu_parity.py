@@ -350,3 +350,39 @@ def test_ragged_encoder_falls_back_when_padding_hides_data():
     np.testing.assert_allclose(memory.cpu().numpy(), omem.numpy(), atol=5e-5, rtol=0)
     rows = memory[:64, 0][pad[0].cuda()]
     assert not torch.equal(rows, rows[:1].expand_as(rows))        # the padded rows really are distinct here
+
+
+# --------------------------------------------------------------------------- ids -> SMILES
+def _ref_tensor_to_smiles_and_prob_2(tensor, token_prob, itos):
+    """The reference's element-by-element loop (helper_functions_pl_v15_4.py:390-410), restated for the check."""
+    seqs, cut = [], []
+    for i in range(tensor.shape[1]):
+        seq = []
+        for j in range(tensor.shape[0]):
+            tok = itos[str(int(tensor[j, i]))]
+            if tok == "<EOS>":
+                break
+            seq.append(tok)
+        seqs.append("".join(seq))
+        cut.append(token_prob[:len(seq), i])
+    return seqs, cut
+
+
+def test_tensor_to_smiles_matches_reference_loop():
+    s = setup()
+    itos = {str(i): f"t{i}|" for i in range(43)}
+    itos.update({"0": "<PAD>", "2": "<EOS>", "3": "<SOS>"})
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(0, 43, (128, 300), generator=g)
+    tok[:, 5] = 7                        # never emits <EOS>
+    tok[0, 6] = 2                        # <EOS> first -> empty string
+    pr = torch.rand(128, 300, generator=g)
+    ref_s, ref_p = _ref_tensor_to_smiles_and_prob_2(tok, pr, itos)
+    got_s, got_p = s["M"].tensor_to_smiles_and_prob_2(tok.cuda(), pr.cuda(), itos)
+    assert got_s == ref_s and got_s[6] == "" and len(got_p) == 300
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(got_p, ref_p))
+    assert s["M"].tensor_to_smiles(tok.cuda(), itos) == ref_s
+    got_s1, got_p1 = s["M"].tensor_to_smiles_and_prob(tok.cuda(), pr.t().contiguous().cuda(), itos)   # (N,T) probabilities
+    assert got_s1 == ref_s and all(torch.equal(a.cpu(), b) for a, b in zip(got_p1, ref_p))
+    one_s, one_p = s["M"].tensor_to_smiles_and_prob_2(tok[:, 9].cuda(), pr[:, 9].cuda(), itos)
+    assert one_s == ref_s[9] and torch.equal(one_p.cpu(), ref_p[9])
