@@ -112,7 +112,8 @@ def test_multinomial_bf16_candidates():
 
 
 @pytest.mark.parametrize("M,F,splits", [(256, 2048, 1), (256, 2048, 16), (256, 2048, 32), (77, 2048, 8), (1000, 2048, 1),
-                                         (4097, 2048, 1), (130, 512, 2), (128, 64, 1)])
+                                         (4097, 2048, 1), (130, 512, 2), (128, 64, 1),
+                                         (40001, 2048, 1)])     # >= 2 tiles per SM: two row tiles per CTA, odd tile count
 def test_ffn_fused_tcgen05(M, F, splits):
     """Fused FFN kernel == fp64 evaluation of the same contract: bf16(x) . (W1_hi + W1_lo), bias, ReLU, hidden
     rounded to bf16, . (W2_hi + W2_lo), + b2 + x (fp32 residual), LayerNorm."""
