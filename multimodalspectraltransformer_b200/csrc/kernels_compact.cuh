@@ -103,7 +103,8 @@ struct CompactScanParams {
     int* moff;        // [5][B]    offset of modality m inside a spectrum's cross rows
     int* nk_c;        // [B]       attendable cross rows of a spectrum
     int* ccnt;        // [B]       cross rows of a spectrum
-    int* totals;      // [8]: rows of modality 0..4, cross rows, flag copy (host reads these)
+    int* totals;      // [16]: rows of modality 0..4, cross rows, flag copy, max cross keys / rows per spectrum,
+                      //       [9+m] max rows per spectrum of modality m (host reads these)
     const int* flag;
 };
 // single CTA: six serial prefix sums over <= 256 spectra
@@ -130,6 +131,15 @@ __global__ void __launch_bounds__(256) compact_scan(const CompactScanParams p) {
         p.cstart[p.B] = run;
         p.totals[5] = run;
         p.totals[6] = *p.flag;
+    } else if (t == 6) {
+        int mk = 0, mr = 0;
+        for (int b = 0; b < p.B; ++b) { mk = max(mk, p.nk_c[b]); mr = max(mr, p.ccnt[b]); }
+        p.totals[7] = mk; p.totals[8] = mr;
+    } else if (t >= 7 && t < 12) {
+        const int m = t - 7;
+        int mr = 0;
+        for (int b = 0; b < p.B; ++b) mr = max(mr, p.cnt[m * p.B + b]);
+        p.totals[9 + m] = mr;
     }
 }
 

@@ -377,6 +377,7 @@ struct AttnGroup {
     // ragged encoder: sequence b owns rows [row_start[b], row_start[b] + cnt[b]); kidx rows are kstride apart;
     // every listed key is attendable with bias 0 (kbias == nullptr)
     const int* row_start; const int* cnt; int kstride;
+    int smax;              // rows of the K / V staging areas in shared memory (>= keys of any sequence in the launch)
 };
 struct AttnParams { AttnGroup g[GEMM_MAX_GROUPS]; float scale; };
 
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
     const AttnGroup& g = p.g[blockIdx.z];
     const int h = blockIdx.x, b = blockIdx.y;
     const int S = g.cnt ? g.cnt[b] : g.S;            // query rows of this sequence
-    const int Smax = g.S;                            // smem carve-up bound (host sizes smem for it)
+    const int Smax = g.smax;                         // smem carve-up bound (host sizes smem for it)
     const int kstride = g.cnt ? g.kstride : g.S;
     const int64_t row0 = g.row_start ? (int64_t)g.row_start[b] : (int64_t)b * g.S;
     const int nk = g.nk[b];
