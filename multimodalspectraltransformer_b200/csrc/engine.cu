@@ -330,43 +330,57 @@ struct EncGroupRun {
     __nv_bfloat16 *x16, *att16, *h16, *out16;
     // ragged encoder (kernels_compact.cuh): per-sequence row ranges, key-list stride, explicit output rows
     const int *row_start, *cnt; int kstride; const int* out_rows;
+    int max_keys, max_rows;   // ragged: actual per-sequence maxima (size the attention CTA: smem carve-up, threads); 0 = S
 };
 
-static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
-    int maxM = 0, maxS = 0;
-    for (int i = 0; i < ng; ++i) { maxM = std::max(maxM, gr[i].rows); maxS = std::max(maxS, gr[i].S); }
+// Encoder self-attention launch over `ng` groups.  Shared memory and the CTA width are sized for the keys / query rows a
+// sequence can actually have (ragged encoder: per-batch maxima from the index kernels) -- 60 KB instead of 151 KB per CTA
+// in the cross encoder, i.e. three resident CTAs per SM instead of one for this latency-bound kernel.
+static int launch_encoder_attention(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, bool bf16_out, cudaStream_t s) {
     const int dh = D / heads;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.scale = 1.0f / sqrtf((float)dh);
+    int key_bound = 0, row_bound = 0;
+    for (int i = 0; i < ng; ++i) {
+        const bool ragged = gr[i].cnt != nullptr;
+        const int kb = (ragged && gr[i].max_keys > 0) ? gr[i].max_keys : gr[i].S;
+        const int rb = (ragged && gr[i].max_rows > 0) ? gr[i].max_rows : gr[i].S;
+        key_bound = std::max(key_bound, kb); row_bound = std::max(row_bound, rb);
+        p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk;
+        p.g[i].out = bf16_out ? nullptr : gr[i].att; p.g[i].out16 = bf16_out ? gr[i].att16 : nullptr;
+        p.g[i].S = gr[i].S;
+        p.g[i].row_start = gr[i].row_start; p.g[i].cnt = gr[i].cnt; p.g[i].kstride = gr[i].kstride;
+    }
+    for (int i = 0; i < ng; ++i) p.g[i].smax = key_bound;
+    dim3 grid(heads, Bc, ng);
+    const size_t smem = (size_t)key_bound * (2 * dh + 1) * sizeof(float);
+    const int threads = std::min(256, std::max(64, (row_bound + 31) / 32 * 32));
+    if (dh == 8) {
+        MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_pre(e, s);
+        attn_encoder_f32<8><<<grid, threads, smem, s>>>(p);
+    } else if (dh == 32) {
+        MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_pre(e, s);
+        attn_encoder_f32<32><<<grid, threads, smem, s>>>(p);
+    } else if (dh == 16) {
+        MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_pre(e, s);
+        attn_encoder_f32<16><<<grid, threads, smem, s>>>(p);
+    } else MMT_FAIL("unsupported head dim " + std::to_string(dh));
+    return check_launch(e, "attn_encoder_f32", s);
+}
+
+static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
+    int maxM = 0;
+    for (int i = 0; i < ng; ++i) maxM = std::max(maxM, gr[i].rows);
     {   // QKV projection
         GemmParams p = gemm_params(3 * D, D, 3 * D, 0);
         for (int i = 0; i < ng; ++i) { p.g[i].A = gr[i].X; p.g[i].lda = D; p.g[i].W = gr[i].w->in_w; p.g[i].bias = gr[i].w->in_b; p.g[i].C = gr[i].qkv; p.g[i].M = gr[i].rows; }
         MMT_TRY(launch_gemm(e, p, ng, maxM, s));
     }
-    {   // attention
-        AttnParams p;
-        memset(&p, 0, sizeof(p));
-        p.scale = 1.0f / sqrtf((float)dh);
-        for (int i = 0; i < ng; ++i) {
-            p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = gr[i].att; p.g[i].S = gr[i].S;
-            p.g[i].row_start = gr[i].row_start; p.g[i].cnt = gr[i].cnt; p.g[i].kstride = gr[i].kstride;
-        }
-        dim3 grid(heads, Bc, ng);
-        size_t smem = (size_t)maxS * (2 * dh + 1) * sizeof(float);
-        int threads = maxS > 256 ? 256 : 128;
-        if (dh == 8) {
-            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_pre(e, s);
-            attn_encoder_f32<8><<<grid, threads, smem, s>>>(p);
-        } else if (dh == 32) {
-            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_pre(e, s);
-            attn_encoder_f32<32><<<grid, threads, smem, s>>>(p);
-        } else if (dh == 16) {
-            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_pre(e, s);
-            attn_encoder_f32<16><<<grid, threads, smem, s>>>(p);
-        } else MMT_FAIL("unsupported head dim " + std::to_string(dh));
-        MMT_TRY(check_launch(e, "attn_encoder_f32", s));
-    }
+    MMT_TRY(launch_encoder_attention(e, gr, ng, Bc, heads, false, s));
     {   // out-proj -> +residual -> LN1 (in place on X)
         GemmParams p = gemm_params(D, D, D, 0);
         for (int i = 0; i < ng; ++i) { p.g[i].A = gr[i].att; p.g[i].lda = D; p.g[i].W = gr[i].w->out_w; p.g[i].C = gr[i].part; p.g[i].M = gr[i].rows; }
@@ -406,40 +420,12 @@ static int encoder_layer_fp32(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
 // The same layer with every projection on the tensor cores (bf16 operands, fp32 accumulate);
 // residual stream, LayerNorm statistics and the attention softmax stay fp32.
 static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, int heads, int d_ff, cudaStream_t s) {
-    int maxS = 0;
-    for (int i = 0; i < ng; ++i) maxS = std::max(maxS, gr[i].S);
-    const int dh = D / heads;
     for (int i = 0; i < ng; ++i) {   // QKV projection -> fp32 (the attention kernel's softmax input)
         TcGemmParams p = tc_params(gr[i].rows, 3 * D, D);
         p.bias = gr[i].w->in_b; p.out_f32 = gr[i].qkv; p.ld_f32 = 3 * D;
         MMT_TRY(launch_tc(e, p, gr[i].x16, D, e->Wb(gr[i].w->in_w), TC_EPI_STORE, s, e->Wlo(gr[i].w->in_w)));
     }
-    {
-        AttnParams p;
-        memset(&p, 0, sizeof(p));
-        p.scale = 1.0f / sqrtf((float)dh);
-        for (int i = 0; i < ng; ++i) {
-            p.g[i].qkv = gr[i].qkv; p.g[i].kbias = gr[i].kbias; p.g[i].kidx = gr[i].kidx; p.g[i].nk = gr[i].nk; p.g[i].out = nullptr; p.g[i].out16 = gr[i].att16; p.g[i].S = gr[i].S;
-            p.g[i].row_start = gr[i].row_start; p.g[i].cnt = gr[i].cnt; p.g[i].kstride = gr[i].kstride;
-        }
-        dim3 grid(heads, Bc, ng);
-        size_t smem = (size_t)maxS * (2 * dh + 1) * sizeof(float);
-        int threads = maxS > 256 ? 256 : 128;
-        if (dh == 8) {
-            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_pre(e, s);
-            attn_encoder_f32<8><<<grid, threads, smem, s>>>(p);
-        } else if (dh == 32) {
-            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_pre(e, s);
-            attn_encoder_f32<32><<<grid, threads, smem, s>>>(p);
-        } else if (dh == 16) {
-            MMT_CUDA(cudaFuncSetAttribute(attn_encoder_f32<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prof_pre(e, s);
-            attn_encoder_f32<16><<<grid, threads, smem, s>>>(p);
-        } else MMT_FAIL("unsupported head dim " + std::to_string(dh));
-        MMT_TRY(check_launch(e, "attn_encoder_f32", s));
-    }
+    MMT_TRY(launch_encoder_attention(e, gr, ng, Bc, heads, true, s));
     for (int i = 0; i < ng; ++i) {   // out-proj + residual + LN1, in place on X (fp32) and X16
         TcGemmParams p = tc_params(gr[i].rows, D, D);
         p.bias = gr[i].w->out_b; p.res = gr[i].X; p.gamma = gr[i].w->n1_w; p.beta = gr[i].w->n1_b;
@@ -480,7 +466,7 @@ static int encode_chunk_compact(mmt_engine* e, const mmt_spectra& in, int b0, in
         ix.cnt = a.get<int>(5 * Bc); ix.nkeys = a.get<int>(5 * Bc);
         ix.d2c = a.get<int>((size_t)5 * Bc * CP_SMAX); ix.kidx = a.get<int>((size_t)5 * Bc * CP_SMAX);
         ix.flag = a.get<int>(1); ix.row_start = a.get<int>(5 * (Bc + 1)); ix.cstart = a.get<int>(Bc + 1);
-        ix.moff = a.get<int>(5 * Bc); ix.nk_c = a.get<int>(Bc); ix.ccnt = a.get<int>(Bc); ix.totals = a.get<int>(8);
+        ix.moff = a.get<int>(5 * Bc); ix.nk_c = a.get<int>(Bc); ix.ccnt = a.get<int>(Bc); ix.totals = a.get<int>(16);
         ix.out_rows = a.get<int>((size_t)5 * Bc * maxS); ix.kidx_c = a.get<int>(R);
         int64_t rows_mod = 0;
         for (int m = 0; m < 5; ++m) { X[m] = a.get<float>((size_t)Bc * L.S_m[m] * D); rows_mod += (int64_t)Bc * L.S_m[m]; }
@@ -544,13 +530,16 @@ static int encode_chunk_compact(mmt_engine* e, const mmt_spectra& in, int b0, in
         prof_pre(e, s);
         compact_cross_index<<<Bc, 32, 0, s>>>(c);
         MMT_TRY(check_launch(e, "compact_cross_index", s));
-        MMT_CUDA(cudaMemcpyAsync(e->h_pinned, ix.totals, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MMT_CUDA(cudaMemcpyAsync(e->h_pinned, ix.totals, 16 * sizeof(int), cudaMemcpyDeviceToHost, s));
         MMT_CUDA(cudaStreamSynchronize(s));
     }
     int rows_m[5];
     for (int m = 0; m < 5; ++m) rows_m[m] = e->h_pinned[m];
     const int rows_c = e->h_pinned[5];
     if (e->h_pinned[6] != 0) return 2;
+    const int max_keys_c = e->h_pinned[7], max_rows_c = e->h_pinned[8];
+    int max_rows_m = 0;
+    for (int m = 0; m < 5; ++m) max_rows_m = std::max(max_rows_m, e->h_pinned[9 + m]);
 
     // ---- IR projection 1000 -> 128 (+ReLU)
     {
@@ -609,6 +598,7 @@ static int encode_chunk_compact(mmt_engine* e, const mmt_spectra& in, int b0, in
             g.X = X[m]; g.rows = rows_m[m]; g.S = L.S_m[m];
             g.kbias = nullptr; g.kidx = ix.kidx + (size_t)m * Bc * CP_SMAX; g.nk = ix.nkeys + m * Bc;
             g.row_start = ix.row_start + m * (Bc + 1); g.cnt = ix.cnt + m * Bc; g.kstride = CP_SMAX;
+            g.max_keys = max_rows_m; g.max_rows = max_rows_m;
             g.qkv = QKV + row_off * 3 * D;
             if (bf16) { g.x16 = X16[m]; g.att16 = ATT16 + row_off * D; }
             else { g.att = ATT + row_off * D; g.part = PART + row_off * D; g.h = H + row_off * d.d_ff; }
@@ -632,6 +622,7 @@ static int encode_chunk_compact(mmt_engine* e, const mmt_spectra& in, int b0, in
         memset(&g, 0, sizeof(g));
         g.X = Xc; g.rows = rows_c; g.S = L.S_total; g.kbias = nullptr; g.kidx = ix.kidx_c; g.nk = ix.nk_c;
         g.row_start = ix.cstart; g.cnt = ix.ccnt; g.kstride = L.S_total;
+        g.max_keys = max_keys_c; g.max_rows = max_rows_c;
         g.qkv = QKV; g.att = ATT; g.part = PART; g.h = H;
         g.x16 = Xc16; g.att16 = ATT16;
         for (int l = 0; l < d.n_enc_layers; ++l) {
@@ -1279,7 +1270,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     e->reg = build_registry(*desc);
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
     if (getenv("MMT_NO_PDL")) e->use_pdl = false;
-    if (getenv("MMT_FFN_ONE_TILE")) e->ffn_tiles2 = false;
+    if (getenv("MMT_FFN_TWO_TILES")) e->ffn_tiles2 = true;
     if (const char* v = getenv("MMT_DECODE_LANES")) e->decode_lanes = std::max(1, atoi(v));
     if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);

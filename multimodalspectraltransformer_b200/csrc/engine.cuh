@@ -118,7 +118,8 @@ struct mmt_engine {
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
-    bool ffn_tiles2 = true;            // fused FFN: two row tiles per CTA on large M (MMT_FFN_ONE_TILE=1 disables)
+    bool ffn_tiles2 = false;           // fused FFN: two row tiles per CTA on large M (MMT_FFN_TWO_TILES=1 enables; measured neutral: the chunk
+                                       // loop is bound by shared-memory operand reads, not by the L2 weight stream)
     bool use_pdl = true;               // programmatic dependent launch between the kernels of a fused decode step (MMT_NO_PDL=1 disables)
     cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only streams, one per decode lane (the caller's stream may be the legacy default stream)
     cudaEvent_t lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};       // fork / join events of the lane branches
