@@ -29,7 +29,8 @@ METRIC = "generated SMILES tokens/sec"
 UNIT = "tokens/s"
 B_PER_GPU = 256
 MAX_LEN = 128
-REF_SAMPLE_SPECTRA = 8          # BASELINE.json configs[0]: the reference's CPU-runnable case
+REF_SAMPLE_SPECTRA = 32         # --impl reference: spectra per step (a bounded sample of the 256; BASELINE configs[0] uses 8)
+CPU_BASELINE_SPECTRA = 64       # cpu_baseline leg of the main arm: one pass, ~10-30 s of CPU work
 STOI = {"<PAD>": 0, "<UNK>": 1, "<EOS>": 2, "<SOS>": 3, "<MASK>": 4}
 # algorithmic work model (SURVEY.md 8d / BASELINE.md 4)
 FLOP_ENCODE_PER_SPECTRUM = 9.50e9
@@ -277,6 +278,14 @@ def main():
                 "traffic": None, "peak_source": pk["src"]}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    try:     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if dom in tj and precision == "bf16":
+            roof["traffic"] = tj[dom]["dram_bytes_read"] + tj[dom]["dram_bytes_write"]
+            roof["traffic_source"] = "profiles/r01_ncu_traffic.json (one ncu --set full capture of this command)"
+            roof["algorithmic_bytes_per_launch"] = alg_bytes.get(dom)
+    except (OSError, ValueError, KeyError):
+        pass
     roof["share_of_step"] = d["ms"] / total_ms if total_ms else None
     roof["launch_us"] = per_launch_ms * 1e3
     roof["kernels"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
@@ -291,9 +300,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "wall_s": {"resident": wall_res, "e2e": wall_e2e}}
         if world == 1 and not args.no_cpu_baseline:
-            v, toks, sec, threads = cpu_reference_tokens_per_s(REF_SAMPLE_SPECTRA, steps=1, warmup=0)
+            v, toks, sec, threads = cpu_reference_tokens_per_s(CPU_BASELINE_SPECTRA, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{REF_SAMPLE_SPECTRA} spectra x {MAX_LEN} greedy steps ({toks} tokens, {sec:.1f} s) of the same workload, "
+                                    "sample": f"{CPU_BASELINE_SPECTRA} of the {B_PER_GPU} spectra x {MAX_LEN} greedy steps ({toks} tokens, {sec:.1f} s) of the same workload, "
                                               "oracle port of the reference's full-prefix loop on the host cores"}
         print(json.dumps(line), flush=True)
     if world > 1:
