@@ -951,6 +951,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             q.in_w = w.in_w; q.in_b = w.in_b; q.out_w = w.out_w; q.out_b = w.out_b; q.n1_w = w.n1_w; q.n1_b = w.n1_b;
             q.kv_pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz; q.block_table = b.block_table; q.pps = pps;
             q.step = step;
+            q.in_w16 = e->Wb(w.in_w); q.out_w16 = e->Wb(w.out_w); q.cq_w16 = e->Wb(w.ca_in_w); q.co_w16 = e->Wb(w.ca_out_w);
             q.cq_w = w.ca_in_w; q.cq_b = w.ca_in_b; q.co_w = w.ca_out_w; q.co_b = w.ca_out_b; q.n2_w = w.n2_w; q.n2_b = w.n2_b;
             q.ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz; q.rows_total = a.S;
             q.nk = b.nk; q.row_start = b.row_start; q.kbias_c = b.kbias_c; q.n_cand = a.n_cand;

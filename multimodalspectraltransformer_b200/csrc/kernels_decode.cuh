@@ -19,8 +19,11 @@
 //     kernel start (no registers held), so that HBM stream overlaps the self-attention phases;
 //   * one warp per (row, head): every per-warp index / page-table load is issued up front.
 //
-// Arithmetic is fp32 in both precision modes (these projections are 20 % of the decoder's weights
-// and the larger share of the bf16 logit error, DESIGN.md "bf16 numerics").
+// Arithmetic is fp32 FMA with fp32 activations in both precision modes.  The kernel is bound by the bytes an
+// SM can pull in (~30 B/cycle measured for LDG and TMA alike: profiles/micro/load_latency.cu), and the fp32
+// weights were 57 % of them; in the tensor-core mode the four projection matrices are therefore read as bf16
+// (the hi term of the two-term split: measured logit error unchanged, DESIGN.md "bf16 numerics"), which also
+// lets all four sit in shared memory at once -- every weight copy is issued before the PDL wait.
 //
 // Shape of the work: the kernels are pure latency chains (L2 / HBM round trips), so a CTA is a full
 // 1024-thread SM's worth of warps for DA_R rows: one warp per (row, head) in the attention phases,
@@ -86,6 +89,34 @@ __device__ __forceinline__ void gemv_rows(const float* W, const float* bias, int
     }
 }
 
+// the same with bf16 weights in shared memory (row-major [n_out][128]): lane owns k = 4 lane .. 4 lane + 3
+__device__ __forceinline__ void gemv_rows_w16(const __nv_bfloat16* W, const float* bias, int n_out,
+                                              const float (*xs)[D], float* out, int ldo, int warp, int lane) {
+    float4 xr[DA_R];
+#pragma unroll
+    for (int r = 0; r < DA_R; ++r) xr[r] = *reinterpret_cast<const float4*>(&xs[r][4 * lane]);
+    for (int n0 = warp * 16; n0 < n_out; n0 += DA_WARPS * 16) {
+        float acc[DA_R][16];
+        const uint2* wp = reinterpret_cast<const uint2*>(W + n0 * D) + lane;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint2 u = wp[j * (D / 4)];
+            const float w0 = __uint_as_float(u.x << 16), w1 = __uint_as_float(u.x & 0xffff0000u);
+            const float w2 = __uint_as_float(u.y << 16), w3 = __uint_as_float(u.y & 0xffff0000u);
+#pragma unroll
+            for (int r = 0; r < DA_R; ++r)
+                acc[r][j] = fmaf(w3, xr[r].w, fmaf(w2, xr[r].z, fmaf(w1, xr[r].y, w0 * xr[r].x)));
+        }
+        const int n = n0 + ((lane >> 1) & 15);
+        const float b = bias[n];
+#pragma unroll
+        for (int r = 0; r < DA_R; ++r) {
+            const float v = reduce_scatter16(acc[r], lane) + b;
+            if (!(lane & 1)) out[r * ldo + n] = v;
+        }
+    }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- bulk async copy global -> shared, completion on an mbarrier (same primitives as kernels_tc.cuh)
@@ -136,6 +167,8 @@ struct DecAttnParams {
     const int* nk; const int* row_start; const float* kbias_c; int n_cand;
     float* x2; __nv_bfloat16* x2_16;           // out [M][D] fp32 (+ bf16 operand copy for the FFN, optional)
     int64_t M; float scale; float eps;
+    // tensor-core mode: the four projection matrices as bf16 (hi term of the two-term split), same shapes as the fp32 ones
+    const __nv_bfloat16 *in_w16, *out_w16, *cq_w16, *co_w16;
     long long* dbg;                            // optional [gridDim.x][16] phase timestamps (MMT_DA_DEBUG)
 };
 
@@ -144,7 +177,9 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     static_assert(DH == 8 && DH * DA_H == D, "8-element key rows, 16 heads");
     typedef KvRow<KVT> KV;
     extern __shared__ __align__(128) uint8_t da_smem[];
+    constexpr bool W16 = sizeof(KVT) == 2;            // tensor-core mode: bf16 projection weights, all four resident at once
     float* Wbuf = reinterpret_cast<float*>(da_smem);
+    __nv_bfloat16* Wb16 = reinterpret_cast<__nv_bfloat16*>(da_smem);    // W16 layout: in_w [384][128] | out_w | cq_w | co_w (192 KB)
     float* Ps = Wbuf + DA_W_FLOATS;
     __shared__ __align__(8) uint64_t bars[4];      // 0: in_w + vectors, 1: out_w, 2: cq_w, 3: co_w
     __shared__ __align__(16) float xs[DA_R][D];
@@ -169,15 +204,24 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             for (int i = 0; i < 4; ++i) da_mbar_init(&bars[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const uint32_t vec_bytes = (uint32_t)(3 * D + 7 * D + (p.part ? 3 * D : 0)) * 4u;
-            da_mbar_expect_tx(&bars[0], (uint32_t)DA_W_FLOATS * 4u + vec_bytes);
+            da_mbar_expect_tx(&bars[0], (W16 ? 3u * D * D * 2u : (uint32_t)DA_W_FLOATS * 4u) + vec_bytes);
+            if (W16) for (int i = 1; i < 4; ++i) da_mbar_expect_tx(&bars[i], D * D * 2);
         }
         __syncwarp();
-        if (lane == 0) {
+        if (W16) {
+            if (lane < 12) {     // 12 pieces of 16 KB: in_w (6), out_w (2), cq_w (2), co_w (2) -- all before the PDL wait
+                const int m = lane < 6 ? 0 : (lane - 4) >> 1;                        // matrix 0..3
+                const int piece = lane < 6 ? lane : (lane & 1);
+                const __nv_bfloat16* src = (m == 0 ? p.in_w16 : (m == 1 ? p.out_w16 : (m == 2 ? p.cq_w16 : p.co_w16))) + piece * 8192;
+                da_bulk_g2s(Wb16 + (size_t)lane * 8192, src, 8192 * 2, &bars[m]);
+            }
+        } else if (lane == 0) {
             // every CTA reads the same matrix in the same order: requests for one line from many SMs that
             // arrive close together are merged by L2 (measured: a per-CTA rotated order is 2x slower)
             for (int piece = 0; piece < 12; ++piece)
                 da_bulk_g2s(Wbuf + piece * 4096, p.in_w + piece * 4096, 4096 * 4, &bars[0]);
-        } else if (lane >= 12) {
+        }
+        if (lane >= 12) {
             const float* src = nullptr; int dst = 0, nf = D;
             switch (lane) {
                 case 12: src = p.in_b; dst = DA_P_INB; nf = 3 * D; break;
@@ -211,6 +255,16 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     constexpr int PF = 64 / (int)sizeof(KVT);     // elements per 64-byte prefetch granule
     // L2 prefetch of this warp's cross-attention K/V rows (64-byte granules; consumed in the second half)
     for (int g = lane; g * PF < cnt * DH; g += 32) { prefetch_l2(Kc + g * PF); prefetch_l2(Vc + g * PF); }
+#ifdef DA_TLB_WARM
+    if (live) {   // experiment: touch the pages this warp will read later (address translation warmed up off the critical path)
+        const int pg0 = __shfl_sync(0xffffffffu, my_page, 0);
+        const KVT* kp = reinterpret_cast<const KVT*>(p.kv_pool) + (int64_t)pg0 * (2 * PAGE_TOKENS * D) + (h * PAGE_TOKENS) * DH;
+        unsigned d0, d1;
+        asm volatile("ld.global.u32 %0, [%1];" : "=r"(d0) : "l"(kp + lane * 8) : "memory");
+        asm volatile("ld.global.u32 %0, [%1];" : "=r"(d1) : "l"(Kc + lane * 8) : "memory");
+        if ((d0 ^ d1) == 0x12345679u) printf("x");     // keep the loads
+    }
+#endif
     // ---- everything above reads only decode-loop constants; from here on the previous kernel's results are needed
     pdl_wait();
     const int t = *p.step;
@@ -276,13 +330,14 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
 
     DA_STAMP(2);
     // ---- QKV projection (384 outputs) from shared memory
-    gemv_rows(Wbuf, Ps + DA_P_INB, 3 * D, xs, &qkv[0][0], 3 * D, warp, lane);
+    if (W16) gemv_rows_w16(Wb16, Ps + DA_P_INB, 3 * D, xs, &qkv[0][0], 3 * D, warp, lane);
+    else gemv_rows(Wbuf, Ps + DA_P_INB, 3 * D, xs, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
     DA_STAMP(3);
     // the QKV matrix is dead after the barrier above: the three 128x128 matrices of the later phases are pulled
     // into its place (issued by warp 0 from inside the attention phase, see DA_ISSUE_ROUND2)
 #define DA_ISSUE_ROUND2() do {                                                                              \
-        if (warp == 0) {                                                                                    \
+        if (!W16 && warp == 0) {                                                                                  \
             if (lane < 3) da_mbar_expect_tx(&bars[1 + lane], D * D * 4);                                    \
             __syncwarp();                                                                                   \
             if (lane < 12) {                                                                                \
@@ -392,7 +447,8 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     // ---- out-projection -> qkv[r][0..127] (reused as scratch), then LN1
     da_mbar_wait(&bars[1], 0);
     DA_STAMP(5);
-    gemv_rows(Wbuf, Ps + DA_P_OUTB, D, att, &qkv[0][0], 3 * D, warp, lane);
+    if (W16) gemv_rows_w16(Wb16 + 3 * D * D, Ps + DA_P_OUTB, D, att, &qkv[0][0], 3 * D, warp, lane);
+    else gemv_rows(Wbuf, Ps + DA_P_OUTB, D, att, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
     if (warp < DA_R) {
         const float4 a = *reinterpret_cast<const float4*>(&xs[warp][lane * 4]);
@@ -405,7 +461,8 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     DA_STAMP(6);
     // ---- cross-attention query projection -> xs (the layer input is no longer needed)
     da_mbar_wait(&bars[2], 0);
-    gemv_rows(Wbuf + D * D, Ps + DA_P_CQB, D, x1s, &xs[0][0], D, warp, lane);
+    if (W16) gemv_rows_w16(Wb16 + 4 * D * D, Ps + DA_P_CQB, D, x1s, &xs[0][0], D, warp, lane);
+    else gemv_rows(Wbuf + D * D, Ps + DA_P_CQB, D, x1s, &xs[0][0], D, warp, lane);
     __syncthreads();
     DA_STAMP(7);
 
@@ -464,7 +521,8 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
 
     // ---- cross out-projection -> qkv scratch, then LN2 -> x2
     da_mbar_wait(&bars[3], 0);
-    gemv_rows(Wbuf + 2 * D * D, Ps + DA_P_COB, D, att, &qkv[0][0], 3 * D, warp, lane);
+    if (W16) gemv_rows_w16(Wb16 + 5 * D * D, Ps + DA_P_COB, D, att, &qkv[0][0], 3 * D, warp, lane);
+    else gemv_rows(Wbuf + 2 * D * D, Ps + DA_P_COB, D, att, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
     DA_STAMP(9);
     if (warp < DA_R) {
