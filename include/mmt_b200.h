@@ -177,6 +177,20 @@ uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threa
 int32_t mmt_pack_tokens_u8(const int64_t* d_tokens, int64_t n, uint8_t* d_out, void* stream);
 int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, void* stream);
 
+/* ---- ragged ingest (the data format in front of the path) -------------------------- */
+
+/* Replaces MultimodalData._zero_pad + the per-modality normalisation of __getitem__
+ * (dataloaders_pl_v15_4.py:267-299, 352-365, 456-460, 481-485, 505-509, 546-550): CSR peak lists
+ * (d_values: nnz x cols doubles, d_offsets: B+1 int64) -> d_src (B,P[,cols]) f32 = value / div_c rounded like
+ * torch.tensor(python floats), zero padded, truncated at P; d_mask (B,P) f32, 0 valid / 1 pad.  cols == 1
+ * reproduces the reference's all-ones mask for lists with >= P entries. */
+int32_t mmt_ingest_peaks(const double* d_values, const int64_t* d_offsets, int32_t B, int32_t cols,
+                         double div0, double div1, int32_t pad_points, float* d_src, float* d_mask, void* stream);
+/* Replaces MultimodalData._load_IR_data's binning (dataloaders_pl_v15_4.py:324-346): every spectrum of
+ * arbitrary length -> `bins` mean-binned values divided by the spectrum's maximum, (B,bins) f32. */
+int32_t mmt_ingest_ir(const double* d_values, const int64_t* d_offsets, int32_t B, int32_t bins,
+                      float* d_src_IR, void* stream);
+
 /* Replaces the per-element .item() scans of tensor_to_smiles / tensor_to_smiles_and_prob(_2)
  * (helper_functions_pl_v15_4.py:255-301, 390-419): d_len[n] = position of the first `eos` id in column n
  * of d_tokens (T,N) i64, or T if the sequence never emits it.  The host then slices tokens / probabilities

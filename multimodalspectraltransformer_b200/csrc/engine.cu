@@ -1394,6 +1394,25 @@ int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, 
     return 0;
 }
 
+int32_t mmt_ingest_peaks(const double* d_values, const int64_t* d_offsets, int32_t B, int32_t cols, double div0, double div1,
+                         int32_t pad_points, float* d_src, float* d_mask, void* stream) {
+    if (!d_values || !d_offsets || !d_src || !d_mask) MMT_FAIL("null argument");
+    if (cols != 1 && cols != 2) MMT_FAIL("ingest: cols must be 1 or 2");
+    if (B <= 0 || pad_points <= 0) return 0;
+    ingest_peaks<<<B, 64, 0, (cudaStream_t)stream>>>(d_values, d_offsets, cols, div0, div1, pad_points, cols == 1 ? 1 : 0, d_src, d_mask);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int32_t mmt_ingest_ir(const double* d_values, const int64_t* d_offsets, int32_t B, int32_t bins, float* d_src_IR, void* stream) {
+    if (!d_values || !d_offsets || !d_src_IR) MMT_FAIL("null argument");
+    if (B <= 0 || bins <= 0) return 0;
+    if (bins > 8192) MMT_FAIL("ingest: too many IR bins");
+    ingest_ir<<<B, 256, (size_t)(bins + 1) * sizeof(int), (cudaStream_t)stream>>>(d_values, d_offsets, bins, d_src_IR);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int32_t mmt_first_eos(const int64_t* d_tokens, int32_t T, int64_t N, int32_t eos, int32_t* d_len, void* stream) {
     if (!d_tokens || !d_len) MMT_FAIL("null argument");
     if (N <= 0 || T <= 0) return 0;

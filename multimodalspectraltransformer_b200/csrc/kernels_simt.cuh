@@ -813,6 +813,54 @@ __global__ void first_eos_scan(const int64_t* tokens, int T, int64_t N, int eos,
     len[n] = L;
 }
 
+// Ragged ingest (reference dataloaders_pl_v15_4.py:267-299 _zero_pad, :352-365 / :456-460 / :481-485 normalisation):
+// CSR peak lists -> the padded (B,P[,cols]) fp32 tensor + (B,P) mask of the collate contract.  Values are divided in
+// double like the reference's Python floats, then rounded to fp32 (torch.tensor of Python floats).  Peaks beyond P are
+// dropped.  `quirk_1d`: the reference's 1-D branch leaves the mask all-ones when a list has >= P entries.
+__global__ void __launch_bounds__(64) ingest_peaks(const double* vals, const int64_t* off, int cols, double div0, double div1,
+                                                   int P, int quirk_1d, float* src, float* mask) {
+    const int b = blockIdx.x;
+    const int64_t o = off[b];
+    const int64_t n = off[b + 1] - o;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const bool have = i < n;
+        for (int c = 0; c < cols; ++c)
+            src[((int64_t)b * P + i) * cols + c] = have ? (float)(vals[(o + i) * cols + c] / (c == 0 ? div0 : div1)) : 0.f;
+        mask[(int64_t)b * P + i] = (quirk_1d && n >= P) ? 1.f : (have ? 0.f : 1.f);
+    }
+}
+
+// IR spectrum -> `bins` mean-binned, max-normalised values (dataloaders_pl_v15_4.py:324-346): bin i averages
+// spectra[round(start_i) : round(start_i + span)] with span = len / bins, start accumulated in double exactly like the
+// reference's loop (Python round = round-half-even = rint), divided by the spectrum's maximum.
+__global__ void __launch_bounds__(256) ingest_ir(const double* vals, const int64_t* off, int bins, float* out) {
+    extern __shared__ int ir_edges[];          // [bins + 1]
+    __shared__ double red[256];
+    const int b = blockIdx.x;
+    const double* x = vals + off[b];
+    const int64_t len = off[b + 1] - off[b];
+    double mx = -INFINITY;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) mx = fmax(mx, x[i]);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    mx = red[0];
+    if (threadIdx.x == 0) {
+        const double span = (double)len / (double)bins;
+        double start = 0.0;
+        for (int i = 0; i < bins; ++i) { ir_edges[i] = (int)rint(start); start = start + span; }
+        ir_edges[bins] = (int)rint(start);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+        // slice [round(start_i), round(end_i)) with end_i = start_i + span = start_{i+1} (same double)
+        const int64_t lo = min((int64_t)ir_edges[i], len), hi = min((int64_t)ir_edges[i + 1], len);
+        double sum = 0.0;
+        for (int64_t k = lo; k < hi; ++k) sum += x[k];
+        out[(int64_t)b * bins + i] = (float)((sum / (double)(hi - lo)) / mx);      // empty slice -> NaN like np.mean([])
+    }
+}
+
 __global__ void pack_tokens_u8(const int64_t* in, int64_t n, uint8_t* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint8_t)in[i];
