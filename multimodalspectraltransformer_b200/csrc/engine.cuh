@@ -120,6 +120,9 @@ struct mmt_engine {
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     bool ffn_tiles2 = false;           // fused FFN: two row tiles per CTA on large M (MMT_FFN_TWO_TILES=1 enables; measured neutral: the chunk
                                        // loop is bound by shared-memory operand reads, not by the L2 weight stream)
+    bool use_enc_streams = true;       // ragged encoder: the five modality stacks as concurrent chains (MMT_NO_ENC_STREAMS=1 disables)
+    cudaStream_t enc_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t enc_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool use_pdl = true;               // programmatic dependent launch between the kernels of a fused decode step (MMT_NO_PDL=1 disables)
     cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only streams, one per decode lane (the caller's stream may be the legacy default stream)
     cudaEvent_t lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};       // fork / join events of the lane branches
