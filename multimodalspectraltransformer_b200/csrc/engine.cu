@@ -134,10 +134,8 @@ static int tc_init(mmt_engine* e) {
     const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES_WSPLIT + 1024;
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    MMT_CUDA((cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes(1))));
-    MMT_CUDA((cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes(1))));
-    MMT_CUDA((cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes(2))));
-    MMT_CUDA((cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes(2))));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
     e->tc_ready = true;
     return 0;
 }
@@ -216,18 +214,10 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
         MMT_TRY(make_tmap(&p.tmW1lo, W1lo, p.F, D, D, FF_CH));
         MMT_TRY(make_tmap(&p.tmW2lo, W2lo, D, p.F, p.F));
     }
-    // two row tiles per CTA when there are enough tiles to fill the GPU anyway: halves the L2 -> SM weight stream
-    const int tiles = (p.M + TC_BM - 1) / TC_BM;
-    const int T = (e->ffn_tiles2 && (int64_t)tiles * p.splits >= 2 * e->sm_count) ? 2 : 1;
-    dim3 grid(p.splits, (tiles + T - 1) / T);
+    dim3 grid(p.splits, (p.M + TC_BM - 1) / TC_BM);
     prof_pre(e, s);
-    if (T == 2) {
-        if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 2>, grid, dim3(FF_THREADS), ff_smem_bytes(2), s, pdl, p);
-        else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 2>, grid, dim3(FF_THREADS), ff_smem_bytes(2), s, pdl, p);
-    } else {
-        if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 1>, grid, dim3(FF_THREADS), ff_smem_bytes(1), s, pdl, p);
-        else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 1>, grid, dim3(FF_THREADS), ff_smem_bytes(1), s, pdl, p);
-    }
+    if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN>, grid, dim3(FF_THREADS), FF_SMEM_BYTES, s, pdl, p);
+    else launch_kernel(ffn_fused_tc<TC_EPI_STORE>, grid, dim3(FF_THREADS), FF_SMEM_BYTES, s, pdl, p);
     return check_launch(e, "ffn_fused_tc", s, 4.0 * p.M * D * p.F);
 }
 
@@ -1297,7 +1287,6 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
     if (getenv("MMT_NO_PDL")) e->use_pdl = false;
     if (getenv("MMT_NO_ENC_STREAMS")) e->use_enc_streams = false;
-    if (getenv("MMT_FFN_TWO_TILES")) e->ffn_tiles2 = true;
     if (const char* v = getenv("MMT_DECODE_LANES")) e->decode_lanes = std::max(1, atoi(v));
     if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);

@@ -118,8 +118,6 @@ struct mmt_engine {
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
-    bool ffn_tiles2 = false;           // fused FFN: two row tiles per CTA on large M (MMT_FFN_TWO_TILES=1 enables; measured neutral: the chunk
-                                       // loop is bound by shared-memory operand reads, not by the L2 weight stream)
     bool use_enc_streams = true;       // ragged encoder: the five modality stacks as concurrent chains (MMT_NO_ENC_STREAMS=1 disables)
     cudaStream_t enc_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t enc_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

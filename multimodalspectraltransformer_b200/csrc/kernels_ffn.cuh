@@ -5,28 +5,28 @@
 // The F-wide hidden activation never leaves the SM.  A CTA owns 128 rows of X (resident in shared
 // memory) and walks its share of F in chunks of 64 columns:
 //
-//   GEMM1   acc1[c&1] (TMEM, 64 cols)  = X . W1[c]^T              tcgen05.mma 128x64x16, K = 128
-//   convert H[c&1] (smem, bf16, 128B-swizzled K-major) = relu(acc1 + b1[c])     4 epilogue warps
-//   GEMM2   acc2 (TMEM, 128 cols)     += H[c&1] . W2[:, c]^T      tcgen05.mma 128x128x16, K = 64
+//   GEMM1   acc1[c&1] (TMEM)  = X . [W1_hi[c] ; W1_lo[c]]^T         tcgen05.mma 128x128x16, K = 128
+//   convert H[c&1] (smem, bf16, 128B-swizzled K-major) = relu(acc1_hi + acc1_lo + b1[c])    8 epilogue warps
+//   GEMM2   acc2 (TMEM)      += H[c&1] . [W2_hi[:, c] ; W2_lo[:, c]]^T   tcgen05.mma 128x256x16, K = 64
 //
-// software-pipelined so that GEMM1 of chunk c+1 runs on the tensor core while the epilogue warps
-// convert chunk c (acc1 and H are double-buffered).  W1 and W2 chunks travel through two independent
-// two-stage TMA rings fed by two producer lanes: a W1 slot is free as soon as GEMM1 of its chunk retires,
-// so the next chunks' weights are always in flight while the tensor core works (one shared ring would hold
-// every slot until GEMM2 and expose the TMA latency once per chunk).
-// Weights are the two-term bf16 split W_hi + W_lo (kernels_tc.cuh): every MMA pass runs twice.
+// Weights are the two-term bf16 split W_hi + W_lo (kernels_tc.cuh).  The two terms are stacked along the MMA's
+// N dimension (hi rows, then lo rows, of one shared-memory tile) instead of being issued as two MMA passes: the
+// chunk loop is bound by shared-memory operand reads (measured 2.1 K cycles per chunk vs 1.0 K of tensor time;
+// halving the L2 weight stream with two row tiles per CTA changed nothing), and stacking reads every A slice
+// (X, H) once instead of twice.  The hi and lo halves of the accumulators are summed by the epilogue warps.
 //
-// A CTA may own T = 2 row tiles (256 rows) and run every weight chunk against both: each 128-row tile otherwise
-// re-streams all 2 MB of W1/W2 (hi + lo) from L2, which -- not the tensor core -- paces the kernel on large M
-// (measured 2.1 K cycles per chunk vs 1.0 K of MMA time).  acc2 then holds one 128-column accumulator per tile.
+// Software pipeline: GEMM1 of chunk c+1 runs on the tensor core while the epilogue warps convert chunk c
+// (acc1 and H are double-buffered).  W1 and W2 chunks travel through two independent two-stage TMA rings fed by
+// two producer lanes: a W1 slot is free as soon as GEMM1 of its chunk retires, so the next chunks' weights are
+// always in flight while the tensor core works.
 //
-// grid = (splits, ceil(M / (128 T))).  splits == 1: the epilogue is bias + residual + LayerNorm over the
+// grid = (splits, ceil(M/128)).  splits == 1: the epilogue is bias + residual + LayerNorm over the
 // 128-wide row (encoder layers, large decode batches).  splits > 1 (small decode batches: more CTAs
 // than M/128): each CTA handles F/64/splits chunks and writes a raw fp32 partial; the consumer
-// (decode_attn_self / sample_tokens prologue, or bias_res_layernorm) reduces them in a fixed order.
+// (decode_attn / sample_tokens prologue, or bias_res_layernorm) reduces them in a fixed order.
 //
-// warp 0: TMA producers (two lanes) | warp 1: MMA issuer (one lane) + TMEM alloc (256 / 512 cols) | warps 2-9: epilogue
-// (two epilogue warps per TMEM lane quarter: the acc1 -> H conversion paces the chunk loop otherwise)
+// warp 0: TMA producers (two lanes) | warp 1: MMA issuer (one lane) + TMEM alloc (512 cols) | warps 2-9: epilogue
+// (two epilogue warps per TMEM lane quarter: with one warp per scheduler the conversion is a latency chain)
 #pragma once
 #include "kernels_tc.cuh"
 
@@ -34,22 +34,22 @@ namespace mmt {
 
 constexpr int FF_CH = 64;                                  // hidden columns per chunk
 constexpr int FF_THREADS = TC_THREADS;                     // 2 + 8 epilogue warps
-constexpr int FF_X_BYTES = 2 * TC_SLAB_BYTES;              // X of one row tile: two K slabs of [128 rows x 64]
+constexpr int FF_X_BYTES = 2 * TC_SLAB_BYTES;              // X: two K slabs of [128 rows x 64]
 constexpr int FF_H_BYTES = TC_SLAB_BYTES;                  // one H buffer: [128 rows x 64] bf16
-constexpr int FF_W1_SLAB = FF_CH * TC_BK * 2;              // 8 KB: [64 rows x 64 K]
-constexpr int FF_W1_STAGE = 4 * FF_W1_SLAB;                // W1 chunk: hi (2 K slabs) + lo (2 K slabs) = 32 KB
-constexpr int FF_W2_STAGE = 2 * TC_SLAB_BYTES;             // W2 chunk: hi + lo slabs of [128 rows x 64 K] = 32 KB
+constexpr int FF_W1_HALF = FF_CH * 128;                    // 8 KB: 64 rows x 128 B (one term of one K slab)
+constexpr int FF_W1_STAGE = 2 * TC_SLAB_BYTES;             // W1 chunk: 2 K slabs of [64 hi rows ; 64 lo rows] x 64 k = 32 KB
+constexpr int FF_W2_STAGE = 2 * TC_SLAB_BYTES;             // W2 chunk: [128 hi rows ; 128 lo rows] x 64 k = 32 KB
 constexpr int FF_MAX_F = 2048;
-// dynamic smem of a T-tile CTA: X (T x 32 KB) | H (2 x 16 KB) | W1 ring (2 x 32 KB) | W2 ring (2 x 32 KB) + alignment slack
-__host__ __device__ constexpr int ff_smem_bytes(int T) { return T * FF_X_BYTES + 2 * FF_H_BYTES + 2 * FF_W1_STAGE + 2 * FF_W2_STAGE + 1024; }
+// dynamic smem: X (32 KB) | H (2 x 16 KB) | W1 ring (2 x 32 KB) | W2 ring (2 x 32 KB) + alignment slack
+constexpr int FF_SMEM_BYTES = FF_X_BYTES + 2 * FF_H_BYTES + 2 * FF_W1_STAGE + 2 * FF_W2_STAGE + 1024;
 static_assert(2 * FF_W1_STAGE + 2 * FF_W2_STAGE >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
-static_assert(ff_smem_bytes(2) <= 232448, "two row tiles must fit the 227 KB shared memory of an SM");
+constexpr uint32_t FF_TMEM_COLS = 512;                     // acc1: 2 x (64 hi + 64 lo) | acc2: 128 hi + 128 lo
 
 struct FfnParams {
     CUtensorMap tmX;                 // X  [M,128] bf16, box {64,128}
     CUtensorMap tmW1, tmW1lo;        // W1 [F,128] bf16, box {64,64}
     CUtensorMap tmW2, tmW2lo;        // W2 [128,F] bf16, box {64,128}
-    int wsplit;
+    int wsplit;                      // 0: single-term weights (the lo halves are skipped)
     int M, N, F;                     // N == 128
     int splits;
     const float* b1;                 // [F]
@@ -68,24 +68,39 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int EPI, int T>
+// TMEM -> staging tile for an accumulator stored as two 128-column halves (hi | lo): the halves are summed on the way
+__device__ __forceinline__ void epi_tmem2_to_stage(uint32_t tmem_acc, int q, int hf, int lane, float* stage_q) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int c = hf * 2 + cc;
+        uint32_t a[32], b[32];
+        tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), a);
+        tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(TC_BN + c * 32), b);
+        tmem_ld_wait();
+        float* dst = stage_q + lane * TC_LDS + c * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + 4 * j) =
+                make_float4(__uint_as_float(a[4 * j]) + __uint_as_float(b[4 * j]), __uint_as_float(a[4 * j + 1]) + __uint_as_float(b[4 * j + 1]),
+                            __uint_as_float(a[4 * j + 2]) + __uint_as_float(b[4 * j + 2]), __uint_as_float(a[4 * j + 3]) + __uint_as_float(b[4 * j + 3]));
+    }
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
-    static_assert(T == 1 || T == 2, "one or two row tiles per CTA");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t x_full, w1_full[2], w1_empty[2], w2_full[2], w2_empty[2], acc1_full[2], h_full[2], h_empty[2], acc2_full;
     __shared__ uint32_t tmem_slot;
-    constexpr uint32_t TMEM_COLS = T == 1 ? 256 : 512;     // acc1 2 x 64 | acc2 T x 128 (power of two)
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space
     uint8_t* sX = smem;
-    uint8_t* sH = sX + T * FF_X_BYTES;
+    uint8_t* sH = sX + FF_X_BYTES;
     uint8_t* sW = sH + 2 * FF_H_BYTES;   // W1 ring; the two rings together also hold the final staging tile
     uint8_t* sW2 = sW + 2 * FF_W1_STAGE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x, m0 = blockIdx.y * (T * TC_BM);
+    const int split = blockIdx.x, m0 = blockIdx.y * TC_BM;
     const int n = (p.F / FF_CH) / p.splits;      // chunks of this CTA (host guarantees divisibility, n >= 1)
     const int c0 = split * n;
-    const int nv = n * T;                        // virtual chunks v = chunk * T + tile
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
 #define FF_STAMP(i) do { if (p.dbg) p.dbg[cta * 16 + (i)] = clock64(); } while (0)
     if (threadIdx.x == 64) FF_STAMP(0);
@@ -102,34 +117,33 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
+    if (warp == 1) tmem_alloc(&tmem_slot, FF_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tmem_acc2 = tmem_base + 128;
+    const uint32_t tmem_acc2 = tmem_base + 256;          // acc1[b] at columns [128 b, 128 b + 128): hi 64 | lo 64
+    // N of the MMAs: both terms stacked, or the hi half alone
+    const int n1 = p.wsplit ? 2 * FF_CH : FF_CH, n2 = p.wsplit ? 2 * TC_BN : TC_BN;
     if (threadIdx.x == 64) FF_STAMP(1);
 
     if (warp == 0) {
         auto load_x = [&]() {
-            mbar_arrive_expect_tx(&x_full, T * FF_X_BYTES);
-#pragma unroll
-            for (int tl = 0; tl < T; ++tl) {
-                tma_load_2d(sX + tl * FF_X_BYTES, &p.tmX, &x_full, 0, m0 + tl * TC_BM);
-                tma_load_2d(sX + tl * FF_X_BYTES + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0 + tl * TC_BM);
-            }
+            mbar_arrive_expect_tx(&x_full, FF_X_BYTES);
+            tma_load_2d(sX, &p.tmX, &x_full, 0, m0);
+            tma_load_2d(sX + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0);
         };
         if (lane == 0) {                  // W1 ring (decode-loop constants only: runs ahead of the PDL wait)
             for (int i = 0; i < n; ++i) {
                 const int s = i & 1, c = c0 + i;
                 mbar_wait(&w1_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&w1_full[s], p.wsplit ? FF_W1_STAGE : FF_W1_STAGE / 2);
-                uint8_t* w = sW + (size_t)s * FF_W1_STAGE;
+                uint8_t* w = sW + (size_t)s * FF_W1_STAGE;          // K slab ks: rows 0-63 hi, rows 64-127 lo
                 tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
-                tma_load_2d(w + FF_W1_SLAB, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
+                tma_load_2d(w + TC_SLAB_BYTES, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
                 if (p.wsplit) {
-                    tma_load_2d(w + 2 * FF_W1_SLAB, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
-                    tma_load_2d(w + 3 * FF_W1_SLAB, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
+                    tma_load_2d(w + FF_W1_HALF, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
+                    tma_load_2d(w + TC_SLAB_BYTES + FF_W1_HALF, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
                 }
             }
         } else if (lane == 1) {           // W2 ring, and X once the producer of X has finished (PDL)
@@ -138,7 +152,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                 if (i == min(n, 2)) { pdl_wait(); load_x(); }
                 mbar_wait(&w2_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&w2_full[s], p.wsplit ? FF_W2_STAGE : FF_W2_STAGE / 2);
-                uint8_t* w = sW2 + (size_t)s * FF_W2_STAGE;
+                uint8_t* w = sW2 + (size_t)s * FF_W2_STAGE;         // rows 0-127 hi, rows 128-255 lo
                 tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
                 if (p.wsplit) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
             }
@@ -146,57 +160,41 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc1 = umma_idesc_bf16(TC_BM, FF_CH);
-            constexpr uint32_t idesc2 = umma_idesc_bf16(TC_BM, TC_BN);
-            // acc2[tile] += H[u&1] . W2[:, chunk]^T       (u = virtual chunk)
-            auto gemm2 = [&](int u) {
-                const int c = u / T, tile = u - c * T, s = c & 1, b = u & 1;
-                if (tile == 0) mbar_wait(&w2_full[s], ((uint32_t)c >> 1) & 1u);
-                mbar_wait(&h_full[b], ((uint32_t)u >> 1) & 1u);
+            const uint32_t idesc1 = umma_idesc_bf16(TC_BM, n1);
+            const uint32_t idesc2 = umma_idesc_bf16(TC_BM, n2);
+            const uint32_t x_addr = smem_u32(sX);
+            // acc2 += H[j&1] . [W2_hi ; W2_lo][:, chunk j]^T
+            auto gemm2 = [&](int j) {
+                const int b = j & 1;
+                mbar_wait(&w2_full[b], ((uint32_t)j >> 1) & 1u);
+                mbar_wait(&h_full[b], ((uint32_t)j >> 1) & 1u);
                 tc_fence_after();
                 const uint64_t adesc = umma_desc_sw128(smem_u32(sH + (size_t)b * FF_H_BYTES));
-                const uint32_t w2 = smem_u32(sW2 + (size_t)s * FF_W2_STAGE);
-                const uint64_t bdesc = umma_desc_sw128(w2);
-                const uint32_t acc2 = tmem_acc2 + (uint32_t)(tile * TC_BN);
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sW2 + (size_t)b * FF_W2_STAGE));
 #pragma unroll
                 for (int k = 0; k < FF_CH / 16; ++k)
-                    umma_bf16(acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (c > 0 || k > 0) ? 1u : 0u);
-                if (p.wsplit) {
-                    const uint64_t bdesc2 = umma_desc_sw128(w2 + TC_SLAB_BYTES);
-#pragma unroll
-                    for (int k = 0; k < FF_CH / 16; ++k)
-                        umma_bf16(acc2, adesc + (uint64_t)(2 * k), bdesc2 + (uint64_t)(2 * k), idesc2, 1u);
-                }
-                if (tile == T - 1) umma_commit(&w2_empty[s]);     // W2 stage reusable after the last tile used it
-                umma_commit(&h_empty[b]);                          // H buffer b reusable
+                    umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&w2_empty[b]);     // W2 stage b reusable
+                umma_commit(&h_empty[b]);      // H buffer b reusable
             };
             mbar_wait(&x_full, 0);
-            for (int v = 0; v < nv; ++v) {
-                const int c = v / T, tile = v - c * T, s = c & 1, b = v & 1;
-                if (tile == 0) mbar_wait(&w1_full[s], ((uint32_t)c >> 1) & 1u);
+            for (int i = 0; i < n; ++i) {
+                const int s = i & 1;
+                mbar_wait(&w1_full[s], ((uint32_t)i >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t x_addr = smem_u32(sX + tile * FF_X_BYTES);
                 const uint32_t w1 = smem_u32(sW + (size_t)s * FF_W1_STAGE);
-                const uint32_t acc1 = tmem_base + (uint32_t)(b * FF_CH);
+                const uint32_t acc1 = tmem_base + (uint32_t)(s * 2 * FF_CH);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
                     const uint64_t adesc = umma_desc_sw128(x_addr + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
-                    const uint64_t bdesc = umma_desc_sw128(w1 + (k >> 2) * FF_W1_SLAB) + (uint64_t)(2 * (k & 3));
+                    const uint64_t bdesc = umma_desc_sw128(w1 + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
                     umma_bf16(acc1, adesc, bdesc, idesc1, k > 0 ? 1u : 0u);
                 }
-                if (p.wsplit) {
-#pragma unroll
-                    for (int k = 0; k < D / 16; ++k) {
-                        const uint64_t adesc = umma_desc_sw128(x_addr + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
-                        const uint64_t bdesc = umma_desc_sw128(w1 + (2 + (k >> 2)) * FF_W1_SLAB) + (uint64_t)(2 * (k & 3));
-                        umma_bf16(acc1, adesc, bdesc, idesc1, 1u);
-                    }
-                }
-                umma_commit(&acc1_full[b]);
-                if (tile == T - 1) umma_commit(&w1_empty[s]);     // W1 stage reusable as soon as the last tile's GEMM1 retires
-                if (v > 0) gemm2(v - 1);
+                umma_commit(&acc1_full[s]);
+                umma_commit(&w1_empty[s]);     // W1 stage s reusable as soon as this GEMM1 retires
+                if (i > 0) gemm2(i - 1);
             }
-            gemm2(nv - 1);
+            gemm2(n - 1);
             umma_commit(&acc2_full);
         }
     } else {
@@ -204,31 +202,34 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         // the two warps of a quarter split the chunk's 64 columns
         const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
-        for (int v = 0; v < nv; ++v) {
-            const int b = v & 1, c = v / T;
+        for (int i = 0; i < n; ++i) {
+            const int b = i & 1;
             // bias slice of this chunk (a decode-loop constant): in registers before the accumulator is ready
             float4 bb[8];
-            const float4* bsrc = reinterpret_cast<const float4*>(p.b1 + (size_t)(c0 + c) * FF_CH + hf * 32);
+            const float4* bsrc = reinterpret_cast<const float4*>(p.b1 + (size_t)(c0 + i) * FF_CH + hf * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) bb[j] = __ldg(bsrc + j);
-            mbar_wait(&acc1_full[b], ((uint32_t)v >> 1) & 1u);
+            mbar_wait(&acc1_full[b], ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
-            if (threadIdx.x == 64 && v == 0) FF_STAMP(2);
+            if (threadIdx.x == 64 && i == 0) FF_STAMP(2);
             uint32_t pk[16];
             {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * FF_CH + hf * 32), r);
+                uint32_t r[32], rl[32];
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 2 * FF_CH + hf * 32);
+                tmem_ld_32x32(t0, r);
+                if (p.wsplit) tmem_ld_32x32(t0 + FF_CH, rl);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float v0 = fmaxf(__uint_as_float(r[4 * j]) + bb[j].x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * j + 1]) + bb[j].y, 0.f);
-                    const float v2 = fmaxf(__uint_as_float(r[4 * j + 2]) + bb[j].z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * j + 3]) + bb[j].w, 0.f);
+                    float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]), v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
+                    if (p.wsplit) { v0 += __uint_as_float(rl[4 * j]); v1 += __uint_as_float(rl[4 * j + 1]); v2 += __uint_as_float(rl[4 * j + 2]); v3 += __uint_as_float(rl[4 * j + 3]); }
+                    v0 = fmaxf(v0 + bb[j].x, 0.f); v1 = fmaxf(v1 + bb[j].y, 0.f); v2 = fmaxf(v2 + bb[j].z, 0.f); v3 = fmaxf(v3 + bb[j].w, 0.f);
                     __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
                     pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
                     pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
                 }
             }
-            mbar_wait(&h_empty[b], (((uint32_t)v >> 1) & 1u) ^ 1u);
+            mbar_wait(&h_empty[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
             uint8_t* hrow = sH + (size_t)b * FF_H_BYTES + (size_t)row * 128;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {    // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
@@ -238,25 +239,21 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             tc_fence_before();
             mbar_arrive(&h_full[b]);
-            if (threadIdx.x == 64 && v == 0) FF_STAMP(3);
-            if (threadIdx.x == 64 && v >= 8 && v < 16) FF_STAMP(v);     // steady-state chunk cadence
+            if (threadIdx.x == 64 && i == 0) FF_STAMP(3);
+            if (threadIdx.x == 64 && i >= 8 && i < 16) FF_STAMP(i);     // steady-state chunk cadence
         }
         float* stage_q = reinterpret_cast<float*>(sW) + (q * 32) * TC_LDS;
         pdl_wait();                            // (already satisfied: acc2 depends on X) orders the stores below explicitly
         mbar_wait(&acc2_full, 0);
         tc_fence_after();
         if (threadIdx.x == 64) FF_STAMP(4);
-#pragma unroll
-        for (int tile = 0; tile < T; ++tile) {
-            if (tile > 0) epi_bar_sync();      // the staging tile is reused: everyone is done reading the previous one
-            epi_tmem_to_stage<TC_BN>(tmem_acc2 + (uint32_t)(tile * TC_BN), q, hf, lane, stage_q);
-            epi_bar_sync();
-            if (threadIdx.x == 64 && tile == 0) FF_STAMP(5);
-            const float* st = stage_q + (hf * 16) * TC_LDS;
-            const int r0 = m0 + tile * TC_BM + q * 32 + hf * 16;
-            if (EPI == TC_EPI_LN) epi_rows_ln(p, st, r0, 16, lane);
-            else epi_rows_store(p, st, r0, 16, 0, split, lane);
-        }
+        if (p.wsplit) epi_tmem2_to_stage(tmem_acc2, q, hf, lane, stage_q);
+        else epi_tmem_to_stage<TC_BN>(tmem_acc2, q, hf, lane, stage_q);
+        epi_bar_sync();
+        if (threadIdx.x == 64) FF_STAMP(5);
+        const float* st = stage_q + (hf * 16) * TC_LDS;
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane);
+        else epi_rows_store(p, st, m0 + q * 32 + hf * 16, 16, 0, split, lane);
         if (threadIdx.x == 64) FF_STAMP(6);
     }
     tc_fence_before();
@@ -265,7 +262,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
 #undef FF_STAMP
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, FF_TMEM_COLS);
     }
 }
 

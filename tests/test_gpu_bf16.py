@@ -139,27 +139,3 @@ def test_ffn_fused_tcgen05(M, F, splits):
     # accumulation order: a handful of elements may round the other way (1 bf16 ulp of h ~ 4e-3 * |h|)
     torch.testing.assert_close(out.double(), ref, atol=3e-3, rtol=1e-3)
     assert float((out.double() - ref).abs().mean()) < 2e-4
-
-
-def test_ffn_two_row_tiles_per_cta():
-    """The T = 2 variant of the fused FFN (two 128-row tiles share every weight chunk) on an odd tile count."""
-    import os
-    s = setup()
-    from multimodalspectraltransformer_b200.engine import Engine
-    os.environ["MMT_FFN_TWO_TILES"] = "1"
-    try:
-        eng = Engine(s["model"].state_dict(), s["cfg"], "cuda")
-    finally:
-        del os.environ["MMT_FFN_TWO_TILES"]
-    g = torch.Generator().manual_seed(17)
-    M, F = 38017, 2048
-    x = torch.randn(M, 128, generator=g).cuda()
-    w1 = (torch.randn(F, 128, generator=g) / 128 ** 0.5).cuda()
-    b1 = (0.1 * torch.randn(F, generator=g)).cuda()
-    w2 = (torch.randn(128, F, generator=g) / F ** 0.5).cuda()
-    b2 = (0.1 * torch.randn(128, generator=g)).cuda()
-    gamma = (1 + 0.1 * torch.randn(128, generator=g)).cuda()
-    beta = (0.1 * torch.randn(128, generator=g)).cuda()
-    out2 = eng.ffn(x, w1, b1, w2, b2, gamma, beta, splits=1)
-    out1 = s["eng"].ffn(x, w1, b1, w2, b2, gamma, beta, splits=1)
-    torch.testing.assert_close(out2, out1, atol=2e-5, rtol=0)      # same MMAs in the same order per row
