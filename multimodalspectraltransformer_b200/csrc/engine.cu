@@ -803,6 +803,7 @@ struct DecBuffers {
     size_t kv_esz;                     // 4 (fp32 check mode) | 2 (bf16 tensor-core mode)
     int *nk, *row_start; int64_t* row_off; float* kbias_c;
     int* ctl;   // [0] step, [1] done_ctas, [8..8+max_len) nonpad counts
+    uint64_t* rng_state;   // {philox seed, offset of step 0} of this call (read by the sampler from device memory)
     // bf16 operand copies (tensor-core mode)
     __nv_bfloat16 *x16, *att16, *h16, *mem16;
 };
@@ -827,6 +828,7 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     b.row_off = a.get<int64_t>(R);
     b.kbias_c = a.get<float>(R);
     b.ctl = a.get<int>(8 + 256);
+    b.rng_state = a.get<uint64_t>(2);
     b.x16 = b.att16 = b.h16 = b.mem16 = nullptr;
     if (bf16) {
         b.x16 = a.get<__nv_bfloat16>(Nw * D);
@@ -1047,6 +1049,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     sp.rng.seed = a.philox_seed; sp.rng.offset = a.philox_offset; sp.rng.numel = Nrng * d.vocab;
     sp.rng.threads = torch_rng_threads(sp.rng.numel, smc, mts);
     sp.rng_inc = torch_rng_increment(sp.rng.numel, smc, mts);
+    sp.rng_dev = b.rng_state;
     sp.seq_index_base = a.seq_index_base + n0;
     sp.tokens = r.tokens ? r.tokens + n0 : nullptr; sp.probs = r.probs ? r.probs + n0 : nullptr;
     sp.logits = r.logits ? r.logits + n0 * d.vocab : nullptr;
@@ -1092,13 +1095,24 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         }
     }
     const int Bm_lane = (Bm_wave + NL - 1) / NL;
+    // Single-wave sampling runs write ids / probabilities into engine-owned staging buffers (copied to the caller's
+    // tensors at the end): nothing a captured decode-step graph touches then depends on the caller's allocations, so the
+    // instantiated graph is reused across calls (capture + instantiation of ~400 nodes costs ~1.2 ms with the GPU idle).
+    const bool staged = e->use_graph && e->use_graph_cache && !e->profiling && n_waves == 1 && r.mode != 2;
     Arena ar;
     DecBuffers lb[MAX_LANES];
+    int64_t* st_tokens = nullptr; float* st_probs = nullptr;
+    auto plan_all = [&]() {
+        for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16);
+        if (staged) { st_tokens = ar.get<int64_t>((size_t)a.max_len * N_total); st_probs = ar.get<float>((size_t)a.max_len * N_total); }
+    };
     ar.plan = true;
-    for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16);
+    plan_all();
     MMT_TRY(ensure_arena(e, ar.off));
     ar.plan = false; ar.base = e->arena; ar.cap = e->arena_bytes; ar.off = 0;
-    for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16);
+    plan_all();
+    DecodeRun rs = r;                        // the run as the kernels see it
+    if (staged) { rs.tokens = st_tokens; rs.probs = r.probs ? st_probs : nullptr; }
     const int pps = (a.max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
     const bool early = (r.mode == 0) && a.stop_on_all_pad && n_waves == 1;
     int steps_done = r.T;
@@ -1115,6 +1129,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         for (int i = 0; i < nl; ++i) {
             DecBuffers& b = lb[i];
             MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
+            set_u64x2<<<1, 1, 0, s>>>(b.rng_state, a.philox_seed, a.philox_offset);
             prof_pre(e, s);
             init_block_table<<<(unsigned)((lane[i].Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, lane[i].Nw * pps);
             MMT_TRY(check_launch(e, "init_block_table", s));
@@ -1124,10 +1139,21 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         // the device), so a group of U consecutive steps of every lane is captured once per wave into a CUDA
         // graph (programmatic-dependent-launch edges included) and replayed T / U times.
         int U = 1;
-        for (int u = 2; u <= 16; ++u) if (r.T % u == 0) U = u;
+        for (int u = 2; u <= e->graph_steps; ++u) if (r.T % u == 0) U = u;
         cudaGraphExec_t exec = nullptr;
         int64_t launches_per_group = 0;
-        if (e->use_graph && !e->profiling) {
+        std::vector<uint64_t> key;            // every value baked into the graph's nodes
+        if (staged) {
+            auto put = [&](uint64_t v) { key.push_back(v); };
+            uint32_t tbits; memcpy(&tbits, &a.temperature, 4);
+            put((uint64_t)r.mode); put((uint64_t)r.T); put((uint64_t)(r.probs != nullptr)); put((uint64_t)a.S); put((uint64_t)a.Bm);
+            put((uint64_t)a.n_cand); put((uint64_t)a.max_len); put(tbits); put((uint64_t)a.precision);
+            put((uint64_t)a.seq_index_base); put((uint64_t)a.N_total); put((uint64_t)a.rng_sm_count); put((uint64_t)a.rng_max_threads_per_sm);
+            put((uint64_t)(uintptr_t)e->arena); put((uint64_t)e->arena_bytes); put((uint64_t)nl); put((uint64_t)U);
+            put((uint64_t)e->fused_decode_rows); put((uint64_t)e->use_pdl); put((uint64_t)(uintptr_t)e->da_dbg);
+            for (auto& c : e->graph_cache) if (c.key == key) { exec = c.exec; launches_per_group = c.launches_per_group; c.stamp = ++e->graph_cache_clock; break; }
+        }
+        if (e->use_graph && !e->profiling && !exec) {
             if (bf16) MMT_TRY(tc_init(e));
             for (int i = 0; i < nl; ++i) {
                 if (!e->cap_stream[i]) MMT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream[i], cudaStreamNonBlocking));
@@ -1142,7 +1168,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
                 for (int i = 1; i < nl && fe == cudaSuccess; ++i) fe = cudaStreamWaitEvent(e->cap_stream[i], e->lane_ev[0], 0);
             }
             for (int u = 0; u < U && !rc && fe == cudaSuccess; ++u)
-                for (int i = 0; i < nl && !rc; ++i) rc = decode_step(e, r, lane[i].n0, lane[i].Nw, lane[i].Bm, lb[i], bf16, e->cap_stream[i]);
+                for (int i = 0; i < nl && !rc; ++i) rc = decode_step(e, rs, lane[i].n0, lane[i].Nw, lane[i].Bm, lb[i], bf16, e->cap_stream[i]);
             for (int i = 1; i < nl && fe == cudaSuccess; ++i) {   // join
                 fe = cudaEventRecord(e->lane_ev[i], e->cap_stream[i]);
                 if (fe == cudaSuccess) fe = cudaStreamWaitEvent(e->cap_stream[0], e->lane_ev[i], 0);
@@ -1157,15 +1183,23 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
             ce = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) MMT_FAIL(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
-        } else {
+            if (staged) {
+                if (e->graph_cache.size() >= 4) {      // evict the least recently used entry
+                    size_t lru = 0;
+                    for (size_t i = 1; i < e->graph_cache.size(); ++i) if (e->graph_cache[i].stamp < e->graph_cache[lru].stamp) lru = i;
+                    cudaGraphExecDestroy(e->graph_cache[lru].exec);
+                    e->graph_cache.erase(e->graph_cache.begin() + lru);
+                }
+                e->graph_cache.push_back({key, exec, launches_per_group, ++e->graph_cache_clock});
+            }
+        } else if (!exec) {
             U = 1;
         }
-        // (caching the instantiated graph across calls was measured slower than re-capturing: 165-177 vs 149-156 us/position)
-        struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { if (x) cudaGraphExecDestroy(x); } } guard{exec};
+        struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { if (x) cudaGraphExecDestroy(x); } } guard{staged ? nullptr : exec};
         // greedy early exit (validate_generate_MMT_v15_4.py:763): the per-step non-PAD counts are polled one
         // group behind the launches, so the host never drains the stream inside the loop
         if (early) for (int i = 0; i < 2; ++i) if (!e->poll_ev[i]) MMT_CUDA(cudaEventCreateWithFlags(&e->poll_ev[i], cudaEventDisableTiming));
-        const int poll_every = (16 / U) * U > 0 ? std::max(U, (16 / U) * U) : U;    // steps between polls (multiple of U, ~16)
+        const int poll_every = U >= 16 ? U : (16 / U) * U;    // steps between polls (multiple of U, >= ~16)
         int n_polls = 0, checked_polls = 0;
         bool stop = false;
         auto check_poll = [&](int k) -> int {       // inspect poll k (covers steps < (k+1)*poll_every, capped at T)
@@ -1181,7 +1215,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         };
         for (int t = 0; t < r.T && !stop; t += U) {
             if (exec) { MMT_CUDA(cudaGraphLaunch(exec, s)); e->launches += launches_per_group; }
-            else for (int i = 0; i < nl; ++i) MMT_TRY(decode_step(e, r, lane[i].n0, lane[i].Nw, lane[i].Bm, lb[i], bf16, s));
+            else for (int i = 0; i < nl; ++i) MMT_TRY(decode_step(e, rs, lane[i].n0, lane[i].Nw, lane[i].Bm, lb[i], bf16, s));
             const int done = t + U;
             if (early && (done % poll_every == 0 || done == r.T)) {
                 if (n_polls - checked_polls >= 2) { MMT_TRY(check_poll(checked_polls)); ++checked_polls; }
@@ -1200,6 +1234,10 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
             MMT_CUDA(cudaStreamSynchronize(s));
             for (int i = 0; i < nl; ++i) for (int q = 0; q < r.T; ++q) nonpad_total[q] += e->h_pinned[i * 128 + q];
         }
+    }
+    if (staged) {
+        MMT_CUDA(cudaMemcpyAsync(r.tokens, st_tokens, (size_t)r.T * N_total * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+        if (r.probs) MMT_CUDA(cudaMemcpyAsync(r.probs, st_probs, (size_t)r.T * N_total * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1)
         for (int q = 0; q < r.T; ++q) if (nonpad_total[q] == 0) { steps_done = q + 1; break; }
@@ -1286,6 +1324,8 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     e->reg = build_registry(*desc);
     if (getenv("MMT_NO_GRAPH")) e->use_graph = false;
     if (getenv("MMT_NO_PDL")) e->use_pdl = false;
+    if (getenv("MMT_NO_GRAPH_CACHE")) e->use_graph_cache = false;
+    if (const char* v = getenv("MMT_GRAPH_STEPS")) e->graph_steps = std::max(1, atoi(v));
     if (getenv("MMT_NO_ENC_STREAMS")) e->use_enc_streams = false;
     if (const char* v = getenv("MMT_DECODE_LANES")) e->decode_lanes = std::max(1, atoi(v));
     if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
@@ -1318,6 +1358,7 @@ void mmt_destroy(mmt_engine* e) {
     if (e->w16lo) cudaFree(e->w16lo);
     if (e->arena) cudaFree(e->arena);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    for (auto& c : e->graph_cache) cudaGraphExecDestroy(c.exec);
     for (int i = 0; i < 5; ++i) if (e->enc_stream[i]) cudaStreamDestroy(e->enc_stream[i]);
     for (int i = 0; i < 6; ++i) if (e->enc_ev[i]) cudaEventDestroy(e->enc_ev[i]);
     for (int i = 0; i < 4; ++i) { if (e->cap_stream[i]) cudaStreamDestroy(e->cap_stream[i]); if (e->lane_ev[i]) cudaEventDestroy(e->lane_ev[i]); }

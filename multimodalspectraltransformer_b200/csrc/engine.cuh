@@ -118,9 +118,14 @@ struct mmt_engine {
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
+    struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int64_t launches_per_group; uint64_t stamp; };
+    std::vector<GraphEntry> graph_cache;   // instantiated decode-step graphs of single-wave runs (staged outputs), keyed by what their nodes bake in
+    uint64_t graph_cache_clock = 0;
+    bool use_graph_cache = true;           // MMT_NO_GRAPH_CACHE=1: capture + instantiate on every call, write the caller's tensors directly
     bool use_enc_streams = true;       // ragged encoder: the five modality stacks as concurrent chains (MMT_NO_ENC_STREAMS=1 disables)
     cudaStream_t enc_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t enc_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int graph_steps = 16;              // decode positions captured per CUDA graph (MMT_GRAPH_STEPS overrides)
     bool use_pdl = true;               // programmatic dependent launch between the kernels of a fused decode step (MMT_NO_PDL=1 disables)
     cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only streams, one per decode lane (the caller's stream may be the legacy default stream)
     cudaEvent_t lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};       // fork / join events of the lane branches

@@ -687,6 +687,8 @@ struct SampleParams {
     int mode;                // 0 greedy, 1 multinomial, 2 forced (logits only)
     RngGeom rng;             // rng.offset is the offset of step 0; step t adds t*rng_inc
     uint64_t rng_inc;
+    const uint64_t* rng_dev; // optional {seed, offset} in device memory (overrides rng.seed / rng.offset: keeps a captured
+                             // decode graph reusable across calls with a different generator state)
     int64_t seq_index_base;
     int64_t* tokens;         // [max_len][N] or nullptr
     float* probs;            // [max_len][N] or nullptr
@@ -761,6 +763,7 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
             float r0 = p0, r1 = p1;
             if (p.mode == 1) {
                 RngGeom g = p.rng;
+                if (p.rng_dev) { g.seed = p.rng_dev[0]; g.offset = p.rng_dev[1]; }
                 g.offset += (uint64_t)t * p.rng_inc;
                 int64_t li = (p.seq_index_base + n) * p.V;
                 if (ok0) r0 = p0 / torch_exponential_at(g, li + v0);
@@ -860,6 +863,8 @@ __global__ void __launch_bounds__(256) ingest_ir(const double* vals, const int64
         out[(int64_t)b * bins + i] = (float)((sum / (double)(hi - lo)) / mx);      // empty slice -> NaN like np.mean([])
     }
 }
+
+__global__ void set_u64x2(uint64_t* dst, uint64_t a, uint64_t b) { dst[0] = a; dst[1] = b; }
 
 __global__ void pack_tokens_u8(const int64_t* in, int64_t n, uint8_t* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
