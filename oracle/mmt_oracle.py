@@ -307,6 +307,40 @@ def multinomial_sequence_multi(P, memory, mask, config, generator=None, max_len=
 # --------------------------------------------------------------------------
 # sampling RNG restatement -- numpy, bit-exact integers
 # --------------------------------------------------------------------------
+def beam_search(P, memory, mask, config, beam_size, gen_len, sos=3, eos=2):
+    """validate_generate_MMT_v15_4.py:995-1086 (beam_search_step + beam_search), per item, full-prefix decoder runs.
+    Returns beams[item] = [(score, sequence, prob_sequence), ...] sorted by score, like the reference.
+    NB the reference ranks with softmax(logits) WITHOUT the temperature (:1038) and multiplies Python floats (double)."""
+    N = memory.size(1)
+    beams = [[(1, [sos], [])] for _ in range(N)]
+    for _ in range(gen_len):
+        new_beams = []
+        for i in range(N):
+            mem_i, mask_i = memory[:, i:i + 1, :], mask[i:i + 1]
+            new_beam, seen = [], set()
+            for score, seq, pseq in beams[i]:
+                if tuple(seq) in seen:
+                    continue
+                seen.add(tuple(seq))
+                if seq[-1] == eos:
+                    new_beam.append((score, seq, pseq))
+                    continue
+                trg = torch.tensor(seq, dtype=torch.long).unsqueeze(1)
+                logits = teacher_forced_logits(P, mem_i, mask_i, trg, config)
+                probs = torch.softmax(logits[-1, :, :], dim=-1)
+                top_p, top_i = torch.topk(probs, beam_size, dim=-1)
+                for k in range(beam_size):
+                    ns = seq + [top_i[0, k].item()]
+                    if tuple(ns) in seen:
+                        continue
+                    seen.add(tuple(ns))
+                    new_beam.append((score * top_p[0, k].item(), ns, pseq + [top_p[0, k].item()]))
+            new_beam.sort(key=lambda x: x[0], reverse=True)
+            new_beams.append(new_beam[:beam_size])
+        beams = new_beams
+    return beams
+
+
 def philox4x32_10(counter, key):
     """Philox4x32-10 (Salmon et al., Random123) as used by curand's
     curandStatePhilox4_32_10: counter (..,4) uint32, key (..,2) uint32 -> (..,4)."""
