@@ -168,6 +168,21 @@ int32_t mmt_decode(mmt_engine* e, const mmt_decode_args* a, int64_t* d_tokens, f
 int32_t mmt_teacher_forced(mmt_engine* e, const mmt_decode_args* a, const int64_t* d_trg, int32_t T,
                            float* d_logits, void* stream);
 
+/* Replaces vgmmt.beam_search / beam_search_step (validate_generate_MMT_v15_4.py:995-1086), batched: the
+ * beam_size beams of each of the a->Bm memory columns are slots of one KV-cached decode wave (a->n_cand, max_len,
+ * temperature and sampling are ignored: the reference ranks with softmax(logits) without temperature, :1038).
+ * gen_len steps (config.gen_len) from the single [<SOS>] beam; beams ending in `eos` are carried unchanged;
+ * score = product of the chosen probabilities in double (Python floats); per step a stable sort by score.
+ * Slot n = column * beam_size + rank (rank 0 = best):
+ *   d_seq   out (N, gen_len+1) i64  sequence incl. <SOS>, zero-filled past d_len
+ *   d_len   out (N) i32             tokens in the sequence (<SOS> included)
+ *   d_score out (N) f64
+ *   d_probs out (N, gen_len) f32    probability of every chosen token, zero-filled past d_len-1
+ *   h_steps out host int or NULL: steps executed (fewer than gen_len once every beam has finished; the skipped
+ *           steps are fixed points of the reference's loop).  Synchronises `stream` every 16 steps. */
+int32_t mmt_beam_search(mmt_engine* e, const mmt_decode_args* a, int32_t beam_size, int32_t gen_len, int32_t eos,
+                        int64_t* d_seq, int32_t* d_len, double* d_score, float* d_probs, int32_t* h_steps, void* stream);
+
 /* Offset increment torch applies to its Philox generator for one
  * exponential_() over `numel` elements (DistributionTemplates.h calc_execution_policy). */
 uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm);

@@ -6,6 +6,7 @@
 #include "kernels_decode.cuh"
 #include "kernels_ffn.cuh"
 #include "kernels_compact.cuh"
+#include "kernels_beam.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -799,6 +800,7 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
 struct DecBuffers {
     float *x, *qkv, *att, *part, *qc, *h;
     char* kv_pool; int* block_table;   // paged self-attention cache, 6 pools of kv_esz-byte elements
+    int64_t pool_pages;                // pages per layer pool (Nw * pps; twice that for the beam search's copy-on-write parity)
     char* cross_kv;                    // projected memory [layer][K|V][head][row][dh], kv_esz-byte elements
     size_t kv_esz;                     // 4 (fp32 check mode) | 2 (bf16 tensor-core mode)
     int *nk, *row_start; int64_t* row_off; float* kbias_c;
@@ -809,7 +811,7 @@ struct DecBuffers {
 };
 constexpr int MAX_SPLITS = 32;
 
-static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b, bool bf16) {
+static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b, bool bf16, int kv_copies = 1) {
     const int L = d.n_dec_layers;
     const int pps = (max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
     b.x = a.get<float>(Nw * D);
@@ -819,7 +821,8 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     b.qc = a.get<float>(Nw * D);
     b.h = a.get<float>(bf16 ? 0 : Nw * d.d_ff);
     b.kv_esz = bf16 ? 2 : 4;
-    b.kv_pool = a.get<char>((size_t)L * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz);
+    b.pool_pages = (int64_t)kv_copies * Nw * pps;
+    b.kv_pool = a.get<char>((size_t)L * b.pool_pages * 2 * PAGE_TOKENS * D * b.kv_esz);
     b.block_table = a.get<int>(Nw * pps);
     int64_t R = (int64_t)Bmw * S;
     b.cross_kv = a.get<char>((size_t)L * 2 * R * D * b.kv_esz);
@@ -849,6 +852,8 @@ struct DecodeRun {
     const int64_t* trg;       // forced tokens (T, N_total)
     int T;                    // steps to run
     int64_t* tokens; float* probs; float* logits;   // outputs, leading dimension N_total
+    int64_t ldn = -1;         // >= 0 overrides the leading dimension (0: single-row token / logit buffers, beam search)
+    bool serial_first = false;   // the step's first kernel waits for full completion of its predecessor (its prologue reads the block table)
 };
 
 // Projects the memory of one wave to per-layer cross-attention K/V (head-major) once;
@@ -898,6 +903,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     const float scale = 1.0f / sqrtf((float)dh);
     const int* step = b.ctl;
     const int64_t N_total = (int64_t)a.Bm * a.n_cand;
+    const int64_t ldn = r.ldn >= 0 ? r.ldn : N_total;
     const int M = (int)Nw;
 
     // x = LN(x + bias + sum_s part[s]) (separate kernel; fp32 mode and split-K FFN2)
@@ -958,14 +964,14 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             if (l == 0) {
                 if (r.mode == 2) { q.tokens = r.trg + n0; q.tok_shift = 0; }
                 else { q.tokens = r.tokens + n0; q.tok_shift = 1; }
-                q.sos = 3; q.ldn = N_total; q.E_tok = e->W("embed_trg.weight"); q.E_pos = e->W("pe_trg.weight"); q.vocab = d.vocab;
+                q.sos = 3; q.ldn = ldn; q.E_tok = e->W("embed_trg.weight"); q.E_pos = e->W("pe_trg.weight"); q.vocab = d.vocab;
             } else {
                 const LayerW& pw = e->dec[l - 1];
                 q.x_in = b.x; q.part = b.part; q.splits = ffn_splits; q.part_stride = Nw * D;
                 q.pbias = pw.l2_b; q.pgamma = pw.n3_w; q.pbeta = pw.n3_b;
             }
             q.in_w = w.in_w; q.in_b = w.in_b; q.out_w = w.out_w; q.out_b = w.out_b; q.n1_w = w.n1_w; q.n1_b = w.n1_b;
-            q.kv_pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz; q.block_table = b.block_table; q.pps = pps;
+            q.kv_pool = b.kv_pool + (size_t)l * b.pool_pages * 2 * PAGE_TOKENS * D * b.kv_esz; q.block_table = b.block_table; q.pps = pps;
             q.step = step;
             q.in_w16 = e->Wb(w.in_w); q.out_w16 = e->Wb(w.out_w); q.cq_w16 = e->Wb(w.ca_in_w); q.co_w16 = e->Wb(w.ca_out_w);
             q.cq_w = w.ca_in_w; q.cq_b = w.ca_in_b; q.co_w = w.ca_out_w; q.co_b = w.ca_out_b; q.n2_w = w.n2_w; q.n2_b = w.n2_b;
@@ -974,8 +980,9 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             q.x2 = b.x; q.x2_16 = bf16 ? b.x16 : nullptr; q.M = Nw; q.scale = scale; q.eps = 1e-5f;
             q.dbg = (e->da_dbg && l == 3) ? e->da_dbg : nullptr;
             prof_pre(e, s);
-            if (bf16) launch_kernel(decode_attn<8, __nv_bfloat16>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl, q);
-            else launch_kernel(decode_attn<8, float>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl, q);
+            const bool pdl_l = pdl && !(l == 0 && r.serial_first);
+            if (bf16) launch_kernel(decode_attn<8, __nv_bfloat16>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl_l, q);
+            else launch_kernel(decode_attn<8, float>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl_l, q);
             MMT_TRY(check_launch(e, "decode_attn", s));
             if (bf16) {
                 FfnParams f = ffn_params(M, d.d_ff);
@@ -989,15 +996,15 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         }
     } else {
         prof_pre(e, s);
-        if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
-        else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, N_total, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+        if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+        else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
         MMT_TRY(check_launch(e, "decode_embed", s));
 
         const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
         if (dh != 8) MMT_FAIL("decoder head dim must be 8");
         for (int l = 0; l < d.n_dec_layers; ++l) {
             const LayerW& w = e->dec[l];
-            char* pool = b.kv_pool + (size_t)l * Nw * pps * 2 * PAGE_TOKENS * D * b.kv_esz;
+            char* pool = b.kv_pool + (size_t)l * b.pool_pages * 2 * PAGE_TOKENS * D * b.kv_esz;
             const char* ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz;
             if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
             else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
@@ -1041,7 +1048,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     }
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.x = b.x; sp.W = e->W("fc_out.weight"); sp.b = e->W("fc_out.bias"); sp.V = d.vocab; sp.N = Nw; sp.ldn = N_total;
+    sp.x = b.x; sp.W = e->W("fc_out.weight"); sp.b = e->W("fc_out.bias"); sp.V = d.vocab; sp.N = Nw; sp.ldn = ldn;
     sp.temperature = a.temperature; sp.mode = r.mode;
     int smc = a.rng_sm_count > 0 ? a.rng_sm_count : e->sm_count;
     int mts = a.rng_max_threads_per_sm > 0 ? a.rng_max_threads_per_sm : e->max_threads_per_sm;
@@ -1265,6 +1272,115 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     return 0;
 }
 
+// Batched beam search (reference validate_generate_MMT_v15_4.py:995-1086): the K beams of every memory column are K
+// slots of one KV-cached wave; per step one decoder step over all slots (forced-token mode, single-row token / logit
+// buffers), then beam_select + beam_copy_pages (kernels_beam.cuh).  The per-step kernel sequence is position
+// independent (step counter and page parity live on the device), so groups of steps replay as one CUDA graph.
+static int run_beam(mmt_engine* e, const mmt_decode_args& a0, int K, int T, int eos, int64_t* d_seq, int32_t* d_len,
+                    double* d_score, float* d_probs, int32_t* h_steps, cudaStream_t s) {
+    const mmt_model_desc& d = e->desc;
+    if (a0.Bm <= 0 || a0.S <= 0) MMT_FAIL("beam: empty batch");
+    if (K < 1 || K > BEAM_MAX || K > d.vocab) MMT_FAIL("beam: beam_size must be in [1, min(32, vocab)]");
+    if (T < 1 || T > d.max_len || T > 128) MMT_FAIL("beam: gen_len must be in [1, min(128, pe_trg rows)]");
+    if (eos < 0 || eos >= d.vocab) MMT_FAIL("beam: bad <EOS> id");
+    if ((a0.stride_s % 4) || (a0.stride_b % 4) || ((uintptr_t)a0.d_memory % 16)) MMT_FAIL("beam: memory must be 16-byte aligned with strides that are multiples of 4 floats");
+    if (a0.precision != MMT_PREC_FP32 && a0.precision != MMT_PREC_BF16) MMT_FAIL("beam: bad precision");
+    const bool bf16 = a0.precision == MMT_PREC_BF16;
+    mmt_decode_args a = a0;
+    a.n_cand = K; a.max_len = T; a.temperature = 1.f; a.sampling = MMT_SAMPLE_GREEDY; a.stop_on_all_pad = 0;
+    const int pps = (T + PAGE_TOKENS - 1) / PAGE_TOKENS;
+    const int Bm_wave = (int)std::max<int64_t>(1, std::min<int64_t>(a.Bm, 8192 / K));
+    const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
+    const int64_t Nw_max = (int64_t)Bm_wave * K;
+    Arena ar;
+    DecBuffers b;
+    float* logits = nullptr; int64_t* cur_tok = nullptr; int *copy_src = nullptr, *copy_dst = nullptr;
+    auto plan_all = [&]() {
+        plan_decoder(ar, d, Nw_max, Bm_wave, a.S, T, b, bf16, 2);
+        logits = ar.get<float>((size_t)Nw_max * d.vocab);
+        cur_tok = ar.get<int64_t>((size_t)Nw_max);
+        copy_src = ar.get<int>((size_t)Nw_max); copy_dst = ar.get<int>((size_t)Nw_max);
+    };
+    ar.plan = true;
+    plan_all();
+    MMT_TRY(ensure_arena(e, ar.off));
+    ar.plan = false; ar.base = e->arena; ar.cap = e->arena_bytes; ar.off = 0;
+    plan_all();
+    if (bf16) MMT_TRY(tc_init(e));
+    int steps_max = 0;
+    for (int wv = 0; wv < n_waves; ++wv) {
+        const int b0 = wv * Bm_wave, Bmw = std::min(Bm_wave, a.Bm - b0);
+        const int64_t n0 = (int64_t)b0 * K, Nw = (int64_t)Bmw * K;
+        // the wave addresses its slots from 0: pools of a smaller last wave keep the planned (larger) layer stride
+        BeamParams bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.logits = logits; bp.V = d.vocab; bp.K = K; bp.T = T; bp.eos = eos; bp.pps = pps; bp.Nw = Nw; bp.step = b.ctl;
+        bp.score = d_score + n0; bp.len = d_len + n0; bp.hist = d_seq + n0 * (T + 1); bp.probs = d_probs + n0 * T;
+        bp.cur_tok = cur_tok; bp.block_table = b.block_table; bp.copy_src = copy_src; bp.copy_dst = copy_dst; bp.unfinished = b.ctl + 8;
+        MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
+        prof_pre(e, s);
+        beam_init<<<(unsigned)((Nw + 255) / 256), 256, 0, s>>>(bp, 3);
+        MMT_TRY(check_launch(e, "beam_init", s));
+        MMT_TRY(decode_prepare_wave(e, a, b0, Bmw, b, bf16, s));
+        DecodeRun r;
+        r.a = &a; r.mode = 2; r.trg = cur_tok; r.T = T; r.tokens = nullptr; r.probs = nullptr; r.logits = logits;
+        r.ldn = 0; r.serial_first = true;
+        const size_t page_bytes = (size_t)2 * PAGE_TOKENS * D * b.kv_esz;
+        auto one_step = [&](cudaStream_t cs) -> int {
+            MMT_TRY(decode_step(e, r, 0, Nw, Bmw, b, bf16, cs));
+            prof_pre(e, cs);
+            beam_select<<<Bmw, 256, 0, cs>>>(bp);
+            MMT_TRY(check_launch(e, "beam_select", cs));
+            prof_pre(e, cs);
+            beam_copy_pages<<<dim3((unsigned)Nw, d.n_dec_layers), 256, 0, cs>>>(b.kv_pool, (size_t)b.pool_pages * page_bytes, (int)page_bytes, copy_src, copy_dst);
+            MMT_TRY(check_launch(e, "beam_copy_pages", cs));
+            return 0;
+        };
+        int U = 1;
+        for (int u = 2; u <= e->graph_steps; ++u) if (T % u == 0) U = u;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches_per_group = 0;
+        if (e->use_graph && !e->profiling) {
+            if (!e->cap_stream[0]) MMT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream[0], cudaStreamNonBlocking));
+            const int64_t l0 = e->launches;
+            MMT_CUDA(cudaStreamBeginCapture(e->cap_stream[0], cudaStreamCaptureModeRelaxed));
+            int rc = 0;
+            for (int u = 0; u < U && !rc; ++u) rc = one_step(e->cap_stream[0]);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(e->cap_stream[0], &graph);
+            launches_per_group = e->launches - l0;
+            e->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+            if (ce != cudaSuccess) MMT_FAIL(std::string("beam step capture failed: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) MMT_FAIL(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+        } else {
+            U = 1;
+        }
+        struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { if (x) cudaGraphExecDestroy(x); } } guard{exec};
+        // every beam of every item finished -> the remaining steps are fixed points of the reference's loop
+        const int poll_every = U >= 16 ? U : (16 / U) * U;
+        int steps_done = T;
+        for (int t = 0; t < T; t += U) {
+            if (exec) { MMT_CUDA(cudaGraphLaunch(exec, s)); e->launches += launches_per_group; }
+            else MMT_TRY(one_step(s));
+            const int done = t + U;
+            if (done < T && done % poll_every == 0) {
+                MMT_CUDA(cudaMemcpyAsync(e->h_pinned, b.ctl + 8, done * sizeof(int), cudaMemcpyDeviceToHost, s));
+                MMT_CUDA(cudaStreamSynchronize(s));
+                bool stop = false;
+                for (int q = 0; q < done; ++q) if (e->h_pinned[q] == 0) { steps_done = q + 1; stop = true; break; }
+                if (stop) break;
+            }
+        }
+        steps_max = std::max(steps_max, steps_done);
+        if (n_waves > 1) MMT_CUDA(cudaStreamSynchronize(s));   // the next wave reuses the pools
+    }
+    if (h_steps) *h_steps = steps_max;
+    return 0;
+}
+
 }  // namespace mmt
 
 // ===========================================================================
@@ -1433,6 +1549,13 @@ int32_t mmt_teacher_forced(mmt_engine* e, const mmt_decode_args* a, const int64_
     DecodeRun r;
     r.a = a; r.mode = 2; r.trg = d_trg; r.T = T; r.tokens = nullptr; r.probs = nullptr; r.logits = d_logits;
     return run_decode(e, r, nullptr, (cudaStream_t)stream);
+}
+
+int32_t mmt_beam_search(mmt_engine* e, const mmt_decode_args* a, int32_t beam_size, int32_t gen_len, int32_t eos,
+                        int64_t* d_seq, int32_t* d_len, double* d_score, float* d_probs, int32_t* h_steps, void* stream) {
+    if (!e || !a || !d_seq || !d_len || !d_score || !d_probs) MMT_FAIL("null argument");
+    MMT_CUDA(cudaSetDevice(e->device));
+    return run_beam(e, *a, beam_size, gen_len, eos, d_seq, d_len, d_score, d_probs, h_steps, (cudaStream_t)stream);
 }
 
 uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm) {

@@ -192,6 +192,21 @@ class Engine:
             t.record_stream(torch.cuda.current_stream(self.dev_index))
         return logits
 
+    def beam_search(self, memory, key_bias, *, beam_size, gen_len, eos=2, precision="fp32"):
+        """-> (seq (Bm,K,gen_len+1) i64, len (Bm,K) i32, score (Bm,K) f64, probs (Bm,K,gen_len) f32, steps)."""
+        a, keep = self._decode_args(memory, key_bias, beam_size, gen_len, 1.0, 0, False, precision)
+        Bm, K, T = a.Bm, beam_size, gen_len
+        seq = torch.empty(Bm, K, T + 1, device=self.device, dtype=torch.int64)
+        ln = torch.empty(Bm, K, device=self.device, dtype=torch.int32)
+        score = torch.empty(Bm, K, device=self.device, dtype=torch.float64)
+        probs = torch.empty(Bm, K, T, device=self.device, dtype=torch.float32)
+        steps = C.c_int32(T)
+        _lib.check(self.L.mmt_beam_search(self.h, C.byref(a), K, T, eos, seq.data_ptr(), ln.data_ptr(), score.data_ptr(),
+                                          probs.data_ptr(), C.byref(steps), self._stream()))
+        for t in keep:
+            t.record_stream(torch.cuda.current_stream(self.dev_index))
+        return seq, ln, score, probs, int(steps.value)
+
     # ------------------------------------------------------------ unit hooks
     def sample(self, x, temperature=1.0, sampling="greedy", seed=0, offset=0, seq_index_base=0, n_total=0,
                want_logits=False):

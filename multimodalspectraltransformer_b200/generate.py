@@ -8,6 +8,7 @@ running on the B200 engine.
     duplicate_tensor / _dict     run_batch_gen_val_MMT_v15_4.py:93-107
     greedy_sequence_2            mmt_result_test_functions_15_4.py:984-1032
     multinomial_sequence_multi_2 mmt_result_test_functions_15_4.py:791-829
+    beam_search                  validate_generate_MMT_v15_4.py:995-1086
 
 ``model`` may be this package's ``MultimodalTransformer`` or the reference's own
 instance: only its ``state_dict()`` is read.  Runtime knobs (``device``,
@@ -153,3 +154,22 @@ def teacher_forced_logits(model, memory, src_padding_mask, trg_SMI_input, config
     eng = _engine.engine_for(model, config)
     bias = _mask_to_bias(src_padding_mask.to(eng.device))
     return eng.teacher_forced(memory, bias, trg_SMI_input, n_cand=n_candidates, precision=_engine.default_precision(config))
+
+
+def beam_search(model, stoi, memory, src_padding_mask, config, beam_size):
+    """validate_generate_MMT_v15_4.py:1058-1086: -> beams[item] = [(score, sequence, prob_sequence), ...] best first,
+    ``config.gen_len`` steps from [<SOS>]; sequences keep their <SOS> and stop growing at <EOS>; score is the double
+    product of the float32 probabilities under softmax(logits) (no temperature, :1038).  All items and beams advance
+    together on the KV-cached decoder (the reference re-runs every beam's whole prefix, one item at a time)."""
+    model.eval()
+    sos = _check_sos(stoi)
+    gen_len = int(config.gen_len)
+    N = memory.size(1)
+    if gen_len <= 0:
+        return [[(1, [sos], [])] for _ in range(N)]
+    eng = _engine.engine_for(model, config)
+    bias = torch.zeros(N, memory.size(0), device=eng.device) if src_padding_mask is None else _mask_to_bias(src_padding_mask.to(eng.device))
+    seq, ln, score, probs, _ = eng.beam_search(memory, bias, beam_size=int(beam_size), gen_len=gen_len, eos=int(stoi["<EOS>"]),
+                                               precision=_engine.default_precision(config))
+    seq, ln, score, probs = seq.cpu().tolist(), ln.cpu().tolist(), score.cpu().tolist(), probs.cpu().tolist()
+    return [[(score[i][k], seq[i][k][:ln[i][k]], probs[i][k][:ln[i][k] - 1]) for k in range(len(seq[i]))] for i in range(N)]
