@@ -348,6 +348,15 @@ static int launch_encoder_attention(mmt_engine* e, EncGroupRun* gr, int ng, int 
     }
     for (int i = 0; i < ng; ++i) p.g[i].smax = key_bound;
     dim3 grid(heads, Bc, ng);
+    if (dh == AT_DH && e->use_tc_attention && (bf16_out || e->tc_attention_fp32)) {   // encoder_cross in the tensor-core mode: mma.sync flash attention, two-term operand splits
+        const size_t smem_tc = at_smem_bytes(key_bound);
+        const int warps = std::min(8, std::max(1, (row_bound + 15) / 16));   // 8 warps x <= 85 registers: three CTAs per SM hide each other's staging latency
+        MMT_CUDA(cudaFuncSetAttribute(attn_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        MMT_CUDA(cudaFuncSetAttribute(attn_encoder_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        prof_pre(e, s);
+        attn_encoder_tc<<<grid, warps * 32, smem_tc, s>>>(p);
+        return check_launch(e, "attn_encoder_tc", s);
+    }
     const size_t smem = (size_t)key_bound * (2 * dh + 1) * sizeof(float);
     const int threads = std::min(256, std::max(64, (row_bound + 31) / 32 * 32));
     if (dh == 8) {
@@ -1445,6 +1454,8 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_NO_ENC_STREAMS")) e->use_enc_streams = false;
     if (const char* v = getenv("MMT_DECODE_LANES")) e->decode_lanes = std::max(1, atoi(v));
     if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
+    if (getenv("MMT_NO_TC_ATTENTION")) e->use_tc_attention = false;
+    if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };

@@ -460,6 +460,206 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Tensor-core variant for the 32-wide heads of encoder_cross (bf16 mode): flash-style attention of one
+// (head, sequence) per CTA on mma.sync m16n8k16 (bf16 in, fp32 accumulate).  The operands stay at fp32
+// accuracy through two-term bf16 splits -- s = qh.kh + qh.kl + ql.kh, o += ph.vh + ph.vl + pl.vh (the dropped
+// lo.lo terms are 2^-18 relative) -- so the kernel changes the speed of the attention, not the numerics of the
+// mode.  K and V are staged row-major [key][32] (+8 pad: 80-byte rows, conflict-free for ldmatrix) as hi / lo
+// bf16 planes; B fragments come from ldmatrix (K) / ldmatrix.trans (V).  One warp per 16 query rows, keys in
+// blocks of 16, online softmax in the log2 domain on the accumulator layout (the score tile's C fragment is
+// the P tile's A fragment).
+// ---------------------------------------------------------------------------
+constexpr int AT_DH = 32;
+constexpr int AT_KROW = AT_DH + 8;     // bf16 elements per staged K / V row
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// (x, y) -> packed bf16 hi pair and the packed bf16 pair of the rounding residuals
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - __low2float(h), y - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__host__ __device__ inline int at_keys_padded(int nk) { return (nk + 15) / 16 * 16; }
+__host__ __device__ inline size_t at_smem_bytes(int key_bound) {
+    const int nkp = at_keys_padded(key_bound);
+    return (size_t)4 * nkp * AT_KROW * 2 + (size_t)nkp * 4;
+}
+
+__global__ void __launch_bounds__(256, 3) attn_encoder_tc(const __grid_constant__ AttnParams p) {
+    extern __shared__ __align__(16) unsigned char at_smem[];
+    const AttnGroup& g = p.g[blockIdx.z];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int S = g.cnt ? g.cnt[b] : g.S;
+    const int kstride = g.cnt ? g.kstride : g.S;
+    const int64_t row0 = g.row_start ? (int64_t)g.row_start[b] : (int64_t)b * g.S;
+    const int nk = g.nk[b];
+    const int nkp_max = at_keys_padded(g.smax);
+    const int nkp = at_keys_padded(nk);
+    const size_t plane = (size_t)nkp_max * AT_KROW;                  // bf16 elements per plane
+    __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(at_smem);  // [nkp][AT_KROW] each
+    __nv_bfloat16* Kl = Kh + plane;
+    __nv_bfloat16* Vh = Kl + plane;
+    __nv_bfloat16* Vl = Vh + plane;
+    float* bs = reinterpret_cast<float*>(Vl + plane);               // [nkp] key bias * log2(e)
+    const float* base = g.qkv + row0 * (3 * D);
+    constexpr float LOG2E = 1.4426950408889634f;
+    // ---- stage K / V of the attendable keys as hi / lo bf16 planes; zero the padding keys.
+    // Four items per thread and pass: the index loads, then the row loads, are all in flight before the first conversion.
+    const int total = nkp * (AT_DH / 4);
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        int key[4];
+        float4 kk[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x, jj = i / (AT_DH / 4);
+            key[u] = (i < total && jj < nk) ? g.kidx[(int64_t)b * kstride + jj] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x, q4 = i % (AT_DH / 4);
+            kk[u] = make_float4(0.f, 0.f, 0.f, 0.f); vv[u] = kk[u];
+            if (key[u] >= 0) {
+                const float* row = base + (int64_t)key[u] * (3 * D) + h * AT_DH + q4 * 4;
+                kk[u] = *reinterpret_cast<const float4*>(row + D);
+                vv[u] = *reinterpret_cast<const float4*>(row + 2 * D);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i >= total) break;
+            const int jj = i / (AT_DH / 4), q4 = i % (AT_DH / 4);
+            if (q4 == 0) bs[jj] = key[u] >= 0 ? (g.kbias ? g.kbias[(int64_t)b * g.S + key[u]] * LOG2E : 0.f) : MMT_NEG_INF;
+            uint32_t h0, l0, h1, l1;
+            split_pair(kk[u].x, kk[u].y, h0, l0); split_pair(kk[u].z, kk[u].w, h1, l1);
+            *reinterpret_cast<uint2*>(Kh + jj * AT_KROW + q4 * 4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Kl + jj * AT_KROW + q4 * 4) = make_uint2(l0, l1);
+            split_pair(vv[u].x, vv[u].y, h0, l0); split_pair(vv[u].z, vv[u].w, h1, l1);
+            *reinterpret_cast<uint2*>(Vh + jj * AT_KROW + q4 * 4) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Vl + jj * AT_KROW + q4 * 4) = make_uint2(l0, l1);
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    // ldmatrix row addresses of this lane (bytes from the plane base, without the key-block offset):
+    //   K: matrix lane/8 = dims (lane/8)*8.., row = key (lane%8) of the tile
+    //   V (trans): matrix lane/8: keys ((lane/8)&1)*8 + lane%8, dims ((lane/8)>>1)*8..
+    const uint32_t k_lane_off = (uint32_t)(((lane & 7) * AT_KROW + (lane >> 3) * 8) * 2);
+    const uint32_t v_lane_off = (uint32_t)((((((lane >> 3) & 1) * 8) + (lane & 7)) * AT_KROW + (lane >> 4) * 8) * 2);
+    const uint32_t sKh = (uint32_t)__cvta_generic_to_shared(Kh), sKl = (uint32_t)__cvta_generic_to_shared(Kl);
+    const uint32_t sVh = (uint32_t)__cvta_generic_to_shared(Vh), sVl = (uint32_t)__cvta_generic_to_shared(Vl);
+    const float qscale = p.scale * LOG2E;
+    for (int tile = warp; tile * 16 < S; tile += nwarps) {
+        const int r_lo = tile * 16 + gq, r_hi = r_lo + 8;
+        // Q fragments (scaled into the log2 domain, split): [kstep][4 regs]
+        uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {            // columns ks*16 + 2t (+8)
+                const int col = h * AT_DH + ks * 16 + half * 8 + 2 * tq;
+                float2 a = make_float2(0.f, 0.f), c = a;
+                if (r_lo < S) a = *reinterpret_cast<const float2*>(base + (int64_t)r_lo * (3 * D) + col);
+                if (r_hi < S) c = *reinterpret_cast<const float2*>(base + (int64_t)r_hi * (3 * D) + col);
+                split_pair(a.x * qscale, a.y * qscale, qh[ks][half * 2], ql[ks][half * 2]);
+                split_pair(c.x * qscale, c.y * qscale, qh[ks][half * 2 + 1], ql[ks][half * 2 + 1]);
+            }
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+        float m_lo = MMT_NEG_INF, m_hi = MMT_NEG_INF, l_lo = 0.f, l_hi = 0.f;
+        for (int kb = 0; kb < nkp; kb += 16) {
+            const uint32_t kb_off = (uint32_t)(kb * AT_KROW * 2);
+            // ---- scores of 16 keys: two 16x8 tiles
+            float sc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float2 bb = *reinterpret_cast<const float2*>(bs + kb + nt * 8 + 2 * tq);
+                sc[nt][0] = bb.x; sc[nt][1] = bb.y; sc[nt][2] = bb.x; sc[nt][3] = bb.y;
+                uint32_t kh[4], kl[4];          // {b0, b1} of k-step 0, {b0, b1} of k-step 1
+                const uint32_t t_off = kb_off + (uint32_t)(nt * 8 * AT_KROW * 2) + k_lane_off;
+                ldmatrix_x4(kh, sKh + t_off);
+                ldmatrix_x4(kl, sKl + t_off);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    mma_bf16_16816(sc[nt], qh[ks], kh[ks * 2], kh[ks * 2 + 1]);
+                    mma_bf16_16816(sc[nt], qh[ks], kl[ks * 2], kl[ks * 2 + 1]);
+                    mma_bf16_16816(sc[nt], ql[ks], kh[ks * 2], kh[ks * 2 + 1]);
+                }
+            }
+            // ---- online softmax over the block (rows g and g+8; a row lives in the 4 lanes of a quad)
+            float bm_lo = fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1]));
+            float bm_hi = fmaxf(fmaxf(sc[0][2], sc[0][3]), fmaxf(sc[1][2], sc[1][3]));
+            bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+            bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+            const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
+            const float corr_lo = ex2_approx(m_lo - nm_lo), corr_hi = ex2_approx(m_hi - nm_hi);     // first block: 2^-inf = 0
+            m_lo = nm_lo; m_hi = nm_hi;
+            l_lo *= corr_lo; l_hi *= corr_hi;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) { acc[nt][0] *= corr_lo; acc[nt][1] *= corr_lo; acc[nt][2] *= corr_hi; acc[nt][3] *= corr_hi; }
+            uint32_t ph[4], pl[4];      // A fragment of P over the 16 keys: {tile0 row g, tile0 row g+8, tile1 row g, tile1 row g+8}
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float e0 = ex2_approx(sc[nt][0] - m_lo), e1 = ex2_approx(sc[nt][1] - m_lo);
+                const float e2 = ex2_approx(sc[nt][2] - m_hi), e3 = ex2_approx(sc[nt][3] - m_hi);
+                l_lo += e0 + e1; l_hi += e2 + e3;
+                split_pair(e0, e1, ph[nt * 2], pl[nt * 2]);
+                split_pair(e2, e3, ph[nt * 2 + 1], pl[nt * 2 + 1]);
+            }
+            // ---- o += P V  (B fragments by ldmatrix.trans: keys kb + 2t (+8), column d = nt*8 + g)
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {      // pairs of 8-wide output tiles
+                uint32_t vh[4], vl[4];            // {b0, b1} of tile 2*np, {b0, b1} of tile 2*np + 1
+                const uint32_t t_off = kb_off + (uint32_t)(np * 16 * 2) + v_lane_off;
+                ldmatrix_x4_trans(vh, sVh + t_off);
+                ldmatrix_x4_trans(vl, sVl + t_off);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    mma_bf16_16816(acc[np * 2 + u], ph, vh[u * 2], vh[u * 2 + 1]);
+                    mma_bf16_16816(acc[np * 2 + u], ph, vl[u * 2], vl[u * 2 + 1]);
+                    mma_bf16_16816(acc[np * 2 + u], pl, vh[u * 2], vh[u * 2 + 1]);
+                }
+            }
+        }
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+        const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = h * AT_DH + nt * 8 + 2 * tq;
+            if (r_lo < S) {
+                if (g.out) *reinterpret_cast<float2*>(g.out + (row0 + r_lo) * D + col) = make_float2(acc[nt][0] * inv_lo, acc[nt][1] * inv_lo);
+                if (g.out16) *reinterpret_cast<__nv_bfloat162*>(g.out16 + (row0 + r_lo) * D + col) = __floats2bfloat162_rn(acc[nt][0] * inv_lo, acc[nt][1] * inv_lo);
+            }
+            if (r_hi < S) {
+                if (g.out) *reinterpret_cast<float2*>(g.out + (row0 + r_hi) * D + col) = make_float2(acc[nt][2] * inv_hi, acc[nt][3] * inv_hi);
+                if (g.out16) *reinterpret_cast<__nv_bfloat162*>(g.out16 + (row0 + r_hi) * D + col) = __floats2bfloat162_rn(acc[nt][2] * inv_hi, acc[nt][3] * inv_hi);
+            }
+        }
+    }
+}
+
 // mean over the S rows of a sequence-first memory (S,B,D) -> (B,D)   (models_MMT_v15_4.py:946)
 __global__ void __launch_bounds__(128) mean_over_sequence(const float* mem, int S, int B, float* avg) {
     const int b = blockIdx.x, d = threadIdx.x;

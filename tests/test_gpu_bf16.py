@@ -139,3 +139,34 @@ def test_ffn_fused_tcgen05(M, F, splits):
     # accumulation order: a handful of elements may round the other way (1 bf16 ulp of h ~ 4e-3 * |h|)
     torch.testing.assert_close(out.double(), ref, atol=3e-3, rtol=1e-3)
     assert float((out.double() - ref).abs().mean()) < 2e-4
+
+
+@pytest.mark.parametrize("name,dense", [("full_b5", False), ("full_b5", True), ("maxpeaks_b2", False), ("mode_hsqc_b2", True),
+                                        ("blank_hsqc_only_b3", True)])
+def test_cross_encoder_tensor_core_attention_equals_simt(name, dense, monkeypatch):
+    """attn_encoder_tc (mma.sync, two-term operand splits, exp2) reproduces the fp32 SIMT attention kernel to fp32
+    round-off.  Checked in the fp32 mode (test hook MMT_TC_ATTENTION_FP32), where no bf16 rounding downstream
+    amplifies last-bit differences: ragged and dense key lists, bool and float key masks.  In the bf16 mode the two
+    variants must agree within that mode's own rounding noise."""
+    from multimodalspectraltransformer_b200.engine import Engine
+    s = setup()
+    case, data, z = load_case(name)
+    cfg = cfg_for(case)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if dense:
+        monkeypatch.setenv("MMT_DENSE_ENCODER", "1")
+    monkeypatch.setenv("MMT_TC_ATTENTION_FP32", "1")
+    eng_tc = Engine(s["model"].state_dict(), cfg, dev)
+    monkeypatch.delenv("MMT_TC_ATTENTION_FP32")
+    monkeypatch.setenv("MMT_NO_TC_ATTENTION", "1")
+    eng_simt = Engine(s["model"].state_dict(), cfg, dev)
+    a = eng_tc.encode(data, case["mode"], "fp32", False)
+    b = eng_simt.encode(data, case["mode"], "fp32", False)
+    assert torch.equal(a[1], b[1])
+    scale = b[0].abs().max().item()
+    assert (a[0] - b[0]).abs().max().item() <= 2e-5 * scale
+    torch.testing.assert_close(a[3], b[3], atol=2e-5, rtol=0)
+    a16 = eng_tc.encode(data, case["mode"], "bf16", False)
+    b16 = eng_simt.encode(data, case["mode"], "bf16", False)
+    assert (a16[0] - b16[0]).abs().max().item() <= 2e-2 * scale
+    assert (a16[0] - b16[0]).abs().mean().item() <= 1e-3 * scale
