@@ -350,7 +350,7 @@ static int launch_encoder_attention(mmt_engine* e, EncGroupRun* gr, int ng, int 
     dim3 grid(heads, Bc, ng);
     if (dh == AT_DH && e->use_tc_attention && (bf16_out || e->tc_attention_fp32)) {   // encoder_cross in the tensor-core mode: mma.sync flash attention, two-term operand splits
         const size_t smem_tc = at_smem_bytes(key_bound);
-        const int warps = std::min(8, std::max(1, (row_bound + 15) / 16));   // 8 warps x <= 85 registers: three CTAs per SM hide each other's staging latency
+        const int warps = std::min(12, std::max(1, (row_bound + 15) / 16));   // one 16-row tile per warp for realistic peak counts; <= 85 registers: two CTAs per SM
         MMT_CUDA(cudaFuncSetAttribute(attn_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         MMT_CUDA(cudaFuncSetAttribute(attn_encoder_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         prof_pre(e, s);

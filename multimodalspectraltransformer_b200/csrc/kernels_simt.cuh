@@ -465,13 +465,15 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
 // (head, sequence) per CTA on mma.sync m16n8k16 (bf16 in, fp32 accumulate).  The operands stay at fp32
 // accuracy through two-term bf16 splits -- s = qh.kh + qh.kl + ql.kh, o += ph.vh + ph.vl + pl.vh (the dropped
 // lo.lo terms are 2^-18 relative) -- so the kernel changes the speed of the attention, not the numerics of the
-// mode.  K and V are staged row-major [key][32] (+8 pad: 80-byte rows, conflict-free for ldmatrix) as hi / lo
-// bf16 planes; B fragments come from ldmatrix (K) / ldmatrix.trans (V).  One warp per 16 query rows, keys in
+// mode.  K and V are staged row-major [key][32] (64-byte rows, 16-byte chunks XOR-swizzled with (key >> 1) & 3:
+// conflict-free for ldmatrix) as hi / lo bf16 planes; B fragments come from ldmatrix (K) / ldmatrix.trans (V).  One warp per 16 query rows, keys in
 // blocks of 16, online softmax in the log2 domain on the accumulator layout (the score tile's C fragment is
 // the P tile's A fragment).
 // ---------------------------------------------------------------------------
 constexpr int AT_DH = 32;
-constexpr int AT_KROW = AT_DH + 8;     // bf16 elements per staged K / V row
+constexpr int AT_KROW = AT_DH;         // bf16 elements per staged K / V row
+// element offset of dims [q4*4, q4*4+4) of key row `key` inside a plane
+__device__ __forceinline__ int at_off(int key, int q4) { return key * AT_KROW + ((((q4 >> 1) ^ (key >> 1)) & 3) << 3) + ((q4 & 1) << 2); }
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -502,7 +504,7 @@ __host__ __device__ inline size_t at_smem_bytes(int key_bound) {
     return (size_t)4 * nkp * AT_KROW * 2 + (size_t)nkp * 4;
 }
 
-__global__ void __launch_bounds__(256, 3) attn_encoder_tc(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(16) unsigned char at_smem[];
     const AttnGroup& g = p.g[blockIdx.z];
     const int h = blockIdx.x, b = blockIdx.y;
@@ -549,11 +551,11 @@ __global__ void __launch_bounds__(256, 3) attn_encoder_tc(const __grid_constant_
             if (q4 == 0) bs[jj] = key[u] >= 0 ? (g.kbias ? g.kbias[(int64_t)b * g.S + key[u]] * LOG2E : 0.f) : MMT_NEG_INF;
             uint32_t h0, l0, h1, l1;
             split_pair(kk[u].x, kk[u].y, h0, l0); split_pair(kk[u].z, kk[u].w, h1, l1);
-            *reinterpret_cast<uint2*>(Kh + jj * AT_KROW + q4 * 4) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(Kl + jj * AT_KROW + q4 * 4) = make_uint2(l0, l1);
+            *reinterpret_cast<uint2*>(Kh + at_off(jj, q4)) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Kl + at_off(jj, q4)) = make_uint2(l0, l1);
             split_pair(vv[u].x, vv[u].y, h0, l0); split_pair(vv[u].z, vv[u].w, h1, l1);
-            *reinterpret_cast<uint2*>(Vh + jj * AT_KROW + q4 * 4) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(Vl + jj * AT_KROW + q4 * 4) = make_uint2(l0, l1);
+            *reinterpret_cast<uint2*>(Vh + at_off(jj, q4)) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(Vl + at_off(jj, q4)) = make_uint2(l0, l1);
         }
     }
     __syncthreads();
@@ -562,8 +564,10 @@ __global__ void __launch_bounds__(256, 3) attn_encoder_tc(const __grid_constant_
     // ldmatrix row addresses of this lane (bytes from the plane base, without the key-block offset):
     //   K: matrix lane/8 = dims (lane/8)*8.., row = key (lane%8) of the tile
     //   V (trans): matrix lane/8: keys ((lane/8)&1)*8 + lane%8, dims ((lane/8)>>1)*8..
-    const uint32_t k_lane_off = (uint32_t)(((lane & 7) * AT_KROW + (lane >> 3) * 8) * 2);
-    const uint32_t v_lane_off = (uint32_t)((((((lane >> 3) & 1) * 8) + (lane & 7)) * AT_KROW + (lane >> 4) * 8) * 2);
+    // (tile bases are multiples of 8 keys, so the swizzle term depends on lane % 8 only)
+    const int sw = (lane & 7) >> 1;
+    const uint32_t k_lane_off = (uint32_t)(((lane & 7) * AT_KROW + (((lane >> 3) ^ sw) & 3) * 8) * 2);
+    const uint32_t v_row_off = (uint32_t)((((((lane >> 3) & 1) * 8) + (lane & 7)) * AT_KROW) * 2);
     const uint32_t sKh = (uint32_t)__cvta_generic_to_shared(Kh), sKl = (uint32_t)__cvta_generic_to_shared(Kl);
     const uint32_t sVh = (uint32_t)__cvta_generic_to_shared(Vh), sVl = (uint32_t)__cvta_generic_to_shared(Vl);
     const float qscale = p.scale * LOG2E;
@@ -613,11 +617,13 @@ __global__ void __launch_bounds__(256, 3) attn_encoder_tc(const __grid_constant_
             bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
             bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
             const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
-            const float corr_lo = ex2_approx(m_lo - nm_lo), corr_hi = ex2_approx(m_hi - nm_hi);     // first block: 2^-inf = 0
-            m_lo = nm_lo; m_hi = nm_hi;
-            l_lo *= corr_lo; l_hi *= corr_hi;
+            if (__any_sync(0xffffffffu, nm_lo != m_lo || nm_hi != m_hi)) {      // a row maximum moved (else every factor is exactly 1)
+                const float corr_lo = ex2_approx(m_lo - nm_lo), corr_hi = ex2_approx(m_hi - nm_hi);     // first block: 2^-inf = 0
+                m_lo = nm_lo; m_hi = nm_hi;
+                l_lo *= corr_lo; l_hi *= corr_hi;
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) { acc[nt][0] *= corr_lo; acc[nt][1] *= corr_lo; acc[nt][2] *= corr_hi; acc[nt][3] *= corr_hi; }
+                for (int nt = 0; nt < 4; ++nt) { acc[nt][0] *= corr_lo; acc[nt][1] *= corr_lo; acc[nt][2] *= corr_hi; acc[nt][3] *= corr_hi; }
+            }
             uint32_t ph[4], pl[4];      // A fragment of P over the 16 keys: {tile0 row g, tile0 row g+8, tile1 row g, tile1 row g+8}
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(256, 3) attn_encoder_tc(const __grid_constant_
 #pragma unroll
             for (int np = 0; np < 2; ++np) {      // pairs of 8-wide output tiles
                 uint32_t vh[4], vl[4];            // {b0, b1} of tile 2*np, {b0, b1} of tile 2*np + 1
-                const uint32_t t_off = kb_off + (uint32_t)(np * 16 * 2) + v_lane_off;
+                const uint32_t t_off = kb_off + v_row_off + (uint32_t)((((np * 2 + (lane >> 4)) ^ sw) & 3) * 16);
                 ldmatrix_x4_trans(vh, sVh + t_off);
                 ldmatrix_x4_trans(vl, sVl + t_off);
 #pragma unroll
