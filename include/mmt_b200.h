@@ -123,6 +123,15 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
                    int32_t precision, float* d_memory, float* d_embedding_src, float* d_key_bias,
                    uint8_t* d_pad_mask, float* d_fingerprint, float* d_avg_memory, void* stream);
 
+/* Bitwise equality of the collated inputs of two encode calls (all arrays of the modalities in mode_bits, B spectra).
+ * Serves the repeated-encode pattern of the callers -- CLIP's forward(trg=None) on a batch run_model has just encoded
+ * (models_CLIP_v15_4.py:278-285, 337-347): the host keeps the last encode's inputs and outputs and
+ * skips the second encode when this returns 1.  One small kernel, a 4-byte device-to-host read, synchronises `stream`.
+ * mmt_encode itself accepts d_memory == NULL with d_embedding_src != NULL for an embedding-only pass (forward()'s
+ * second output when the rest comes from the cache). */
+int32_t mmt_spectra_equal(mmt_engine* e, const mmt_spectra* a, const mmt_spectra* b, int32_t B, uint32_t mode_bits,
+                          int32_t* h_equal, void* stream);
+
 /* ---- decoder ---------------------------------------------------------------- */
 
 typedef struct mmt_decode_args {

@@ -734,6 +734,7 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
         embed_tokens<<<dim3(Bc, 5), 128, 0, s>>>(p);
         MMT_TRY(check_launch(e, "embed_tokens", s));
     }
+    if (!d_memory) return 0;   // embedding-only call (forward()'s 2nd output for an encode served from the cache)
     {   // key compaction for the modality encoders and encoder_cross
         KeyIndexParams p;
         memset(&p, 0, sizeof(p));
@@ -1507,7 +1508,8 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
                    float* d_fingerprint, float* d_avg_memory, void* stream) {
     if (!e || !in) MMT_FAIL("null engine / spectra");
     if (B <= 0) MMT_FAIL("encode: B must be > 0");
-    if (!d_memory) MMT_FAIL("encode: d_memory is required");
+    if (!d_memory && !d_embedding_src) MMT_FAIL("encode: d_memory is required (or d_embedding_src alone for an embedding-only call)");
+    if (!d_memory && (d_fingerprint || d_avg_memory)) MMT_FAIL("encode: fingerprint / mean need d_memory");
     if (precision != MMT_PREC_FP32 && precision != MMT_PREC_BF16) MMT_FAIL("bad precision");
     // reference constraints: some NMR modality and MW must be present
     if (!(mode_bits & 0xF)) MMT_FAIL("training_mode needs at least one of 1H/13C/HSQC/COSY (the reference crashes without)");
@@ -1520,7 +1522,7 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
         int Bc = std::min(chunk, B - b0);
         // ragged path: all five spectra in training_mode (bool key-padding masks everywhere)
         int rc = 2;
-        if (e->use_compact && !L.float_mask && L.present[4])
+        if (d_memory && e->use_compact && !L.float_mask && L.present[4])
             rc = encode_chunk_compact(e, *in, b0, Bc, B, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, precision == MMT_PREC_BF16, s);
         if (rc == 1) return 1;
         if (rc == 2) MMT_TRY(encode_chunk(e, *in, b0, Bc, B, mode_bits, L, d_memory, d_embedding_src, d_key_bias, d_pad_mask, precision == MMT_PREC_BF16, s));
@@ -1567,6 +1569,43 @@ int32_t mmt_beam_search(mmt_engine* e, const mmt_decode_args* a, int32_t beam_si
     if (!e || !a || !d_seq || !d_len || !d_score || !d_probs) MMT_FAIL("null argument");
     MMT_CUDA(cudaSetDevice(e->device));
     return run_beam(e, *a, beam_size, gen_len, eos, d_seq, d_len, d_score, d_probs, h_steps, (cudaStream_t)stream);
+}
+
+int32_t mmt_spectra_equal(mmt_engine* e, const mmt_spectra* a, const mmt_spectra* b, int32_t B, uint32_t mode_bits, int32_t* h_equal, void* stream) {
+    if (!e || !a || !b || !h_equal) MMT_FAIL("null argument");
+    if (B <= 0) MMT_FAIL("B must be > 0");
+    MMT_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const mmt_model_desc& d = e->desc;
+    const int64_t P = d.pad_points;
+    CompareParams p;
+    memset(&p, 0, sizeof(p));
+    int n = 0;
+    bool missing = false;
+    auto seg = [&](const void* x, const void* y, int64_t bytes) {
+        if (!x || !y) { missing = true; return; }
+        p.a[n] = reinterpret_cast<const unsigned char*>(x); p.b[n] = reinterpret_cast<const unsigned char*>(y); p.bytes[n] = bytes; ++n;
+    };
+    if (mode_bits & MMT_MODE_1H) { seg(a->d_src_1H, b->d_src_1H, B * P * 8); seg(a->d_mask_1H, b->d_mask_1H, B * P * 4); }
+    if (mode_bits & MMT_MODE_13C) { seg(a->d_src_13C, b->d_src_13C, B * P * 4); seg(a->d_mask_13C, b->d_mask_13C, B * P * 4); }
+    if (mode_bits & MMT_MODE_HSQC) { seg(a->d_src_HSQC, b->d_src_HSQC, B * P * 8); seg(a->d_mask_HSQC, b->d_mask_HSQC, B * P * 4); }
+    if (mode_bits & MMT_MODE_COSY) { seg(a->d_src_COSY, b->d_src_COSY, B * P * 8); seg(a->d_mask_COSY, b->d_mask_COSY, B * P * 4); }
+    if (mode_bits & MMT_MODE_IR) seg(a->d_src_IR, b->d_src_IR, (int64_t)B * d.ir_bins * 4);
+    if (mode_bits & MMT_MODE_MF) { seg(a->d_src_MF, b->d_src_MF, B * P * 8); seg(a->d_mask_MF, b->d_mask_MF, B * P); }
+    if (mode_bits & MMT_MODE_MS) { seg(a->d_src_MS, b->d_src_MS, B * P * 8); seg(a->d_mask_MS, b->d_mask_MS, B * P); }
+    if (mode_bits & MMT_MODE_MW) seg(a->d_trg_MW, b->d_trg_MW, (int64_t)B * 4);
+    if (missing) MMT_FAIL("spectra pointer missing for a modality in training_mode");
+    p.n = n;
+    MMT_TRY(ensure_arena(e, 256));
+    int* flag = reinterpret_cast<int*>(e->arena);
+    p.differ = flag;
+    MMT_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    compare_segments<<<dim3(64, n), 256, 0, s>>>(p);
+    MMT_CUDA(cudaGetLastError());
+    MMT_CUDA(cudaMemcpyAsync(e->h_pinned, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MMT_CUDA(cudaStreamSynchronize(s));
+    *h_equal = e->h_pinned[0] == 0;
+    return 0;
 }
 
 uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm) {

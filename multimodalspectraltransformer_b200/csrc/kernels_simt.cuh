@@ -1070,6 +1070,25 @@ __global__ void __launch_bounds__(256) ingest_ir(const double* vals, const int64
     }
 }
 
+// Bitwise comparison of up to 16 pairs of arrays (the collated inputs of two encode calls): *differ |= 1 on any mismatch.
+struct CompareParams { const unsigned char* a[16]; const unsigned char* b[16]; int64_t bytes[16]; int n; int* differ; };
+__global__ void __launch_bounds__(256) compare_segments(const __grid_constant__ CompareParams p) {
+    const int sgm = blockIdx.y;
+    const unsigned char *x = p.a[sgm], *y = p.b[sgm];
+    const int64_t nb = p.bytes[sgm];
+    bool diff = false;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)nb) & 15) == 0) {
+        const uint4 *x4 = reinterpret_cast<const uint4*>(x), *y4 = reinterpret_cast<const uint4*>(y);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb / 16; i += (int64_t)gridDim.x * blockDim.x) {
+            const uint4 u = x4[i], v = y4[i];
+            diff |= (u.x != v.x) | (u.y != v.y) | (u.z != v.z) | (u.w != v.w);
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) diff |= x[i] != y[i];
+    }
+    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(p.differ, 1);
+}
+
 __global__ void set_u64x2(uint64_t* dst, uint64_t a, uint64_t b) { dst[0] = a; dst[1] = b; }
 
 __global__ void pack_tokens_u8(const int64_t* in, int64_t n, uint8_t* out) {

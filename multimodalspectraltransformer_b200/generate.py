@@ -43,9 +43,9 @@ def _mask_to_bias(mask: torch.Tensor) -> torch.Tensor:
     return torch.zeros(pad.shape, dtype=torch.float32, device=pad.device).masked_fill_(pad, float("-inf"))
 
 
-def _encode(eng, data, config, want_embedding_src=False):
+def _encode(eng, data, config, want_embedding_src=False, reuse=False):
     prec = _engine.default_precision(config)
-    memory, pad, key_bias, fp, avg, emb = eng.encode(data, config.training_mode, prec, want_embedding_src)
+    memory, pad, key_bias, fp, avg, emb = eng.encode(data, config.training_mode, prec, want_embedding_src, reuse=reuse)
     from . import _lib
     if _lib.lib().mmt_mask_is_float(_lib.mode_bits(config.training_mode)):
         mask = pad.to(torch.float32)       # torch.cat promoted the reference's mask to float 0/1

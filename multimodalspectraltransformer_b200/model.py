@@ -74,14 +74,15 @@ class MultimodalTransformer(nn.Module):
                     src_MF=src_MF, mask_MF=mask_MF, src_MS=src_MS, mask_MS=mask_MS, trg_MW=trg_MW)
         eng = _engine.engine_for(self, self.config)
         prec = _engine.default_precision(self.config)
-        memory, mask, fingerprint, avg, emb = _encode(eng, data, self.config, want_embedding_src=True)
+        # reuse=True: a batch this engine has just encoded (run_model followed by CLIP's forward, models_CLIP_v15_4.py:278-285)
+        # is served from the remembered outputs after a device-side bitwise comparison of the inputs
+        memory, mask, fingerprint, avg, emb = _encode(eng, data, self.config, want_embedding_src=True, reuse=True)
         if trg_SMI_input is None:
             return memory, emb, mask, fingerprint
         if self.training and self.config.drop_out > 0:
             raise RuntimeError("the B200 engine is inference-only: call model.eval() (dropout2 is not implemented)")
         logits = eng.teacher_forced(memory, _mask_to_bias(mask), trg_SMI_input, precision=prec)
         if getattr(self.config, "use_real_data", False):      # :965-971
-            rd = torch.nn.functional.linear(avg, self.real_data_linear.weight.to(avg.device),
-                                            self.real_data_linear.bias.to(avg.device))
+            rd = eng.linear(avg, self.real_data_linear.weight.detach(), self.real_data_linear.bias.detach())
             logits = (logits + rd.unsqueeze(0)) / 2
         return logits, fingerprint, memory, mask

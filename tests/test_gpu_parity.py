@@ -131,6 +131,60 @@ def test_encoder_vs_reference_golden(name):
     np.testing.assert_allclose(emb.double().sum(dim=(0, 2)).cpu().numpy(), z["embedding_src_sum"], atol=1e-3)
 
 
+def test_repeated_encode_is_served_from_the_last_one_only_when_inputs_are_bit_identical(monkeypatch):
+    """CLIP's forward(trg=None) on the batch run_model has just encoded costs one comparison kernel, not a
+    second encode; any change of the inputs (new tensors or in-place), of the mode, or of the returned outputs misses."""
+    s = setup()
+    from multimodalspectraltransformer_b200.engine import Engine, engine_for
+    case, data, z = load_case("full_b5")
+    cfg = cfg_for(case)
+    model = s["model"]
+    model.config = cfg
+    eng = engine_for(model, cfg)
+    keys = ("src_1H", "mask_1H", "src_13C", "mask_13C", "src_HSQC", "mask_HSQC", "src_COSY", "mask_COSY",
+            "src_IR", "mask_IR", "src_MF", "mask_MF", "src_MS", "mask_MS", "trg_MW")
+    memory, mask, _, fp, _, _ = s["M"].run_model(model, data, cfg)
+    h0, l0 = eng.encode_cache_hits, eng.launch_count()
+    mem2, emb, mask2, fp2 = model(*[data[k] for k in keys])             # host tensors again -> fresh device copies
+    assert eng.encode_cache_hits == h0 + 1 and eng.launch_count() - l0 <= 3
+    assert torch.equal(mem2, memory) and torch.equal(fp2, fp) and torch.equal(mask2, mask) and mem2.data_ptr() != memory.data_ptr()
+    monkeypatch.setenv("MMT_NO_ENCODE_CACHE", "1")
+    fresh = Engine(model.state_dict(), cfg, eng.device).encode(data, case["mode"], "fp32", True)
+    monkeypatch.delenv("MMT_NO_ENCODE_CACHE")
+    assert torch.equal(fresh[0], mem2) and torch.equal(fresh[5], emb) and torch.equal(fresh[3], fp2)
+    mem3, emb3, _, _ = model(*[data[k] for k in keys])                   # second hit: embedding_src now remembered too
+    assert eng.encode_cache_hits == h0 + 2 and torch.equal(emb3, emb)
+    # one peak moved -> miss, different memory
+    d2 = {k: v.clone() for k, v in data.items()}
+    d2["src_13C"][1, 0] += 0.25
+    mem4, _, _, _ = model(*[d2[k] for k in keys])
+    assert eng.encode_cache_hits == h0 + 2 and not torch.equal(mem4, memory)
+    # device-resident inputs changed in place -> miss
+    dd = {k: v.cuda() for k, v in data.items()}
+    m5 = model(*[dd[k] for k in keys])[0]
+    assert torch.equal(m5, memory)
+    hits = eng.encode_cache_hits
+    m5b = model(*[dd[k] for k in keys])[0]
+    assert eng.encode_cache_hits == hits + 1 and torch.equal(m5b, memory)
+    dd["src_1H"][0, 0, 0] += 0.5
+    m6 = model(*[dd[k] for k in keys])[0]
+    assert eng.encode_cache_hits == hits + 1 and not torch.equal(m6, memory)
+    # the caller wrote into the returned memory -> the remembered outputs are stale -> miss
+    mem7, mask7, *_ = s["M"].run_model(model, data, cfg)
+    mem7.zero_()
+    hits = eng.encode_cache_hits
+    mem8 = model(*[data[k] for k in keys])[0]
+    assert eng.encode_cache_hits == hits and torch.equal(mem8, memory)
+    # another training_mode on the same data -> miss
+    cfg2 = cfg_for(case)
+    cfg2.training_mode = "1H_13C_HSQC_COSY_MF_MW"
+    model.config = cfg2
+    hits = eng.encode_cache_hits
+    mem9 = model(*[data[k] for k in keys])[0]
+    assert eng.encode_cache_hits == hits and mem9.shape[0] != 0
+    model.config = cfg
+
+
 # --------------------------------------------------------------------------- decoder
 @pytest.mark.parametrize("name", CASES)
 def test_teacher_forced_and_greedy_vs_reference_golden(name):
