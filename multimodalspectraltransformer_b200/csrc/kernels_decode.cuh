@@ -62,6 +62,24 @@ __device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// v[0..7] per lane -> every lane returns the sum over the 32 lanes of v[(lane >> 2) & 7]   (4 + 2 + 1 + 1 + 1 shuffles
+// instead of 8 x 5 for eight separate butterflies)
+__device__ __forceinline__ float reduce_scatter8(float (&v)[8], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 4; off >>= 1) {
+        const int half = off >> 2;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // out[r][n] = bias[n] + W[n,:] . xs[r,:]   for n in [0, n_out), all DA_R rows; W row-major [n_out][128]
 // and bias in SHARED memory.  Warps take groups of 16 outputs round-robin.
 __device__ __forceinline__ void gemv_rows(const float* W, const float* bias, int n_out,
@@ -426,13 +444,9 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         }
         DA_STAMP2(2);
         l = warp_sum(l);
-#pragma unroll
-        for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d]);
-        if (lane < DH) {
-            float v = 0.f;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
-            att[r][h * DH + lane] = v / l;
+        {
+            const float v = reduce_scatter8(acc, lane);       // lane holds dimension (lane >> 2) & 7
+            if (!(lane & 3)) att[r][h * DH + (lane >> 2)] = v / l;
         }
         DA_STAMP2(3);
     } else {
@@ -506,12 +520,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         const float corr = (m == MMT_NEG_INF) ? 0.f : expf(m - Mx);
         l = warp_sum(l * corr);
 #pragma unroll
-        for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d] * corr);
-        if (lane < DH) {
-            float v = 0.f;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) if (lane == d) v = acc[d];
-            att[r][h * DH + lane] = v / l;
+        for (int d = 0; d < DH; ++d) acc[d] *= corr;
+        {
+            const float v = reduce_scatter8(acc, lane);
+            if (!(lane & 3)) att[r][h * DH + (lane >> 2)] = v / l;
         }
         DA_STAMP2(7);
     }
