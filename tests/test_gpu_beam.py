@@ -164,3 +164,20 @@ def test_beam_search_argument_errors():
     cfg = s["M"].default_config(device="cuda")
     cfg.gen_len = 0
     assert s["M"].beam_search(s["model"], STOI, torch.zeros(582, 2, 128, device="cuda"), None, cfg, 3) == [[(1, [3], [])]] * 2
+
+
+def test_beam_search_waves_and_large_slot_counts():
+    """600 items x 16 beams = 9600 slots: two waves (8192 slots on the un-fused kernel family, 1408 on the fused one);
+    every probed item equals its own single-item search (the reference's batching)."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    model, _ = eos_heavy()
+    data = synthetic.make_spectra(600, seed=17)
+    got, memory, mask = run(model, data, 16, 5)
+    cfg = s["M"].default_config(device="cuda")
+    cfg.training_mode = MODE
+    cfg.gen_len = 5
+    assert len(got) == 600 and all(len(item) == 16 for item in got)
+    for i in (0, 255, 511, 512, 599):
+        one = s["M"].beam_search(model, STOI, memory[:, i:i + 1], mask[i:i + 1], cfg, 16)
+        compare([got[i]], one)
