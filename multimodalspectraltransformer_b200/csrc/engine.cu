@@ -1032,7 +1032,9 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 MMT_TRY(gemm(b.x, D, w.ca_in_w, w.ca_in_b, b.qc, D, D, 0, 1));
             }
             prof_pre(e, s);
-            if (bf16) decode_cross_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, nullptr, b.att16);
+            if (bf16 && a.n_cand >= 8 && e->use_tc_attention)   // candidates of a spectrum share K/V: tensor-core tiles of 16 candidates
+                decode_cross_attention_tc<<<dim3(H, Bmw), 256, dx_smem_bytes(a.S), s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, H, scale, nullptr, b.att16);
+            else if (bf16) decode_cross_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, nullptr, b.att16);
             else decode_cross_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const float*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_cross_attention", s));
             if (bf16) {

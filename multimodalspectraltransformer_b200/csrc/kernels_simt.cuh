@@ -878,6 +878,122 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
     }
 }
 
+// Tensor-core cross-attention for candidate waves (bf16 K/V): the n_cand sequences of a spectrum attend to the SAME
+// projected memory (run_batch_gen_val_MMT_v15_4.py:93-158 decodes 128 candidates per spectrum), so per (spectrum, head)
+// the scores are a real [n_cand x 8] . [8 x keys] product and the output a [n_cand x keys] . [keys x 8] one.  One CTA
+// per (head, spectrum) stages that head's K (row-major) and V (transposed) once; a warp owns 16 candidates: Q.K^T on
+// mma.sync m16n8k8, P.V on m16n8k16, online softmax in the log2 domain on the accumulator layout.  Q and P enter as
+// two-term bf16 splits (K and V are bf16 already), so the result equals the SIMT kernel's to fp32 round-off.
+__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], const uint32_t (&a)[2], uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+__host__ __device__ inline size_t dx_smem_bytes(int key_bound) {
+    const int nkp = at_keys_padded(key_bound);
+    return (size_t)nkp * 8 * 2 + (size_t)8 * (nkp + 8) * 2 + (size_t)nkp * 4;
+}
+__global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_in, const __nv_bfloat16* kv, int64_t rows_total,
+                                                                 const int* nk, const int* row_start, const float* kbias_c,
+                                                                 int n_cand, int H, float scale, float* out, __nv_bfloat16* out16) {
+    extern __shared__ __align__(16) unsigned char dx_smem[];
+    constexpr int DH = 8;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int h = blockIdx.x;
+    const int64_t b = blockIdx.y;
+    const int cnt = nk[b];
+    const int64_t r0 = row_start[b];
+    const int nkp_max = at_keys_padded((int)rows_total), nkp = at_keys_padded(cnt);
+    const int vstride = nkp_max + 8;
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(dx_smem);           // [nkp][8]
+    __nv_bfloat16* Vt = Ks + (size_t)nkp_max * DH;                           // [8][vstride]
+    float* bs = reinterpret_cast<float*>(Vt + (size_t)DH * vstride);          // [nkp] bias * log2(e)
+    const __nv_bfloat16* Kh = kv + (((int64_t)b * 2 + 0) * H + h) * rows_total * DH;
+    const __nv_bfloat16* Vh = kv + (((int64_t)b * 2 + 1) * H + h) * rows_total * DH;
+    for (int j = threadIdx.x; j < nkp; j += blockDim.x) {
+        uint4 k = make_uint4(0u, 0u, 0u, 0u), v = k;
+        float bias = MMT_NEG_INF;
+        if (j < cnt) {
+            k = *reinterpret_cast<const uint4*>(Kh + (int64_t)j * DH);
+            v = *reinterpret_cast<const uint4*>(Vh + (int64_t)j * DH);
+            bias = kbias_c[r0 + j] * LOG2E;
+        }
+        *reinterpret_cast<uint4*>(Ks + (size_t)j * DH) = k;
+        const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            Vt[(2 * c) * vstride + j] = __ushort_as_bfloat16((unsigned short)(vw[c] & 0xffffu));
+            Vt[(2 * c + 1) * vstride + j] = __ushort_as_bfloat16((unsigned short)(vw[c] >> 16));
+        }
+        bs[j] = bias;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const float qscale = scale * LOG2E;
+    for (int tile = warp; tile * 16 < n_cand; tile += nwarps) {
+        const int c_lo = tile * 16 + gq, c_hi = c_lo + 8;
+        const int64_t n_lo = b * n_cand + c_lo, n_hi = b * n_cand + c_hi;
+        uint32_t qh[2], ql[2];
+        {
+            float2 a = make_float2(0.f, 0.f), c = a;
+            if (c_lo < n_cand) a = *reinterpret_cast<const float2*>(q_in + n_lo * D + h * DH + 2 * tq);
+            if (c_hi < n_cand) c = *reinterpret_cast<const float2*>(q_in + n_hi * D + h * DH + 2 * tq);
+            split_pair(a.x * qscale, a.y * qscale, qh[0], ql[0]);
+            split_pair(c.x * qscale, c.y * qscale, qh[1], ql[1]);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float m_lo = MMT_NEG_INF, m_hi = MMT_NEG_INF, l_lo = 0.f, l_hi = 0.f;
+        for (int kb = 0; kb < nkp; kb += 16) {
+            float sc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float2 bb = *reinterpret_cast<const float2*>(bs + kb + nt * 8 + 2 * tq);
+                sc[nt][0] = bb.x; sc[nt][1] = bb.y; sc[nt][2] = bb.x; sc[nt][3] = bb.y;
+                const uint32_t kf = *reinterpret_cast<const uint32_t*>(Ks + (size_t)(kb + nt * 8 + gq) * DH + 2 * tq);
+                mma_bf16_1688(sc[nt], qh, kf);
+                mma_bf16_1688(sc[nt], ql, kf);
+            }
+            float bm_lo = fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1]));
+            float bm_hi = fmaxf(fmaxf(sc[0][2], sc[0][3]), fmaxf(sc[1][2], sc[1][3]));
+            bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+            bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+            const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
+            if (__any_sync(0xffffffffu, nm_lo != m_lo || nm_hi != m_hi)) {
+                const float corr_lo = ex2_approx(m_lo - nm_lo), corr_hi = ex2_approx(m_hi - nm_hi);
+                m_lo = nm_lo; m_hi = nm_hi;
+                l_lo *= corr_lo; l_hi *= corr_hi;
+                acc[0] *= corr_lo; acc[1] *= corr_lo; acc[2] *= corr_hi; acc[3] *= corr_hi;
+            }
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float e0 = ex2_approx(sc[nt][0] - m_lo), e1 = ex2_approx(sc[nt][1] - m_lo);
+                const float e2 = ex2_approx(sc[nt][2] - m_hi), e3 = ex2_approx(sc[nt][3] - m_hi);
+                l_lo += e0 + e1; l_hi += e2 + e3;
+                split_pair(e0, e1, ph[nt * 2], pl[nt * 2]);
+                split_pair(e2, e3, ph[nt * 2 + 1], pl[nt * 2 + 1]);
+            }
+            const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + (size_t)gq * vstride + kb + 2 * tq);
+            const uint32_t v0 = vr[0], v1 = vr[4];
+            mma_bf16_16816(acc, ph, v0, v1);
+            mma_bf16_16816(acc, pl, v0, v1);
+        }
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+        const int col = h * DH + 2 * tq;
+        if (c_lo < n_cand) {
+            const float o0 = acc[0] / l_lo, o1 = acc[1] / l_lo;
+            if (out) *reinterpret_cast<float2*>(out + n_lo * D + col) = make_float2(o0, o1);
+            if (out16) *reinterpret_cast<__nv_bfloat162*>(out16 + n_lo * D + col) = __floats2bfloat162_rn(o0, o1);
+        }
+        if (c_hi < n_cand) {
+            const float o0 = acc[2] / l_hi, o1 = acc[3] / l_hi;
+            if (out) *reinterpret_cast<float2*>(out + n_hi * D + col) = make_float2(o0, o1);
+            if (out16) *reinterpret_cast<__nv_bfloat162*>(out16 + n_hi * D + col) = __floats2bfloat162_rn(o0, o1);
+        }
+    }
+}
+
 // ===========================================================================
 // Fused vocab projection + softmax(logits / T) + greedy | multinomial pick
 // (validate_generate_MMT_v15_4.py:753-759, 868-872).  One warp per sequence.

@@ -170,3 +170,32 @@ def test_cross_encoder_tensor_core_attention_equals_simt(name, dense, monkeypatc
     b16 = eng_simt.encode(data, case["mode"], "bf16", False)
     assert (a16[0] - b16[0]).abs().max().item() <= 2e-2 * scale
     assert (a16[0] - b16[0]).abs().mean().item() <= 1e-3 * scale
+
+
+@pytest.mark.parametrize("n_cand,name", [(16, "full_b5"), (40, "mode_hsqc_b2"), (9, "maxpeaks_b2")])
+def test_candidate_wave_cross_attention_on_tensor_cores(n_cand, name, monkeypatch):
+    """decode_cross_attention_tc (candidates of a spectrum share K/V: mma.sync tiles of 16 candidates) against the SIMT
+    kernel it replaces on the un-fused decode path, bf16 mode: teacher-forced logits of random targets agree within the
+    mode's rounding noise and both stay within the tolerance of the fp32 mode; ragged candidate counts, bool and float masks."""
+    from multimodalspectraltransformer_b200.engine import Engine
+    from multimodalspectraltransformer_b200.generate import _mask_to_bias
+    s = setup()
+    case, data, z = load_case(name)
+    cfg = cfg_for(case, precision="bf16")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    monkeypatch.setenv("MMT_FUSED_DECODE_ROWS", "0")
+    eng_tc = Engine(s["model"].state_dict(), cfg, dev)
+    monkeypatch.setenv("MMT_NO_TC_ATTENTION", "1")
+    eng_simt = Engine(s["model"].state_dict(), cfg, dev)
+    memory, pad, key_bias, *_ = eng_simt.encode(data, case["mode"], "bf16", False)
+    B = memory.shape[1]
+    g = torch.Generator().manual_seed(n_cand)
+    trg = torch.randint(0, 43, (6, B * n_cand), generator=g)
+    trg[0] = 3
+    a = eng_tc.teacher_forced(memory, key_bias, trg, n_cand=n_cand, precision="bf16")
+    b = eng_simt.teacher_forced(memory, key_bias, trg, n_cand=n_cand, precision="bf16")
+    ref = eng_simt.teacher_forced(memory, key_bias, trg, n_cand=n_cand, precision="fp32")
+    scale = ref.abs().amax(dim=-1, keepdim=True)
+    assert ((a - b).abs() / scale).max().item() <= 4e-3
+    assert ((a - b).abs() / scale).mean().item() <= 4e-4
+    assert ((a - ref).abs() / scale).max().item() <= REL_TOL and ((b - ref).abs() / scale).max().item() <= REL_TOL
