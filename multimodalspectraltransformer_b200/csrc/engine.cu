@@ -1020,8 +1020,9 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
             else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
             prof_pre(e, s);
-            if (bf16) decode_self_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), b.block_table, pps, Nw, H, scale, step, nullptr, b.att16);
-            else decode_self_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
+            const unsigned sa_blocks = (unsigned)((Nw * (H / 4) + 7) / 8);     // a warp per (sequence, 4 heads)
+            if (bf16) decode_self_attention_g8<8, __nv_bfloat16><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), b.block_table, pps, Nw, H, scale, step, nullptr, b.att16);
+            else decode_self_attention_g8<8, float><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_self_attention", s));
             if (bf16) {
                 MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));

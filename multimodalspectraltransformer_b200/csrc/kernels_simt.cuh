@@ -816,6 +816,89 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, K
     }
 }
 
+// The same, eight lanes per (sequence, head): a warp serves four heads of a sequence, lane (hq, kl) owns the keys
+// j = kl (mod 8) of head hq.  At the positions where most of a 128-token decode lives (t < 64) a warp-per-head mapping
+// leaves most lanes without a key and still pays a five-stage reduction of ten values; here the reduction is three
+// stages over eight lanes (8-value reduce-scatter: lane kl ends up with output dimension kl, so a warp stores 32
+// consecutive outputs) and the wave needs a quarter of the warps.  Online softmax, two keys per lane in flight.
+template <int DH, typename KVT>
+__global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv, KVT* kv_pool, const int* block_table,
+                                                                int pages_per_seq, int64_t N, int H, float scale,
+                                                                const int* step, float* out, __nv_bfloat16* out16) {
+    static_assert(DH == 8, "8-element key rows");
+    typedef KvRow<KVT> KV;
+    const int t = *step;
+    const int HG = H / 4;                                  // head groups per sequence
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= N * HG) return;
+    const int lane = threadIdx.x & 31, hq = lane >> 3, kl = lane & 7;
+    const int64_t n = w / HG;
+    const int h = (int)(w % HG) * 4 + hq;
+    constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
+    const int* bt = block_table + n * pages_per_seq;
+    const float* row = qkv + n * (3 * D) + h * DH;
+    {   // append K,V of position t: lane (hq, kl) writes element kl of its head's K and V rows
+        KVT* page = kv_pool + (int64_t)bt[t / PAGE_TOKENS] * PAGE_ELEMS;
+        KV::st(page + ((0 * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + kl, row[D + kl]);
+        KV::st(page + ((1 * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + kl, row[2 * D + kl]);
+    }
+    __syncwarp();
+    float q[DH], acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) { q[d] = row[d] * scale; acc[d] = 0.f; }
+    float m = MMT_NEG_INF, l = 0.f;
+    for (int j0 = kl; j0 <= t; j0 += 16) {
+        const int j1 = j0 + 8;
+        const bool has1 = j1 <= t;
+        const int j1c = has1 ? j1 : j0;
+        const KVT* p0 = kv_pool + (int64_t)bt[j0 / PAGE_TOKENS] * PAGE_ELEMS + (h * PAGE_TOKENS + (j0 % PAGE_TOKENS)) * DH;
+        const KVT* p1 = kv_pool + (int64_t)bt[j1c / PAGE_TOKENS] * PAGE_ELEMS + (h * PAGE_TOKENS + (j1c % PAGE_TOKENS)) * DH;
+        const typename KV::Raw rk0 = KV::ld(p0), rk1 = KV::ld(p1);
+        const typename KV::Raw rv0 = KV::ld(p0 + H * PAGE_TOKENS * DH), rv1 = KV::ld(p1 + H * PAGE_TOKENS * DH);
+        float k0[DH], k1[DH];
+        KV::unpack(rk0, k0); KV::unpack(rk1, k1);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { s0 = fmaf(q[d], k0[d], s0); s1 = fmaf(q[d], k1[d], s1); }
+        if (!has1) s1 = MMT_NEG_INF;
+        const float mn = fmaxf(m, fmaxf(s0, s1));
+        if (mn > m) {
+            const float corr = expf(m - mn);
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] *= corr;
+            m = mn;
+        }
+        const float e0 = expf(s0 - m), e1 = has1 ? expf(s1 - m) : 0.f;
+        l += e0 + e1;
+        float v0[DH], v1[DH];
+        KV::unpack(rv0, v0); KV::unpack(rv1, v1);
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[d] = fmaf(e1, v1[d], fmaf(e0, v0[d], acc[d]));
+    }
+    // merge the eight per-lane partial softmaxes of a head (lanes without a key carry m = -inf, l = 0)
+    float Mx = m;
+    Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, 1)); Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, 2)); Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, 4));
+    const float corr = (m == MMT_NEG_INF) ? 0.f : expf(m - Mx);
+    l *= corr;
+    l += __shfl_xor_sync(0xffffffffu, l, 1); l += __shfl_xor_sync(0xffffffffu, l, 2); l += __shfl_xor_sync(0xffffffffu, l, 4);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int off = 4; off >= 1; off >>= 1) {          // 8-value reduce-scatter over the 8 lanes: lane kl keeps dimension kl
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? acc[i] : acc[i + off];
+            const float keep = up ? acc[i + off] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    const float o = acc[0] / l;
+    if (out) out[n * D + h * DH + kl] = o;
+    if (out16) out16[n * D + h * DH + kl] = __float2bfloat16_rn(o);
+}
+
 // Cross-attention of the new position over the (compacted) projected memory;
 // one warp per (sequence, head).  K/V layout: [spectrum][K|V][H][rows_total = rows per spectrum][DH] of KVT.
 template <int DH, typename KVT>
