@@ -357,6 +357,14 @@ static int launch_encoder_attention(mmt_engine* e, EncGroupRun* gr, int ng, int 
         attn_encoder_tc<<<grid, warps * 32, smem_tc, s>>>(p);
         return check_launch(e, "attn_encoder_tc", s);
     }
+    if (dh == 8 && e->use_tc_attention && (bf16_out || e->tc_attention_fp32)) {   // modality encoders: same scheme on m16n8k8 tiles
+        const size_t smem_tc = at8_smem_bytes(key_bound);
+        const int warps = std::min(4, std::max(1, (row_bound + 15) / 16));
+        MMT_CUDA(cudaFuncSetAttribute(attn_encoder_tc8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        prof_pre(e, s);
+        attn_encoder_tc8<<<grid, warps * 32, smem_tc, s>>>(p);
+        return check_launch(e, "attn_encoder_tc8", s);
+    }
     const size_t smem = (size_t)key_bound * (2 * dh + 1) * sizeof(float);
     const int threads = std::min(256, std::max(64, (row_bound + 31) / 32 * 32));
     if (dh == 8) {

@@ -666,6 +666,129 @@ __global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant_
     }
 }
 
+// The 8-wide heads of the five modality encoders, same scheme: Q.K^T on m16n8k8, P.V on m16n8k16, every operand a
+// two-term bf16 split (three MMAs per product).  K rows are 16 bytes (eight rows = one conflict-free 128-byte line),
+// V is staged transposed so that both B fragments are single 32-bit loads.
+__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], const uint32_t (&a)[2], uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
+}
+__host__ __device__ inline size_t at8_smem_bytes(int key_bound) {
+    const int nkp = at_keys_padded(key_bound);
+    return (size_t)2 * nkp * 8 * 2 + (size_t)2 * 8 * (nkp + 8) * 2 + (size_t)nkp * 4;
+}
+__global__ void __launch_bounds__(128) attn_encoder_tc8(const __grid_constant__ AttnParams p) {
+    extern __shared__ __align__(16) unsigned char at_smem[];
+    constexpr int DH = 8;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const AttnGroup& g = p.g[blockIdx.z];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int S = g.cnt ? g.cnt[b] : g.S;
+    const int kstride = g.cnt ? g.kstride : g.S;
+    const int64_t row0 = g.row_start ? (int64_t)g.row_start[b] : (int64_t)b * g.S;
+    const int nk = g.nk[b];
+    const int nkp_max = at_keys_padded(g.smax), nkp = at_keys_padded(nk);
+    const int vstride = nkp_max + 8;
+    __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(at_smem);      // [nkp][8]
+    __nv_bfloat16* Kl = Kh + (size_t)nkp_max * DH;
+    __nv_bfloat16* Vh = Kl + (size_t)nkp_max * DH;                      // [8][vstride] (transposed)
+    __nv_bfloat16* Vl = Vh + (size_t)DH * vstride;
+    float* bs = reinterpret_cast<float*>(Vl + (size_t)DH * vstride);     // [nkp] key bias * log2(e)
+    const float* base = g.qkv + row0 * (3 * D);
+    for (int i = threadIdx.x; i < nkp * 2; i += blockDim.x) {           // item = (key, half row of four dims)
+        const int jj = i >> 1, q4 = i & 1;
+        float4 k = make_float4(0.f, 0.f, 0.f, 0.f), v = k;
+        if (jj < nk) {
+            const int j = g.kidx[(int64_t)b * kstride + jj];
+            const float* row = base + (int64_t)j * (3 * D) + h * DH + q4 * 4;
+            k = *reinterpret_cast<const float4*>(row + D);
+            v = *reinterpret_cast<const float4*>(row + 2 * D);
+            if (q4 == 0) bs[jj] = g.kbias ? g.kbias[(int64_t)b * g.S + j] * LOG2E : 0.f;
+        } else if (q4 == 0) bs[jj] = MMT_NEG_INF;
+        uint32_t h0, l0, h1, l1;
+        split_pair(k.x, k.y, h0, l0); split_pair(k.z, k.w, h1, l1);
+        *reinterpret_cast<uint2*>(Kh + jj * DH + q4 * 4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(Kl + jj * DH + q4 * 4) = make_uint2(l0, l1);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const __nv_bfloat16 vh = __float2bfloat16_rn(vv[c]);
+            Vh[(q4 * 4 + c) * vstride + jj] = vh;
+            Vl[(q4 * 4 + c) * vstride + jj] = __float2bfloat16_rn(vv[c] - __bfloat162float(vh));
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const float qscale = p.scale * LOG2E;
+    for (int tile = warp; tile * 16 < S; tile += nwarps) {
+        const int r_lo = tile * 16 + gq, r_hi = r_lo + 8;
+        uint32_t qh[2], ql[2];
+        {
+            const int col = h * DH + 2 * tq;
+            float2 a = make_float2(0.f, 0.f), c = a;
+            if (r_lo < S) a = *reinterpret_cast<const float2*>(base + (int64_t)r_lo * (3 * D) + col);
+            if (r_hi < S) c = *reinterpret_cast<const float2*>(base + (int64_t)r_hi * (3 * D) + col);
+            split_pair(a.x * qscale, a.y * qscale, qh[0], ql[0]);
+            split_pair(c.x * qscale, c.y * qscale, qh[1], ql[1]);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float m_lo = MMT_NEG_INF, m_hi = MMT_NEG_INF, l_lo = 0.f, l_hi = 0.f;
+        for (int kb = 0; kb < nkp; kb += 16) {
+            float sc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float2 bb = *reinterpret_cast<const float2*>(bs + kb + nt * 8 + 2 * tq);
+                sc[nt][0] = bb.x; sc[nt][1] = bb.y; sc[nt][2] = bb.x; sc[nt][3] = bb.y;
+                const uint32_t kh = *reinterpret_cast<const uint32_t*>(Kh + (size_t)(kb + nt * 8 + gq) * DH + 2 * tq);
+                const uint32_t kl = *reinterpret_cast<const uint32_t*>(Kl + (size_t)(kb + nt * 8 + gq) * DH + 2 * tq);
+                mma_bf16_1688(sc[nt], qh, kh);
+                mma_bf16_1688(sc[nt], qh, kl);
+                mma_bf16_1688(sc[nt], ql, kh);
+            }
+            float bm_lo = fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1]));
+            float bm_hi = fmaxf(fmaxf(sc[0][2], sc[0][3]), fmaxf(sc[1][2], sc[1][3]));
+            bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
+            bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
+            const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
+            if (__any_sync(0xffffffffu, nm_lo != m_lo || nm_hi != m_hi)) {
+                const float corr_lo = ex2_approx(m_lo - nm_lo), corr_hi = ex2_approx(m_hi - nm_hi);
+                m_lo = nm_lo; m_hi = nm_hi;
+                l_lo *= corr_lo; l_hi *= corr_hi;
+                acc[0] *= corr_lo; acc[1] *= corr_lo; acc[2] *= corr_hi; acc[3] *= corr_hi;
+            }
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float e0 = ex2_approx(sc[nt][0] - m_lo), e1 = ex2_approx(sc[nt][1] - m_lo);
+                const float e2 = ex2_approx(sc[nt][2] - m_hi), e3 = ex2_approx(sc[nt][3] - m_hi);
+                l_lo += e0 + e1; l_hi += e2 + e3;
+                split_pair(e0, e1, ph[nt * 2], pl[nt * 2]);
+                split_pair(e2, e3, ph[nt * 2 + 1], pl[nt * 2 + 1]);
+            }
+            const uint32_t* vh = reinterpret_cast<const uint32_t*>(Vh + (size_t)gq * vstride + kb + 2 * tq);
+            const uint32_t* vl = reinterpret_cast<const uint32_t*>(Vl + (size_t)gq * vstride + kb + 2 * tq);
+            const uint32_t vh0 = vh[0], vh1 = vh[4], vl0 = vl[0], vl1 = vl[4];
+            mma_bf16_16816(acc, ph, vh0, vh1);
+            mma_bf16_16816(acc, ph, vl0, vl1);
+            mma_bf16_16816(acc, pl, vh0, vh1);
+        }
+        l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+        l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+        const int col = h * DH + 2 * tq;
+        if (r_lo < S) {
+            const float o0 = acc[0] / l_lo, o1 = acc[1] / l_lo;
+            if (g.out) *reinterpret_cast<float2*>(g.out + (row0 + r_lo) * D + col) = make_float2(o0, o1);
+            if (g.out16) *reinterpret_cast<__nv_bfloat162*>(g.out16 + (row0 + r_lo) * D + col) = __floats2bfloat162_rn(o0, o1);
+        }
+        if (r_hi < S) {
+            const float o0 = acc[2] / l_hi, o1 = acc[3] / l_hi;
+            if (g.out) *reinterpret_cast<float2*>(g.out + (row0 + r_hi) * D + col) = make_float2(o0, o1);
+            if (g.out16) *reinterpret_cast<__nv_bfloat162*>(g.out16 + (row0 + r_hi) * D + col) = __floats2bfloat162_rn(o0, o1);
+        }
+    }
+}
+
 // mean over the S rows of a sequence-first memory (S,B,D) -> (B,D)   (models_MMT_v15_4.py:946)
 __global__ void __launch_bounds__(128) mean_over_sequence(const float* mem, int S, int B, float* avg) {
     const int b = blockIdx.x, d = threadIdx.x;
@@ -967,10 +1090,6 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
 // per (head, spectrum) stages that head's K (row-major) and V (transposed) once; a warp owns 16 candidates: Q.K^T on
 // mma.sync m16n8k8, P.V on m16n8k16, online softmax in the log2 domain on the accumulator layout.  Q and P enter as
 // two-term bf16 splits (K and V are bf16 already), so the result equals the SIMT kernel's to fp32 round-off.
-__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], const uint32_t (&a)[2], uint32_t b0) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(b0));
-}
 __host__ __device__ inline size_t dx_smem_bytes(int key_bound) {
     const int nkp = at_keys_padded(key_bound);
     return (size_t)nkp * 8 * 2 + (size_t)8 * (nkp + 8) * 2 + (size_t)nkp * 4;
