@@ -970,16 +970,27 @@ __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv
 #pragma unroll
     for (int d = 0; d < DH; ++d) { q[d] = row[d] * scale; acc[d] = 0.f; }
     float m = MMT_NEG_INF, l = 0.f;
+    // software pipeline: the K/V rows of the next two keys are in flight while the current two are folded in
+    auto row_ptr = [&](int j) { return kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_ELEMS + (h * PAGE_TOKENS + (j % PAGE_TOKENS)) * DH; };
+    typename KV::Raw rk0, rk1, rv0, rv1;
+    if (kl <= t) {
+        const KVT* p0 = row_ptr(kl);
+        const KVT* p1 = row_ptr(kl + 8 <= t ? kl + 8 : kl);
+        rk0 = KV::ld(p0); rk1 = KV::ld(p1);
+        rv0 = KV::ld(p0 + H * PAGE_TOKENS * DH); rv1 = KV::ld(p1 + H * PAGE_TOKENS * DH);
+    }
     for (int j0 = kl; j0 <= t; j0 += 16) {
-        const int j1 = j0 + 8;
-        const bool has1 = j1 <= t;
-        const int j1c = has1 ? j1 : j0;
-        const KVT* p0 = kv_pool + (int64_t)bt[j0 / PAGE_TOKENS] * PAGE_ELEMS + (h * PAGE_TOKENS + (j0 % PAGE_TOKENS)) * DH;
-        const KVT* p1 = kv_pool + (int64_t)bt[j1c / PAGE_TOKENS] * PAGE_ELEMS + (h * PAGE_TOKENS + (j1c % PAGE_TOKENS)) * DH;
-        const typename KV::Raw rk0 = KV::ld(p0), rk1 = KV::ld(p1);
-        const typename KV::Raw rv0 = KV::ld(p0 + H * PAGE_TOKENS * DH), rv1 = KV::ld(p1 + H * PAGE_TOKENS * DH);
+        const bool has1 = j0 + 8 <= t;
+        const typename KV::Raw ck0 = rk0, ck1 = rk1, cv0 = rv0, cv1 = rv1;
+        const int jn = j0 + 16;
+        if (jn <= t) {
+            const KVT* p0 = row_ptr(jn);
+            const KVT* p1 = row_ptr(jn + 8 <= t ? jn + 8 : jn);
+            rk0 = KV::ld(p0); rk1 = KV::ld(p1);
+            rv0 = KV::ld(p0 + H * PAGE_TOKENS * DH); rv1 = KV::ld(p1 + H * PAGE_TOKENS * DH);
+        }
         float k0[DH], k1[DH];
-        KV::unpack(rk0, k0); KV::unpack(rk1, k1);
+        KV::unpack(ck0, k0); KV::unpack(ck1, k1);
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int d = 0; d < DH; ++d) { s0 = fmaf(q[d], k0[d], s0); s1 = fmaf(q[d], k1[d], s1); }
@@ -995,7 +1006,7 @@ __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv
         const float e0 = expf(s0 - m), e1 = has1 ? expf(s1 - m) : 0.f;
         l += e0 + e1;
         float v0[DH], v1[DH];
-        KV::unpack(rv0, v0); KV::unpack(rv1, v1);
+        KV::unpack(cv0, v0); KV::unpack(cv1, v1);
 #pragma unroll
         for (int d = 0; d < DH; ++d) acc[d] = fmaf(e1, v1[d], fmaf(e0, v0[d], acc[d]));
     }
