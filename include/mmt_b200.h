@@ -177,6 +177,16 @@ int32_t mmt_decode(mmt_engine* e, const mmt_decode_args* a, int64_t* d_tokens, f
 int32_t mmt_teacher_forced(mmt_engine* e, const mmt_decode_args* a, const int64_t* d_trg, int32_t T,
                            float* d_logits, void* stream);
 
+/* Replaces the teacher-forced scorers predict_prop_correct_max_sequence(_2) (validate_generate_MMT_v15_4.py:309-509)
+ * and mrtf.predict_prop_correct_max_sequence_3 (mmt_result_test_functions_15_4.py:340-400): T positions with the given
+ * input tokens d_trg_in (T,N) (row 0 = <SOS>), one KV-cached step per position instead of a full-prefix decoder run
+ * per position.  At every position: d_pick / d_pick_prob (T,N) = the greedy (a->sampling == GREEDY: argmax, first max)
+ * or multinomial (Philox contract of mmt_decode) pick under softmax(logits / a->temperature) and its probability --
+ * never fed back; d_target_prob (T,N) = probability of d_target (T,N) (both NULL to skip).  a->stop_on_all_pad is
+ * ignored. */
+int32_t mmt_teacher_forced_scores(mmt_engine* e, const mmt_decode_args* a, const int64_t* d_trg_in, const int64_t* d_target,
+                                  int32_t T, int64_t* d_pick, float* d_pick_prob, float* d_target_prob, void* stream);
+
 /* Replaces vgmmt.beam_search / beam_search_step (validate_generate_MMT_v15_4.py:995-1086), batched: the
  * beam_size beams of each of the a->Bm memory columns are slots of one KV-cached decode wave (a->n_cand, max_len,
  * temperature and sampling are ignored: the reference ranks with softmax(logits) without temperature, :1038).

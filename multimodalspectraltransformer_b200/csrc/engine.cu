@@ -866,8 +866,9 @@ __global__ void init_block_table(int* bt, int64_t n_pages) {
 
 struct DecodeRun {
     const mmt_decode_args* a;
-    int mode;                 // 0 greedy, 1 multinomial, 2 forced
-    const int64_t* trg;       // forced tokens (T, N_total)
+    int mode;                 // pick: 0 greedy, 1 multinomial, 2 none (logits only)
+    const int64_t* trg;       // forced input tokens (T, N_total): teacher forcing; nullptr = feed the picks back
+    const int64_t* target = nullptr; float* target_prob = nullptr;   // optional (T, N_total): probability of a given token at every position
     int T;                    // steps to run
     int64_t* tokens; float* probs; float* logits;   // outputs, leading dimension N_total
     int64_t ldn = -1;         // >= 0 overrides the leading dimension (0: single-row token / logit buffers, beam search)
@@ -981,7 +982,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             DecAttnParams q;
             memset(&q, 0, sizeof(q));
             if (l == 0) {
-                if (r.mode == 2) { q.tokens = r.trg + n0; q.tok_shift = 0; }
+                if (r.trg) { q.tokens = r.trg + n0; q.tok_shift = 0; }
                 else { q.tokens = r.tokens + n0; q.tok_shift = 1; }
                 q.sos = 3; q.ldn = ldn; q.E_tok = e->W("embed_trg.weight"); q.E_pos = e->W("pe_trg.weight"); q.vocab = d.vocab;
             } else {
@@ -1015,7 +1016,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         }
     } else {
         prof_pre(e, s);
-        if (r.mode == 2) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+        if (r.trg) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
         else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
         MMT_TRY(check_launch(e, "decode_embed", s));
 
@@ -1082,6 +1083,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     sp.seq_index_base = a.seq_index_base + n0;
     sp.tokens = r.tokens ? r.tokens + n0 : nullptr; sp.probs = r.probs ? r.probs + n0 : nullptr;
     sp.logits = r.logits ? r.logits + n0 * d.vocab : nullptr;
+    sp.target = r.target ? r.target + n0 : nullptr; sp.target_prob = r.target_prob ? r.target_prob + n0 : nullptr;
     sp.ctl.step = b.ctl; sp.ctl.done_ctas = b.ctl + 1; sp.ctl.nonpad = (r.mode == 0) ? b.ctl + 8 : nullptr;
     sp.advance = 1;
     if (fused) {   // norm3 of the last layer over the FFN2 partials
@@ -1127,7 +1129,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     // Single-wave sampling runs write ids / probabilities into engine-owned staging buffers (copied to the caller's
     // tensors at the end): nothing a captured decode-step graph touches then depends on the caller's allocations, so the
     // instantiated graph is reused across calls (capture + instantiation of ~400 nodes costs ~1.2 ms with the GPU idle).
-    const bool staged = e->use_graph && e->use_graph_cache && !e->profiling && n_waves == 1 && r.mode != 2;
+    const bool staged = e->use_graph && e->use_graph_cache && !e->profiling && n_waves == 1 && r.mode != 2 && !r.trg;   // forced inputs are the caller's tensor: nothing to cache across calls
     Arena ar;
     DecBuffers lb[MAX_LANES];
     int64_t* st_tokens = nullptr; float* st_probs = nullptr;
@@ -1619,6 +1621,21 @@ int32_t mmt_spectra_equal(mmt_engine* e, const mmt_spectra* a, const mmt_spectra
     MMT_CUDA(cudaStreamSynchronize(s));
     *h_equal = e->h_pinned[0] == 0;
     return 0;
+}
+
+int32_t mmt_teacher_forced_scores(mmt_engine* e, const mmt_decode_args* a, const int64_t* d_trg_in, const int64_t* d_target, int32_t T,
+                                  int64_t* d_pick, float* d_pick_prob, float* d_target_prob, void* stream) {
+    if (!e || !a || !d_trg_in || !d_pick) MMT_FAIL("null argument");
+    if (T < 1) MMT_FAIL("T must be >= 1");
+    if (a->sampling != MMT_SAMPLE_GREEDY && a->sampling != MMT_SAMPLE_MULTINOMIAL) MMT_FAIL("bad sampling mode");
+    if ((d_target == nullptr) != (d_target_prob == nullptr)) MMT_FAIL("d_target and d_target_prob go together");
+    MMT_CUDA(cudaSetDevice(e->device));
+    mmt_decode_args a2 = *a;
+    a2.stop_on_all_pad = 0;
+    DecodeRun r;
+    r.a = &a2; r.mode = a->sampling; r.trg = d_trg_in; r.T = T; r.tokens = d_pick; r.probs = d_pick_prob; r.logits = nullptr;
+    r.target = d_target; r.target_prob = d_target_prob;
+    return run_decode(e, r, nullptr, (cudaStream_t)stream);
 }
 
 uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threads_per_sm) {

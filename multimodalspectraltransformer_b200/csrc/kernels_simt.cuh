@@ -1228,6 +1228,8 @@ struct SampleParams {
     int64_t* tokens;         // [max_len][N] or nullptr
     float* probs;            // [max_len][N] or nullptr
     float* logits;           // [T][N][V] (forced / unit test) or nullptr
+    const int64_t* target;   // optional [max_len][N]: a token per sequence and position ...
+    float* target_prob;      // ... whose softmax(logits / T) probability is written here (teacher-forced scorers)
     StepCtl ctl;             // ctl.step may be nullptr (stand-alone use, t = 0)
     int advance;             // 1: the last CTA increments *ctl.step
     // optional prologue (fused decoder path): x <- LN(x + pbias + sum_s part[s]) -- the last layer's FFN2 + norm3
@@ -1295,6 +1297,11 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
             float e1 = ok1 ? expf(z1 - mx) : 0.f;
             float sum = warp_sum(e0 + e1);
             float p0 = e0 / sum, p1 = e1 / sum;
+            if (p.target) {       // probability of the given token (validate_generate_MMT_v15_4.py:372-374)
+                const int64_t tg = p.target[(int64_t)t * p.ldn + n];
+                const float a = __shfl_sync(0xffffffffu, p0, (int)(tg & 31)), b = __shfl_sync(0xffffffffu, p1, (int)(tg & 31));
+                if (lane == 0) p.target_prob[(int64_t)t * p.ldn + n] = (tg < 0 || tg >= p.V) ? 0.f : (tg < 32 ? a : b);
+            }
             float r0 = p0, r1 = p1;
             if (p.mode == 1) {
                 RngGeom g = p.rng;

@@ -223,6 +223,30 @@ class Engine:
             t.record_stream(torch.cuda.current_stream(self.dev_index))
         return logits
 
+    def teacher_forced_scores(self, memory, key_bias, trg_in, target=None, *, n_cand=1, temperature=1.0, sampling="greedy",
+                              precision="fp32", seed=0, offset=0):
+        """trg_in (T,N) forced inputs -> (pick (T,N) i64, pick_prob (T,N) f32, target_prob (T,N) f32 | None)."""
+        trg_in = trg_in.to(self.device, torch.int64).contiguous()
+        T, N = trg_in.shape
+        smp = _lib.SAMPLE_GREEDY if sampling == "greedy" else _lib.SAMPLE_MULTINOMIAL
+        a, keep = self._decode_args(memory, key_bias, n_cand, max(T, 1), temperature, smp, False, precision, seed, offset)
+        if a.Bm * n_cand != N:
+            raise ValueError("target batch does not match memory batch")
+        pick = torch.empty(T, N, device=self.device, dtype=torch.int64)
+        pick_prob = torch.empty(T, N, device=self.device, dtype=torch.float32)
+        tgt = tprob = None
+        if target is not None:
+            tgt = target.to(self.device, torch.int64).contiguous()
+            if tuple(tgt.shape) != (T, N):
+                raise ValueError("target must have the shape of trg_in")
+            tprob = torch.empty(T, N, device=self.device, dtype=torch.float32)
+        _lib.check(self.L.mmt_teacher_forced_scores(self.h, C.byref(a), trg_in.data_ptr(), tgt.data_ptr() if tgt is not None else None, T,
+                                                    pick.data_ptr(), pick_prob.data_ptr(), tprob.data_ptr() if tprob is not None else None,
+                                                    self._stream()))
+        for t in keep + (trg_in,) + ((tgt,) if tgt is not None else ()):
+            t.record_stream(torch.cuda.current_stream(self.dev_index))
+        return pick, pick_prob, tprob
+
     def beam_search(self, memory, key_bias, *, beam_size, gen_len, eos=2, precision="fp32"):
         """-> (seq (Bm,K,gen_len+1) i64, len (Bm,K) i32, score (Bm,K) f64, probs (Bm,K,gen_len) f32, steps)."""
         a, keep = self._decode_args(memory, key_bias, beam_size, gen_len, 1.0, 0, False, precision)

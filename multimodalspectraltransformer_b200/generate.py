@@ -9,6 +9,8 @@ running on the B200 engine.
     greedy_sequence_2            mmt_result_test_functions_15_4.py:984-1032
     multinomial_sequence_multi_2 mmt_result_test_functions_15_4.py:791-829
     beam_search                  validate_generate_MMT_v15_4.py:995-1086
+    predict_prop_correct_max_sequence(_2)   validate_generate_MMT_v15_4.py:309-509
+    predict_prop_correct_max_sequence_3     mmt_result_test_functions_15_4.py:340-400
 
 ``model`` may be this package's ``MultimodalTransformer`` or the reference's own
 instance: only its ``state_dict()`` is read.  Runtime knobs (``device``,
@@ -173,3 +175,48 @@ def beam_search(model, stoi, memory, src_padding_mask, config, beam_size):
                                                precision=_engine.default_precision(config))
     seq, ln, score, probs = seq.cpu().tolist(), ln.cpu().tolist(), score.cpu().tolist(), probs.cpu().tolist()
     return [[(score[i][k], seq[i][k][:ln[i][k]], probs[i][k][:ln[i][k] - 1]) for k in range(len(seq[i]))] for i in range(N)]
+
+
+# ------------------------------------------------------------- teacher-forced scorers
+def _scorer_inputs(stoi, trg_enc_SMI, device):
+    """real_trg = trg_enc_SMI^T[1:] (validate_generate_MMT_v15_4.py:336-338); the decoder sees [<SOS>, real_trg[:-1]]."""
+    sos = _check_sos(stoi)
+    real_trg = trg_enc_SMI.to(device).transpose(0, 1)[1:, :].contiguous()
+    trg_in = torch.cat([torch.full((1, real_trg.shape[1]), sos, dtype=torch.long, device=device), real_trg[:-1]], dim=0)
+    return real_trg, trg_in
+
+
+def predict_prop_correct_max_sequence_2(model, stoi, memory, src_padding_mask, trg_enc_SMI, config):
+    """-> (trg_tensor (N,L) i64, corr_token_prob (L,N), trg_tensor_max (N,L) i64, max_token_prob (L,N)): at every position
+    of the teacher-forced target the probability of the correct token, the arg-max token and its probability under
+    softmax(logits / config.temperature).  One KV-cached pass; the reference re-runs the decoder on every prefix.  Like
+    the reference's .squeeze(), the probability tensors lose their N axis when N == 1."""
+    model.eval()
+    eng = _engine.engine_for(model, config)
+    real_trg, trg_in = _scorer_inputs(stoi, trg_enc_SMI, eng.device)
+    bias = _mask_to_bias(src_padding_mask.to(eng.device))
+    pick, pick_prob, corr = eng.teacher_forced_scores(memory, bias, trg_in, real_trg, temperature=float(config.temperature),
+                                                      precision=_engine.default_precision(config))
+    if real_trg.shape[1] == 1:
+        corr, pick_prob = corr.squeeze(1), pick_prob.squeeze(1)
+    return real_trg.transpose(0, 1), corr, pick.transpose(0, 1), pick_prob
+
+
+predict_prop_correct_max_sequence_3 = predict_prop_correct_max_sequence_2      # identical bodies in the reference
+
+
+def predict_prop_correct_max_sequence(model, stoi, memory, src_padding_mask, trg_enc_SMI, gen_num, config):
+    """The five-output variant (validate_generate_MMT_v15_4.py:309-432): additionally the probability of one multinomial
+    draw per position under the teacher-forced context, flattened to (L*N,) like the reference's .view(1,-1).squeeze(0)
+    (gen_num is overwritten with 1 there, :386).  Draws follow torch.multinomial's CUDA Philox stream: L calls."""
+    if memory.size(1) != 1:    # the reference only runs for N == 1: torch.tensor(list of (N,) tensors) raises at :415
+        raise ValueError("only one element tensors can be converted to Python scalars")
+    out = predict_prop_correct_max_sequence_2(model, stoi, memory, src_padding_mask, trg_enc_SMI, config)
+    eng = _engine.engine_for(model, config)
+    real_trg, trg_in = _scorer_inputs(stoi, trg_enc_SMI, eng.device)
+    bias = _mask_to_bias(src_padding_mask.to(eng.device))
+    gen, seed, offset = _philox_state(eng.dev_index)
+    _, mprob, _ = eng.teacher_forced_scores(memory, bias, trg_in, None, temperature=float(config.temperature), sampling="multinomial",
+                                            precision=_engine.default_precision(config), seed=seed, offset=offset)
+    gen.set_offset(offset + eng.philox_increment(real_trg.shape[1]) * real_trg.shape[0])
+    return out + (mprob.reshape(-1),)

@@ -307,6 +307,25 @@ def multinomial_sequence_multi(P, memory, mask, config, generator=None, max_len=
 # --------------------------------------------------------------------------
 # sampling RNG restatement -- numpy, bit-exact integers
 # --------------------------------------------------------------------------
+def predict_prop_correct_max_sequence_2(P, memory, mask, trg_enc_SMI, config, sos=3):
+    """validate_generate_MMT_v15_4.py:434-509 (= mmt_result_test_functions_15_4.py:340-400), with the reference's
+    full-prefix decoder run per position.  -> (trg (N,L), corr_prob (L,N), trg_max (N,L), max_prob (L,N))."""
+    N = memory.size(1)
+    real_trg = trg_enc_SMI.transpose(0, 1)[1:, :]
+    trg = torch.full((1, N), sos, dtype=torch.long)
+    trg_max = torch.full((1, N), sos, dtype=torch.long)
+    corr, mx = [], []
+    for idx in range(real_trg.shape[0]):
+        logits = teacher_forced_logits(P, memory, mask, trg, config)
+        probs = torch.softmax(logits / config.temperature, dim=2)
+        nxt = torch.argmax(probs[-1], dim=1)
+        mx.append(probs[-1].gather(1, nxt.unsqueeze(-1)).squeeze())
+        trg_max = torch.cat((trg_max, nxt.unsqueeze(0)), dim=0)
+        corr.append(probs[-1].gather(1, real_trg[idx].unsqueeze(-1)).squeeze())
+        trg = torch.cat((trg, real_trg[idx].unsqueeze(0)), dim=0)
+    return trg.transpose(0, 1)[:, 1:], torch.stack(corr), trg_max.transpose(0, 1)[:, 1:], torch.stack(mx)
+
+
 def beam_search(P, memory, mask, config, beam_size, gen_len, sos=3, eos=2):
     """validate_generate_MMT_v15_4.py:995-1086 (beam_search_step + beam_search), per item, full-prefix decoder runs.
     Returns beams[item] = [(score, sequence, prob_sequence), ...] sorted by score, like the reference.

@@ -528,3 +528,51 @@ def test_multinomial_cached_graph_follows_the_generator():
     c, _, _ = s["eng"].decode(memory, kb, seed=5, offset=4 * 24, **kw)
     d, _, _ = s["eng"].decode(memory, kb, seed=6, offset=0, **kw)
     assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+
+
+def test_teacher_forced_scorers_vs_reference_golden():
+    """predict_prop_correct_max_sequence(_2,_3): one KV-cached pass == the reference's prefix-by-prefix loop."""
+    import os
+    from golden_util import GOLDEN
+    from multimodalspectraltransformer_b200 import synthetic
+    s = setup()
+    z = np.load(os.path.join(GOLDEN, "scorer_b3.npz"))
+    for tag in ("a", "b"):
+        cfg = cfg_for(temperature=float(z[f"{tag}_temperature"]))
+        cfg.training_mode = "1H_13C_HSQC_COSY_IR_MF_MW"
+        B = int(z[f"{tag}_B"])
+        data = synthetic.make_spectra(B, seed=int(z[f"{tag}_seed"]))
+        memory, mask, trg_enc_SMI, *_ = s["M"].run_model(s["model"], data, cfg)
+        for fn in (s["M"].predict_prop_correct_max_sequence_2, s["M"].predict_prop_correct_max_sequence_3):
+            trg, corr, trg_max, mx = fn(s["model"], STOI, memory, mask, trg_enc_SMI, cfg)
+            assert trg.shape == z[f"{tag}_trg"].shape and corr.shape == z[f"{tag}_corr"].shape and mx.shape == z[f"{tag}_max"].shape
+            assert np.array_equal(trg.cpu().numpy(), z[f"{tag}_trg"])
+            assert np.array_equal(trg_max.cpu().numpy(), z[f"{tag}_trg_max"])          # arg-max ids bit-exact (fp32 check mode)
+            np.testing.assert_allclose(corr.cpu().numpy(), z[f"{tag}_corr"], atol=2e-5, rtol=0)
+            np.testing.assert_allclose(mx.cpu().numpy(), z[f"{tag}_max"], atol=2e-5, rtol=0)
+        if B > 1:
+            with pytest.raises(ValueError, match="only one element"):            # the reference's own failure for N > 1
+                s["M"].predict_prop_correct_max_sequence(s["model"], STOI, memory, mask, trg_enc_SMI, 3, cfg)
+            continue
+        # five-output variant: the extra output is the probability of one torch.multinomial draw per position
+        gen = torch.cuda.default_generators[torch.cuda.current_device()]
+        torch.manual_seed(99)
+        off0 = gen.get_offset()
+        five = s["M"].predict_prop_correct_max_sequence(s["model"], STOI, memory, mask, trg_enc_SMI, 3, cfg)
+        assert tuple(five[4].shape) == tuple(z[f"{tag}_multinom_shape"])
+        L = five[1].shape[0]
+        assert gen.get_offset() - off0 == L * engine_inc(s, 1)
+        # the same draws from stock torch on the teacher-forced probabilities
+        real_trg = trg_enc_SMI.cuda().transpose(0, 1)[1:]
+        trg_in = torch.cat([torch.full((1, 1), 3, dtype=torch.long, device="cuda"), real_trg[:-1]], dim=0)
+        logits = s["M"].teacher_forced_logits(s["model"], memory, mask, trg_in, cfg)
+        probs = torch.softmax(logits / cfg.temperature, dim=2)
+        torch.manual_seed(99)
+        want = torch.stack([probs[t].gather(1, torch.multinomial(probs[t], 1)).squeeze() for t in range(L)])
+        agree = (torch.isclose(five[4], want, atol=1e-6)).float().mean().item()
+        assert agree >= 0.95, agree
+
+
+def engine_inc(s, n):
+    from multimodalspectraltransformer_b200.engine import engine_for
+    return engine_for(s["model"], s["cfg"]).philox_increment(n)
