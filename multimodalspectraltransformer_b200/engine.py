@@ -17,15 +17,29 @@ _PREC = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
 
 
 def _desc_from(config, state_dict=None) -> ModelDesc:
+    """Hyper-parameters of the model.  Every size a weight shape determines is read from the state_dict, not from
+    ``config``: callers mutate ``config`` (e.g. ``max_len``) long after the model was built from it
+    (mmt_result_test_functions_15_4.py:547), and the model -- not the namespace -- is what the engine must match."""
     g = lambda k, dflt: int(getattr(config, k, dflt))
-    d_ff = 2048                         # torch default dim_feedforward; the reference never overrides it
-    if state_dict is not None and "decoder.layers.0.linear1.weight" in state_dict:
-        d_ff = int(state_dict["decoder.layers.0.linear1.weight"].shape[0])
+    sd = state_dict or {}
+
+    def rows(key, dflt, axis=0):
+        return int(sd[key].shape[axis]) if key in sd else dflt
+
+    def layers(prefix, dflt):
+        idx = [int(k[len(prefix):].split(".")[0]) for k in sd if k.startswith(prefix)]
+        return max(idx) + 1 if idx else dflt
+
     return ModelDesc(
-        d_model=g("hidden_size", 128), n_heads=g("num_heads", 16), n_heads_cross=int(g("num_heads", 16) / 4),
-        d_ff=d_ff, n_enc_layers=g("num_encoder_layers", 6), n_dec_layers=g("num_decoder_layers", 6),
-        vocab=g("out_size", 43), max_len=g("max_len", 128), mf_vocab=g("MF_vocab_size", 212),
-        ms_vocab=g("MS_vocab_size", 43), ir_bins=g("input_dim_IR", 1000), fp_size=g("fingerprint_size", 512),
+        d_model=rows("embed_trg.weight", g("hidden_size", 128), 1), n_heads=g("num_heads", 16), n_heads_cross=int(g("num_heads", 16) / 4),
+        d_ff=rows("decoder.layers.0.linear1.weight", 2048),      # torch default dim_feedforward; the reference never overrides it
+        n_enc_layers=layers("encoder_cross.layers.", g("num_encoder_layers", 6)),
+        n_dec_layers=layers("decoder.layers.", g("num_decoder_layers", 6)),
+        vocab=rows("fc_out.weight", g("out_size", 43)), max_len=rows("pe_trg.weight", g("max_len", 128)),
+        mf_vocab=rows("linear_embedding_MF.embedding.weight", g("MF_vocab_size", 212)),
+        ms_vocab=rows("linear_embedding_MS.embedding.weight", g("MS_vocab_size", 43)),
+        ir_bins=rows("linear_spec_embedding_IR.linear_spec_embedding_IR.weight", g("input_dim_IR", 1000), 1),
+        fp_size=rows("fp1.weight", g("fingerprint_size", 512)),
         pad_points=g("padding_points_number", 64))
 
 

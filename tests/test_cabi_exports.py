@@ -58,3 +58,18 @@ def test_no_cpu_fallback():
     model = M.MultimodalTransformer(cfg)
     with pytest.raises(RuntimeError):
         M.run_model(model, synthetic.make_spectra(2), cfg)
+
+
+def test_model_desc_follows_the_weights_not_the_mutable_config():
+    """Callers lower config.max_len mid-run (mmt_result_test_functions_15_4.py:547) on the very namespace the model was
+    built from; the engine's hyper-parameters must keep describing the model (pe_trg rows, layer counts, vocab sizes)."""
+    import multimodalspectraltransformer_b200 as M
+    from multimodalspectraltransformer_b200.engine import _desc_from
+    cfg = M.default_config(device="cpu")
+    model = M.MultimodalTransformer(cfg)
+    cfg.max_len, cfg.num_decoder_layers, cfg.out_size, cfg.input_dim_IR = 12, 2, 7, 10
+    d = _desc_from(cfg, model.state_dict())
+    assert (d.max_len, d.n_dec_layers, d.n_enc_layers, d.vocab, d.ir_bins, d.mf_vocab, d.fp_size, d.d_ff, d.d_model) == \
+        (128, 6, 6, 43, 1000, 212, 512, 2048, 128)
+    d0 = _desc_from(M.default_config(device="cpu"))
+    assert (d0.max_len, d0.n_dec_layers, d0.vocab) == (128, 6, 43)
