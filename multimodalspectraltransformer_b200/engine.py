@@ -43,6 +43,14 @@ def _desc_from(config, state_dict=None) -> ModelDesc:
         pad_points=g("padding_points_number", 64))
 
 
+def _normalize_state_dict(state_dict):
+    """Lightning checkpoints / the TransformerMultiGPU wrapper prefix every key with ``model.`` (models_MMT_v15_4.py:998);
+    accept either form."""
+    if "embed_trg.weight" not in state_dict and "model.embed_trg.weight" in state_dict:
+        return {k[len("model."):]: v for k, v in state_dict.items() if k.startswith("model.")}
+    return state_dict
+
+
 def default_precision(config) -> str:
     """``config.precision`` ("fp32" check mode | "bf16" tensor-core mode); fp32 when unset."""
     return str(getattr(config, "precision", "fp32"))
@@ -59,6 +67,7 @@ class Engine:
         if self.device.type != "cuda":
             raise RuntimeError(f"mmt_b200 engine cannot run on device {device!r}; there is no CPU fallback")
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        state_dict = _normalize_state_dict(state_dict)
         self.desc = _desc_from(config, state_dict)
         L, d = self.L, C.byref(self.desc)
         n = L.mmt_weight_count(d)

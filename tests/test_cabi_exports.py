@@ -73,3 +73,14 @@ def test_model_desc_follows_the_weights_not_the_mutable_config():
         (128, 6, 6, 43, 1000, 212, 512, 2048, 128)
     d0 = _desc_from(M.default_config(device="cpu"))
     assert (d0.max_len, d0.n_dec_layers, d0.vocab) == (128, 6, 43)
+
+
+def test_lightning_prefixed_state_dict_is_accepted():
+    import multimodalspectraltransformer_b200 as M
+    from multimodalspectraltransformer_b200.engine import _desc_from, _normalize_state_dict
+    model = M.MultimodalTransformer(M.default_config(device="cpu"))
+    sd = model.state_dict()
+    wrapped = {"model." + k: v for k, v in sd.items()}
+    un = _normalize_state_dict(wrapped)
+    assert list(un.keys()) == list(sd.keys()) and _normalize_state_dict(sd) is sd
+    assert _desc_from(M.default_config(device="cpu"), un).max_len == 128
