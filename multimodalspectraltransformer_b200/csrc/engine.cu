@@ -346,6 +346,9 @@ static int launch_encoder_attention(mmt_engine* e, EncGroupRun* gr, int ng, int 
         p.g[i].S = gr[i].S;
         p.g[i].row_start = gr[i].row_start; p.g[i].cnt = gr[i].cnt; p.g[i].kstride = gr[i].kstride;
     }
+    // staging capacity in keys: a 32-wide head costs 260 B per key in either kernel; sequences with more keys (MS modes with
+    // every token valid: up to 902) are walked in chunks of this size
+    if (dh >= 32) key_bound = std::min(key_bound, 768);
     for (int i = 0; i < ng; ++i) p.g[i].smax = key_bound;
     dim3 grid(heads, Bc, ng);
     if (dh == AT_DH && e->use_tc_attention && (bf16_out || e->tc_attention_fp32)) {   // encoder_cross in the tensor-core mode: mma.sync flash attention, two-term operand splits

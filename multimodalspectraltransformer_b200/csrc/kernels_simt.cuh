@@ -387,27 +387,35 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
     const AttnGroup& g = p.g[blockIdx.z];
     const int h = blockIdx.x, b = blockIdx.y;
     const int S = g.cnt ? g.cnt[b] : g.S;            // query rows of this sequence
-    const int Smax = g.smax;                         // smem carve-up bound (host sizes smem for it)
+    const int Smax = g.smax;                         // keys the staging area holds (host sizes smem for it)
     const int kstride = g.cnt ? g.kstride : g.S;
     const int64_t row0 = g.row_start ? (int64_t)g.row_start[b] : (int64_t)b * g.S;
     const int nk = g.nk[b];
-    float* Ks = smem;                    // [nk][DH]
-    float* Vs = Ks + (size_t)Smax * DH;  // [nk][DH]
-    float* bs = Vs + (size_t)Smax * DH;  // [nk]
+    float* Ks = smem;                    // [Smax][DH]
+    float* Vs = Ks + (size_t)Smax * DH;  // [Smax][DH]
+    float* bs = Vs + (size_t)Smax * DH;  // [Smax]
     const float* base = g.qkv + row0 * (3 * D);
     constexpr int V4 = DH / 4;
-    for (int i = threadIdx.x; i < nk * V4; i += blockDim.x) {
-        int jj = i / V4, q4 = i % V4;
-        int j = g.kidx[(int64_t)b * kstride + jj];
-        const float* row = base + (int64_t)j * (3 * D) + h * DH + q4 * 4;
-        *reinterpret_cast<float4*>(Ks + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + D);
-        *reinterpret_cast<float4*>(Vs + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + 2 * D);
-        if (q4 == 0) bs[jj] = g.kbias ? g.kbias[(int64_t)b * g.S + j] : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    // keys [k0, k0 + n) -> shared memory
+    auto stage = [&](int k0, int n) {
+        for (int i = threadIdx.x; i < n * V4; i += blockDim.x) {
+            int jj = i / V4, q4 = i % V4;
+            int j = g.kidx[(int64_t)b * kstride + k0 + jj];
+            const float* row = base + (int64_t)j * (3 * D) + h * DH + q4 * 4;
+            *reinterpret_cast<float4*>(Ks + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + D);
+            *reinterpret_cast<float4*>(Vs + jj * DH + q4 * 4) = *reinterpret_cast<const float4*>(row + 2 * D);
+            if (q4 == 0) bs[jj] = g.kbias ? g.kbias[(int64_t)b * g.S + j] : 0.f;
+        }
+    };
+    // The usual case stages every key once.  A sequence with more keys than the staging area holds (MS modes with
+    // every token valid: up to 902 keys x 260 B > 227 KB) walks them in chunks, re-staged per round of query rows.
+    const bool single = nk <= Smax;
+    if (single) { stage(0, nk); __syncthreads(); }
+    for (int i0 = 0; i0 < S; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool active = i < S;
         float q[DH], acc[DH];
-        const float* qrow = base + (int64_t)i * (3 * D) + h * DH;
+        const float* qrow = base + (int64_t)(active ? i : 0) * (3 * D) + h * DH;
 #pragma unroll
         for (int d4 = 0; d4 < V4; ++d4) {
             float4 t = *reinterpret_cast<const float4*>(qrow + d4 * 4);
@@ -416,30 +424,36 @@ __global__ void __launch_bounds__(256) attn_encoder_f32(const __grid_constant__ 
 #pragma unroll
         for (int d = 0; d < DH; ++d) acc[d] = 0.f;
         float m = MMT_NEG_INF, l = 0.f;
-        for (int j = 0; j < nk; ++j) {
-            float s = bs[j];
+        for (int k0 = 0; k0 < nk; k0 += Smax) {
+            const int n = min(Smax, nk - k0);
+            if (!single) { __syncthreads(); stage(k0, n); __syncthreads(); }
+            if (!active) continue;
+            for (int j = 0; j < n; ++j) {
+                float s = bs[j];
 #pragma unroll
-            for (int d4 = 0; d4 < V4; ++d4) {
-                float4 k = *reinterpret_cast<const float4*>(Ks + j * DH + d4 * 4);
-                s = fmaf(q[d4 * 4], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
-                s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
-            }
-            if (s > m) {
-                float corr = expf(m - s);   // m = -inf on the first key -> 0
-                l *= corr;
+                for (int d4 = 0; d4 < V4; ++d4) {
+                    float4 k = *reinterpret_cast<const float4*>(Ks + j * DH + d4 * 4);
+                    s = fmaf(q[d4 * 4], k.x, s); s = fmaf(q[d4 * 4 + 1], k.y, s);
+                    s = fmaf(q[d4 * 4 + 2], k.z, s); s = fmaf(q[d4 * 4 + 3], k.w, s);
+                }
+                if (s > m) {
+                    float corr = expf(m - s);   // m = -inf on the first key -> 0
+                    l *= corr;
 #pragma unroll
-                for (int d = 0; d < DH; ++d) acc[d] *= corr;
-                m = s;
-            }
-            float e = expf(s - m);
-            l += e;
+                    for (int d = 0; d < DH; ++d) acc[d] *= corr;
+                    m = s;
+                }
+                float e = expf(s - m);
+                l += e;
 #pragma unroll
-            for (int d4 = 0; d4 < V4; ++d4) {
-                float4 v = *reinterpret_cast<const float4*>(Vs + j * DH + d4 * 4);
-                acc[d4 * 4] = fmaf(e, v.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(e, v.y, acc[d4 * 4 + 1]);
-                acc[d4 * 4 + 2] = fmaf(e, v.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(e, v.w, acc[d4 * 4 + 3]);
+                for (int d4 = 0; d4 < V4; ++d4) {
+                    float4 v = *reinterpret_cast<const float4*>(Vs + j * DH + d4 * 4);
+                    acc[d4 * 4] = fmaf(e, v.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(e, v.y, acc[d4 * 4 + 1]);
+                    acc[d4 * 4 + 2] = fmaf(e, v.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(e, v.w, acc[d4 * 4 + 3]);
+                }
             }
         }
+        if (!active) continue;
         float inv = 1.0f / l;
         if (g.out) {
             float* orow = g.out + (row0 + i) * D + h * DH;
@@ -522,16 +536,17 @@ __global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant_
     float* bs = reinterpret_cast<float*>(Vl + plane);               // [nkp] key bias * log2(e)
     const float* base = g.qkv + row0 * (3 * D);
     constexpr float LOG2E = 1.4426950408889634f;
-    // ---- stage K / V of the attendable keys as hi / lo bf16 planes; zero the padding keys.
+    // ---- stage K / V of the attendable keys [k0, k0 + np) as hi / lo bf16 planes; zero the padding keys (>= nk).
     // Four items per thread and pass: the index loads, then the row loads, are all in flight before the first conversion.
-    const int total = nkp * (AT_DH / 4);
+    auto stage = [&](int k0, int np) {
+    const int total = np * (AT_DH / 4);
     for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
         int key[4];
         float4 kk[4], vv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * blockDim.x, jj = i / (AT_DH / 4);
-            key[u] = (i < total && jj < nk) ? g.kidx[(int64_t)b * kstride + jj] : -1;
+            key[u] = (i < total && k0 + jj < nk) ? g.kidx[(int64_t)b * kstride + k0 + jj] : -1;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -558,7 +573,11 @@ __global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant_
             *reinterpret_cast<uint2*>(Vl + at_off(jj, q4)) = make_uint2(l0, l1);
         }
     }
-    __syncthreads();
+    };
+    // The usual case stages every key once.  A sequence with more keys than the staging area holds (MS modes with every
+    // token valid: 902 keys x 260 B > 227 KB) walks them in chunks, re-staged per round of query-row tiles.
+    const bool single = nkp <= nkp_max;
+    if (single) { stage(0, nkp); __syncthreads(); }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     // ldmatrix row addresses of this lane (bytes from the plane base, without the key-block offset):
@@ -571,7 +590,9 @@ __global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant_
     const uint32_t sKh = (uint32_t)__cvta_generic_to_shared(Kh), sKl = (uint32_t)__cvta_generic_to_shared(Kl);
     const uint32_t sVh = (uint32_t)__cvta_generic_to_shared(Vh), sVl = (uint32_t)__cvta_generic_to_shared(Vl);
     const float qscale = p.scale * LOG2E;
-    for (int tile = warp; tile * 16 < S; tile += nwarps) {
+    for (int tile0 = 0; tile0 * 16 < S; tile0 += nwarps) {
+        const int tile = tile0 + warp;
+        const bool active = tile * 16 < S;
         const int r_lo = tile * 16 + gq, r_hi = r_lo + 8;
         // Q fragments (scaled into the log2 domain, split): [kstep][4 regs]
         uint32_t qh[2][4], ql[2][4];
@@ -592,7 +613,11 @@ __global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
         float m_lo = MMT_NEG_INF, m_hi = MMT_NEG_INF, l_lo = 0.f, l_hi = 0.f;
-        for (int kb = 0; kb < nkp; kb += 16) {
+        for (int k0 = 0; k0 < nkp; k0 += nkp_max) {
+        const int np = min(nkp_max, nkp - k0);
+        if (!single) { __syncthreads(); stage(k0, np); __syncthreads(); }
+        if (!active) continue;
+        for (int kb = 0; kb < np; kb += 16) {
             const uint32_t kb_off = (uint32_t)(kb * AT_KROW * 2);
             // ---- scores of 16 keys: two 16x8 tiles
             float sc[2][4];
@@ -635,19 +660,21 @@ __global__ void __launch_bounds__(384, 2) attn_encoder_tc(const __grid_constant_
             }
             // ---- o += P V  (B fragments by ldmatrix.trans: keys kb + 2t (+8), column d = nt*8 + g)
 #pragma unroll
-            for (int np = 0; np < 2; ++np) {      // pairs of 8-wide output tiles
+            for (int np2 = 0; np2 < 2; ++np2) {      // pairs of 8-wide output tiles
                 uint32_t vh[4], vl[4];            // {b0, b1} of tile 2*np, {b0, b1} of tile 2*np + 1
-                const uint32_t t_off = kb_off + v_row_off + (uint32_t)((((np * 2 + (lane >> 4)) ^ sw) & 3) * 16);
+                const uint32_t t_off = kb_off + v_row_off + (uint32_t)((((np2 * 2 + (lane >> 4)) ^ sw) & 3) * 16);
                 ldmatrix_x4_trans(vh, sVh + t_off);
                 ldmatrix_x4_trans(vl, sVl + t_off);
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    mma_bf16_16816(acc[np * 2 + u], ph, vh[u * 2], vh[u * 2 + 1]);
-                    mma_bf16_16816(acc[np * 2 + u], ph, vl[u * 2], vl[u * 2 + 1]);
-                    mma_bf16_16816(acc[np * 2 + u], pl, vh[u * 2], vh[u * 2 + 1]);
+                    mma_bf16_16816(acc[np2 * 2 + u], ph, vh[u * 2], vh[u * 2 + 1]);
+                    mma_bf16_16816(acc[np2 * 2 + u], ph, vl[u * 2], vl[u * 2 + 1]);
+                    mma_bf16_16816(acc[np2 * 2 + u], pl, vh[u * 2], vh[u * 2 + 1]);
                 }
             }
         }
+        }
+        if (!active) continue;
         l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
         l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
         const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;

@@ -39,6 +39,11 @@ CASES = [
     dict(name="mode_hsqc_b2", B=2, seed=15, peaks="realistic", blank=(), mode="HSQC_MF_MW", glen=24, mlen=8),
     dict(name="mode_1h13c_b2", B=2, seed=16, peaks="realistic", blank=(), mode="1H_13C_MF_MW", glen=24, mlen=0),
     dict(name="mode_noir_b2", B=2, seed=17, peaks="realistic", blank=(), mode="1H_13C_HSQC_COSY_MF_MW", glen=16, mlen=0),
+    # "MS" in training_mode: every modality sequence gains a 64-token MS block (193 / 130 rows, 902-row memory)
+    dict(name="mode_ms_b2", B=2, seed=18, peaks="realistic", blank=(), mode="1H_13C_HSQC_COSY_IR_MF_MS_MW", glen=16, mlen=8),
+    dict(name="mode_ms_max_b2", B=2, seed=19, peaks="max", blank=(), mode="1H_13C_HSQC_COSY_IR_MF_MS_MW", glen=12, mlen=0),
+    # MS + ablation: float masks, all ~900 keys of the memory attended (more than the attention kernels stage at once)
+    dict(name="mode_ms_hsqc_b2", B=2, seed=20, peaks="realistic", blank=(), mode="HSQC_MF_MS_MW", glen=12, mlen=0),
 ]
 
 
@@ -64,7 +69,10 @@ def main():
     with open(os.path.join(GOLDEN, "weights_meta.json"), "w") as f:
         json.dump(meta, f)
 
+    only = set(sys.argv[1:])              # python -m oracle.make_golden [case ...]: regenerate just these
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         t0 = time.time()
         cfg.training_mode = case["mode"]
         cfg.temperature = 1
