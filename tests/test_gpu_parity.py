@@ -250,8 +250,33 @@ def test_candidates_share_memory_equals_duplication():
     assert torch.equal(m1, m2) and torch.equal(q1, q2)
     # duplicate_dict path: encode the k copies like the reference does
     dd = s["M"].duplicate_dict({kk: v[:1] for kk, v in data.items()}, k)
-    mem_d, mask_d, *_ = s["M"].run_model(s["model"], dd, cfg)
+    eng = engine_for_cfg(s, cfg)
+    l0 = eng.launch_count()
+    mem_d, mask_d, _, fp_d, *_ = s["M"].run_model(s["model"], dd, cfg)
+    one = eng.launch_count() - l0
     torch.testing.assert_close(mem_d, memory[:, :1].expand(-1, k, -1), atol=1e-6, rtol=0)
+    assert tuple(mem_d.shape) == (582, k, 128) and tuple(mask_d.shape) == (k, 582) and tuple(fp_d.shape) == (k, 512)
+    # the copies are encoded once (same launch count as a single spectrum), in tensor.repeat's order for B0 > 1 ...
+    dd2 = s["M"].duplicate_dict({kk: v[:2] for kk, v in data.items()}, 3)
+    mem2, mask2, trg2, *_ = s["M"].run_model(s["model"], dd2, cfg)
+    torch.testing.assert_close(mem2, memory[:, :2].repeat(1, 3, 1), atol=1e-6, rtol=0)
+    assert torch.equal(trg2.cpu(), data["trg_enc_SMI"][:2].repeat(3, 1))
+    # ... unless the caller changed an entry after duplicating: then every copy is encoded as given
+    dd3 = s["M"].duplicate_dict({kk: v[:1] for kk, v in data.items()}, k)
+    dd3["src_13C"][2, 0] += 0.25
+    l0 = eng.launch_count()
+    mem3, *_ = s["M"].run_model(s["model"], dd3, cfg)
+    assert eng.launch_count() - l0 >= one
+    assert torch.equal(mem3[:, 0], mem3[:, 1]) and not torch.equal(mem3[:, 0], mem3[:, 2])
+    dd4 = s["M"].duplicate_dict({kk: v[:1] for kk, v in data.items()}, k)
+    dd4["src_IR"] = torch.zeros_like(dd4["src_IR"])
+    mem4, *_ = s["M"].run_model(s["model"], dd4, cfg)
+    assert not torch.allclose(mem4[:, 0], mem_d[:, 0])
+
+
+def engine_for_cfg(s, cfg):
+    from multimodalspectraltransformer_b200.engine import engine_for
+    return engine_for(s["model"], cfg)
 
 
 def test_multinomial_vs_oracle_on_device_same_seed():
