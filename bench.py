@@ -300,6 +300,22 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "wall_s": {"resident": wall_res, "e2e": wall_e2e}}
         if world == 1 and not args.no_cpu_baseline:
+            # informational, outside every timed region: one candidate wave of BASELINE.json config 3 (multinomial, 128 spectra x
+            # 128 candidates sharing each spectrum's cross K/V = 16,384 sequences x 128 tokens, decode only, memory resident)
+            try:
+                mem128, mask128 = memory[:, :128], mask[:128]
+                stoi = {"<SOS>": 3}
+                M.multinomial_sequence_multi(model, mem128, mask128, stoi, cfg, n_candidates=128)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                M.multinomial_sequence_multi(model, mem128, mask128, stoi, cfg, n_candidates=128)
+                ev1.record()
+                torch.cuda.synchronize()
+                ms3 = ev0.elapsed_time(ev1)
+                line["config3_wave"] = {"value": 128 * 128 * MAX_LEN / (ms3 * 1e-3), "unit": UNIT, "ms": ms3,
+                                        "workload": "multinomial decode, 128 spectra x 128 candidates x 128 tokens (one 16,384-sequence wave of config 3)"}
+            except Exception as exc:      # never let the extra measurement cost the bench line
+                line["config3_wave"] = {"error": str(exc)[:200]}
             v, toks, sec, threads = cpu_reference_tokens_per_s(CPU_BASELINE_SPECTRA, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{CPU_BASELINE_SPECTRA} of the {B_PER_GPU} spectra x {MAX_LEN} greedy steps ({toks} tokens, {sec:.1f} s) of the same workload, "
