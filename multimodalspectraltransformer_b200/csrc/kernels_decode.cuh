@@ -19,11 +19,12 @@
 //     kernel start (no registers held), so that HBM stream overlaps the self-attention phases;
 //   * one warp per (row, head): every per-warp index / page-table load is issued up front.
 //
-// Arithmetic is fp32 FMA with fp32 activations in both precision modes.  The kernel is bound by the bytes an
-// SM can pull in (~30 B/cycle measured for LDG and TMA alike: profiles/micro/load_latency.cu), and the fp32
-// weights were 57 % of them; in the tensor-core mode the four projection matrices are therefore read as bf16
-// (the hi term of the two-term split: measured logit error unchanged, DESIGN.md "bf16 numerics"), which also
-// lets all four sit in shared memory at once -- every weight copy is issued before the PDL wait.
+// Arithmetic is fp32 FMA with fp32 activations in both precision modes.  In the tensor-core mode the four
+// projection matrices are read as bf16 (the hi term of the two-term split: measured logit error unchanged,
+// DESIGN.md "bf16 numerics"): half the bytes per CTA (worth 2.5 % of the step) and all four fit in shared memory
+// at once, so every weight copy is issued before the PDL wait.  Later same-box knock-outs
+// (profiles/r01_decode_phase_cycles.md) showed the phases to be fixed latency chains -- neither the arithmetic, nor
+// the issue slots, nor the weight stream, nor (with the L2 prefetch below) the K/V stream bounds them.
 //
 // Shape of the work: the kernels are pure latency chains (L2 / HBM round trips), so a CTA is a full
 // 1024-thread SM's worth of warps for DA_R rows: one warp per (row, head) in the attention phases,
