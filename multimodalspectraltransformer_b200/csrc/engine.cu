@@ -60,6 +60,19 @@ static void launch_kernel(void (*kernel)(P), dim3 grid, dim3 block, size_t smem,
     cudaLaunchKernelEx(&cfg, kernel, params);     // errors surface through cudaGetLastError() in check_launch
 }
 
+// the same for kernels that take their arguments one by one
+template <typename... KArgs, typename... Args>
+static void launch_args(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int ensure_arena(mmt_engine* e, size_t bytes) {
     if (bytes <= e->arena_bytes) return 0;
     if (e->arena) {
@@ -165,7 +178,7 @@ static TcGemmParams tc_params(int M, int N, int K) {
 // A [M,K] bf16 (row pitch lda), W [N,K] bf16 (dense), optional low-order weight term Wlo; the
 // rest of `p` is filled by the caller
 static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int epi, cudaStream_t s,
-                     const __nv_bfloat16* Wlo = nullptr) {
+                     const __nv_bfloat16* Wlo = nullptr, bool pdl = false) {
     if (p.M <= 0) return 0;
     MMT_TRY(tc_init(e));
     if (p.K % TC_BK || p.N % 4) MMT_FAIL("tcgen05 GEMM needs K % 64 == 0 and N % 4 == 0");
@@ -183,8 +196,8 @@ static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int
     const size_t smem = (size_t)std::max(p.stages * (p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES), TC_STAGING_BYTES) + 1024;
     dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
     prof_pre(e, s);
-    if (epi == TC_EPI_LN) gemm_bf16_tc<TC_EPI_LN><<<grid, TC_THREADS, smem, s>>>(p);
-    else gemm_bf16_tc<TC_EPI_STORE><<<grid, TC_THREADS, smem, s>>>(p);
+    if (epi == TC_EPI_LN) launch_kernel(gemm_bf16_tc<TC_EPI_LN>, grid, dim3(TC_THREADS), smem, s, pdl, p);
+    else launch_kernel(gemm_bf16_tc<TC_EPI_STORE>, grid, dim3(TC_THREADS), smem, s, pdl, p);
     return check_launch(e, epi == TC_EPI_LN ? "gemm_bf16_tc_ln" : "gemm_bf16_tc", s, 2.0 * p.M * p.N * p.K);
 }
 
@@ -928,6 +941,17 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     const int64_t ldn = r.ldn >= 0 ? r.ldn : N_total;
     const int M = (int)Nw;
 
+    // Small batches: every decoder operation except the FFN is local to one sequence, so two
+    // fused kernels per layer replace the chain of projection / attention / LayerNorm launches
+    // (kernels_decode.cuh); the previous layer's FFN2 split-K partials + norm3 are folded into the
+    // next kernel's prologue (the sampler's for the last layer).
+    const bool fused = e->fused_decode_rows > 0 && Nw <= e->fused_decode_rows;
+    const bool pdl = fused && e->use_pdl && !e->profiling;
+    // un-fused tensor-core step: the same attribute through the chain of 31 launches (every kernel of the chain waits with
+    // griddepcontrol.wait before it touches its predecessor's output; the LayerNorm-only kernel has no hook and is launched plainly)
+    // Only for moderate waves: measured 50.2 -> 45.2 ms for a beam search over 2560 slots, but 1426 -> 1473 us per position at
+    // 16,384 sequences, where the early-scheduled CTAs take SM resources from a predecessor that is throughput-bound.
+    const bool pdl_u = !fused && bf16 && e->use_pdl && !e->profiling && Nw <= 4096;
     // x = LN(x + bias + sum_s part[s]) (separate kernel; fp32 mode and split-K FFN2)
     auto ln = [&](const float* part, int splits, const float* bias, const float* gamma, const float* beta) -> int {
         LnParams q;
@@ -949,20 +973,14 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         TcGemmParams p = tc_params(M, N, K);
         p.bias = bias; p.act = act; p.out_f32 = C32; p.ld_f32 = N; p.out_b16 = C16; p.ld_b16 = N;
         p.splits = splits; p.part_stride = Nw * D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s, e->Wlo(W));
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s, e->Wlo(W), pdl_u);
     };
     auto tc_ln = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, int K, const float* gamma, const float* beta) -> int {
         TcGemmParams p = tc_params(M, D, K);
         p.bias = bias; p.res = b.x; p.gamma = gamma; p.beta = beta;
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W));
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W), pdl_u);
     };
-    // Small batches: every decoder operation except the FFN is local to one sequence, so two
-    // fused kernels per layer replace the chain of projection / attention / LayerNorm launches
-    // (kernels_decode.cuh); the previous layer's FFN2 split-K partials + norm3 are folded into the
-    // next kernel's prologue (the sampler's for the last layer).
-    const bool fused = e->fused_decode_rows > 0 && Nw <= e->fused_decode_rows;
-    const bool pdl = fused && e->use_pdl && !e->profiling;
     int ffn_splits = 1;
     if (fused) {
         if (dh != 8 || H != DA_H) MMT_FAIL("decoder must have 16 heads of dim 8");
@@ -1019,8 +1037,8 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         }
     } else {
         prof_pre(e, s);
-        if (r.trg) decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.trg + n0, 0, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
-        else decode_embed<<<(unsigned)((Nw + 3) / 4), 128, 0, s>>>(r.tokens + n0, 1, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), d.vocab, step, b.x, b.x16);
+        if (r.trg) launch_args(decode_embed, dim3((unsigned)((Nw + 3) / 4)), dim3(128), 0, s, pdl_u, r.trg + n0, 0, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), (int)d.vocab, step, b.x, b.x16);
+        else launch_args(decode_embed, dim3((unsigned)((Nw + 3) / 4)), dim3(128), 0, s, pdl_u, (const int64_t*)(r.tokens + n0), 1, 3, Nw, ldn, e->W("embed_trg.weight"), e->W("pe_trg.weight"), (int)d.vocab, step, b.x, b.x16);
         MMT_TRY(check_launch(e, "decode_embed", s));
 
         const unsigned attn_blocks = (unsigned)((Nw * H + 7) / 8);
@@ -1033,7 +1051,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
             prof_pre(e, s);
             const unsigned sa_blocks = (unsigned)((Nw * (H / 4) + 7) / 8);     // a warp per (sequence, 4 heads)
-            if (bf16) decode_self_attention_g8<8, __nv_bfloat16><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), b.block_table, pps, Nw, H, scale, step, nullptr, b.att16);
+            if (bf16) launch_args(decode_self_attention_g8<8, __nv_bfloat16>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
             else decode_self_attention_g8<8, float><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_self_attention", s));
             if (bf16) {
@@ -1046,8 +1064,8 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             }
             prof_pre(e, s);
             if (bf16 && a.n_cand >= 8 && e->use_tc_attention)   // candidates of a spectrum share K/V: tensor-core tiles of 16 candidates
-                decode_cross_attention_tc<<<dim3(H, Bmw), 256, dx_smem_bytes(a.S), s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, H, scale, nullptr, b.att16);
-            else if (bf16) decode_cross_attention<8, __nv_bfloat16><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, nullptr, b.att16);
+                launch_args(decode_cross_attention_tc, dim3(H, Bmw), dim3(256), dx_smem_bytes(a.S), s, pdl_u, (const float*)b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), (int64_t)a.S, (const int*)b.nk, (const int*)b.row_start, (const float*)b.kbias_c, (int)a.n_cand, H, scale, (float*)nullptr, b.att16);
+            else if (bf16) launch_args(decode_cross_attention<8, __nv_bfloat16>, dim3(attn_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qc, reinterpret_cast<const __nv_bfloat16*>(ckv), (int64_t)a.S, (const int*)b.nk, (const int*)b.row_start, (const float*)b.kbias_c, (int)a.n_cand, Nw, H, scale, (float*)nullptr, b.att16);
             else decode_cross_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const float*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_cross_attention", s));
             if (bf16) {
@@ -1055,11 +1073,11 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 if (M >= 2048) {
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.bias = w.l2_b; f.res = b.x; f.gamma = w.n3_w; f.beta = w.n3_b; f.out_f32 = b.x; f.out_b16 = b.x16;
-                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_LN, s));
+                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_LN, s, pdl_u));
                 } else {   // few rows: split F over the grid, reduce the partials in the LayerNorm kernel
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.splits = MAX_SPLITS; f.out_f32 = b.part; f.part_stride = Nw * D;
-                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s));
+                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s, pdl_u));
                     MMT_TRY(ln(b.part, f.splits, w.l2_b, w.n3_w, w.n3_b));
                 }
             } else {
@@ -1095,7 +1113,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         sp.pbias = pw.l2_b; sp.pgamma = pw.n3_w; sp.pbeta = pw.n3_b; sp.eps = 1e-5f;
     }
     prof_pre(e, s);
-    launch_kernel(sample_tokens, dim3((unsigned)((Nw + 7) / 8)), dim3(256), 0, s, pdl, sp);
+    launch_kernel(sample_tokens, dim3((unsigned)((Nw + 7) / 8)), dim3(256), 0, s, pdl || pdl_u, sp);
     MMT_TRY(check_launch(e, "sample_tokens", s));
     return 0;
 }

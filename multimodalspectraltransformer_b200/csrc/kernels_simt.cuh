@@ -871,6 +871,8 @@ struct StepCtl {
 __global__ void __launch_bounds__(128) decode_embed(const int64_t* tokens, int tok_shift, int sos, int64_t N, int64_t ldn,
                                                     const float* E_tok, const float* E_pos, int vocab,
                                                     const int* step, float* x, __nv_bfloat16* x_bf16) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *step;
     const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (n >= N) return;
@@ -977,6 +979,8 @@ __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv
                                                                 const int* step, float* out, __nv_bfloat16* out16) {
     static_assert(DH == 8, "8-element key rows");
     typedef KvRow<KVT> KV;
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *step;
     const int HG = H / 4;                                  // head groups per sequence
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1069,6 +1073,8 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
                                                               __nv_bfloat16* out16) {
     static_assert(DH == 8, "8-element key rows");
     typedef KvRow<KVT> KV;
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (w >= N * H) return;
     const int lane = threadIdx.x & 31;
@@ -1138,6 +1144,7 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
     extern __shared__ __align__(16) unsigned char dx_smem[];
     constexpr int DH = 8;
     constexpr float LOG2E = 1.4426950408889634f;
+    pdl_launch_dependents();
     const int h = blockIdx.x;
     const int64_t b = blockIdx.y;
     const int cnt = nk[b];
@@ -1167,6 +1174,7 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
         bs[j] = bias;
     }
     __syncthreads();
+    pdl_wait();     // everything above reads decode-loop constants (projected memory, key counts, biases); the queries are the predecessor's
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int gq = lane >> 2, tq = lane & 3;
     const float qscale = scale * LOG2E;

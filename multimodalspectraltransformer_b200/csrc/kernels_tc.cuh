@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
     const int num_kb = kb_end - kb_begin;      // host guarantees >= 1
 
     const int stage_bytes = p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES;
+    pdl_launch_dependents();     // programmatic dependent launch (un-fused decode step): barrier / TMEM set-up overlaps the predecessor's tail
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmW);
@@ -339,6 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
+            pdl_wait();              // A is the predecessor's output
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % p.stages;
                 const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
         float* stage_q = reinterpret_cast<float*>(smem) + (q * 32) * TC_LDS;
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
+        pdl_wait();                  // residual reads / output writes below: the predecessor has completed (satisfied: A was loaded after it)
         epi_tmem_to_stage<TC_BN>(tmem_base, q, hf, lane, stage_q);
         epi_bar_sync();
         const float* st = stage_q + (hf * 16) * TC_LDS;
