@@ -632,3 +632,40 @@ def test_calls_are_ordered_on_the_callers_current_stream():
         side.synchronize()
         assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1]) and torch.equal(out[2], ref[2])
         assert torch.equal(out[3], ref[3]) and torch.equal(out[4], ref[4]) and out[5] == ref[5]
+
+
+def test_engines_follow_their_models():
+    """Callers pass a live nn.Module on every call: two models interleave without cross-talk, and an in-place
+    weight update (optimizer step, checkpoint load) is picked up by the next call."""
+    import copy
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    from multimodalspectraltransformer_b200.engine import engine_for
+    data = synthetic.make_spectra(3, seed=92)
+    cfg = cfg_for(max_len=16)
+    a = s["model"]
+    b = copy.deepcopy(a)
+    with torch.no_grad():
+        b.fc_out.bias[7] += 4.0
+    mem_a, mask_a, *_ = s["M"].run_model(a, data, cfg)
+    mem_b, mask_b, *_ = s["M"].run_model(b, data, cfg)
+    assert torch.equal(mem_a, mem_b)                         # same encoder weights
+    ta, _ = s["M"].greedy_sequence(a, STOI, None, mem_a, mask_a, cfg)
+    tb, _ = s["M"].greedy_sequence(b, STOI, None, mem_b, mask_b, cfg)
+    ta2, _ = s["M"].greedy_sequence(a, STOI, None, mem_a, mask_a, cfg)
+    assert torch.equal(ta, ta2) and not torch.equal(ta, tb) and (tb == 7).float().mean() > (ta == 7).float().mean()
+    assert engine_for(a, cfg) is not engine_for(b, cfg) and engine_for(a, cfg) is engine_for(a, cfg)
+    # in-place update of b -> rebuilt engine, results equal a's again
+    e_before = engine_for(b, cfg)
+    with torch.no_grad():
+        b.fc_out.bias[7] -= 4.0
+    tb2, _ = s["M"].greedy_sequence(b, STOI, None, mem_b, mask_b, cfg)
+    assert engine_for(b, cfg) is not e_before
+    assert torch.equal(tb2, ta)
+    # load_state_dict (checkpoint) is an in-place copy as well
+    with torch.no_grad():
+        sd = {k: v.clone() for k, v in b.state_dict().items()}
+        sd["fc_out.bias"][9] += 5.0
+    b.load_state_dict(sd)
+    tb3, _ = s["M"].greedy_sequence(b, STOI, None, mem_b, mask_b, cfg)
+    assert (tb3 == 9).float().mean() > (ta == 9).float().mean()
