@@ -12,9 +12,14 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer named d_* is DEVICE memory on
  *     the engine's device, h_* is HOST memory.
- *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*),
- *     never synchronises unless documented, and is re-entrant per engine handle
- *     (one in-flight call per handle).
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*)
+ *     and never synchronises unless documented.
+ *   - threads and streams: an engine owns ONE workspace, so calls on one handle
+ *     are serialised -- the library takes a per-engine mutex for the duration of
+ *     each call (callers may use a handle from several threads), and a call
+ *     issued on a different stream than the previous call on that handle first
+ *     waits, on the device, for the previous call's work (an event recorded at
+ *     the end of every call).  Two handles never share state.
  *   - return value: 0 on success, non-zero on failure; mmt_last_error() then
  *     returns a thread-local, NUL-terminated description.  There is no CPU
  *     fallback: without a usable sm_100 device mmt_create fails.

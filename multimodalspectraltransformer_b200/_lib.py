@@ -67,22 +67,49 @@ def mode_bits(training_mode: str) -> int:
     return bits
 
 
+class NvccMissing(RuntimeError):
+    """No compiler on this box (the GPU box runs the .so shipped with the snapshot)."""
+
+
+def _stale(srcs) -> bool:
+    return not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(s) for s in srcs)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).
+
+    Safe under torchrun: ranks serialise on a file lock, the compiler writes to a temporary file in the same
+    directory and the result is moved into place with an atomic rename, so no process can ever dlopen a
+    half-written library; a rank that waited for the lock finds the library fresh and returns."""
+    import fcntl
+    import tempfile
     srcs = SOURCES + [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))
                       if f.endswith((".cuh", ".h"))] + [HEADER]
-    if not force and os.path.exists(LIB_PATH):
-        if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-            return LIB_PATH
+    if not force and not _stale(srcs):
+        return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: cannot build libmmt_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stdout + res.stderr)
+        raise NvccMissing("nvcc not found: cannot build libmmt_b200.so")
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale(srcs):       # another process built it while this one waited
+                return LIB_PATH
+            fd, tmp = tempfile.mkstemp(prefix=".libmmt_b200.", suffix=".so.tmp", dir=_HERE)
+            os.close(fd)
+            try:
+                res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", tmp] + SOURCES, capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+                os.chmod(tmp, 0o755)
+                os.replace(tmp, LIB_PATH)
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+            if verbose:
+                print(res.stdout + res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -100,13 +127,12 @@ def lib():
             raise RuntimeError(f"MMT_B200_LIB={path} does not exist")
     else:
         path = LIB_PATH
-        if not os.path.exists(LIB_PATH):
-            build()
-        else:
-            try:
-                build()
-            except RuntimeError:
-                pass  # no nvcc on this box: use the shipped .so
+        try:
+            build()              # no-op when the library is newer than every source
+        except NvccMissing:
+            if not os.path.exists(LIB_PATH):
+                raise            # nothing shipped and nothing to build it with: fail loudly (no CPU fallback)
+            # no compiler on this box: the .so shipped with the snapshot is the build.  Compile errors are NOT swallowed.
     L = C.CDLL(path)
     vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
     D = C.POINTER(ModelDesc)

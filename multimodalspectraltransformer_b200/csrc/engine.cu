@@ -73,6 +73,23 @@ static void launch_args(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Scope of one C-ABI call on an engine: serialises the host side (the arena, the pinned staging buffer, the graph cache and
+// the launch counter are per engine) and orders the device side across streams -- a call on another stream than the
+// previous call's first waits for the event that call recorded at its end, so the shared workspace is never aliased by
+// two streams' work.  Calls on the same stream are ordered by the stream itself.
+struct EngineCall {
+    mmt_engine* e; cudaStream_t s; std::unique_lock<std::mutex> lk;
+    EngineCall(mmt_engine* e_, cudaStream_t s_) : e(e_), s(s_), lk(e_->mu) {
+        cudaSetDevice(e->device);
+        if (e->last_use_valid && e->last_stream != s) cudaStreamWaitEvent(s, e->last_use, 0);
+    }
+    ~EngineCall() {
+        if (!e->last_use && cudaEventCreateWithFlags(&e->last_use, cudaEventDisableTiming) != cudaSuccess) { e->last_use = nullptr; cudaGetLastError(); return; }
+        if (cudaEventRecord(e->last_use, s) == cudaSuccess) { e->last_use_valid = true; e->last_stream = s; }
+        else { e->last_use_valid = false; cudaGetLastError(); }
+    }
+};
+
 static int ensure_arena(mmt_engine* e, size_t bytes) {
     if (bytes <= e->arena_bytes) return 0;
     if (e->arena) {
@@ -833,6 +850,7 @@ static int encode_chunk(mmt_engine* e, const mmt_spectra& in, int b0, int Bc, in
 // ---------------------------------------------------------------------------
 struct DecBuffers {
     float *x, *qkv, *att, *part, *qc, *h;
+    int64_t part_rows;                 // capacity of `part` in rows of D floats
     char* kv_pool; int* block_table;   // paged self-attention cache, 6 pools of kv_esz-byte elements
     int64_t pool_pages;                // pages per layer pool (Nw * pps; twice that for the beam search's copy-on-write parity)
     char* cross_kv;                    // projected memory [layer][K|V][head][row][dh], kv_esz-byte elements
@@ -845,13 +863,17 @@ struct DecBuffers {
 };
 constexpr int MAX_SPLITS = 32;
 
-static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b, bool bf16, int kv_copies = 1) {
+static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw, int S, int max_len, DecBuffers& b, bool bf16, int fused_rows, int kv_copies = 1) {
     const int L = d.n_dec_layers;
     const int pps = (max_len + PAGE_TOKENS - 1) / PAGE_TOKENS;
     b.x = a.get<float>(Nw * D);
     b.qkv = a.get<float>(Nw * 3 * D);
     b.att = a.get<float>(Nw * D);
-    b.part = a.get<float>(Nw * D * (Nw <= 2048 ? MAX_SPLITS : 1));   // split partials only exist for small waves
+    // FFN2 split partials exist for small waves only (fused step: Nw <= fused_rows; un-fused step: M < 2048) -- but a run
+    // planned for a large wave can end in a short one (17,408 sequences = 16,384 + 1,024), so the buffer is sized for the
+    // largest small wave this plan can meet, not for the planned wave alone
+    b.part_rows = std::max<int64_t>(Nw, std::min<int64_t>(Nw, std::max(fused_rows, 2048)) * MAX_SPLITS);
+    b.part = a.get<float>(b.part_rows * D);
     b.qc = a.get<float>(Nw * D);
     b.h = a.get<float>(bf16 ? 0 : Nw * d.d_ff);
     b.kv_esz = bf16 ? 2 : 4;
@@ -998,6 +1020,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         ffn_splits = pick_splits(M, D, d.d_ff);
         if (bf16) { ffn_splits = 32; while (ffn_splits > 1 && (int64_t)(ffn_splits / 2) * ((M + 127) / 128) >= e->sm_count) ffn_splits /= 2; }
         if (bf16 && e->ffn_splits_override > 0) ffn_splits = e->ffn_splits_override;
+        if ((int64_t)ffn_splits * Nw > b.part_rows) MMT_FAIL("decode: FFN partial buffer too small for this wave (plan_decoder)");
         for (int l = 0; l < d.n_dec_layers; ++l) {
             const LayerW& w = e->dec[l];
             DecAttnParams q;
@@ -1077,6 +1100,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 } else {   // few rows: split F over the grid, reduce the partials in the LayerNorm kernel
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.splits = MAX_SPLITS; f.out_f32 = b.part; f.part_stride = Nw * D;
+                    if ((int64_t)f.splits * Nw > b.part_rows) MMT_FAIL("decode: FFN partial buffer too small for this wave (plan_decoder)");
                     MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s, pdl_u));
                     MMT_TRY(ln(b.part, f.splits, w.l2_b, w.n3_w, w.n3_b));
                 }
@@ -1085,6 +1109,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 MMT_TRY(ln(b.part, 1, w.ca_out_b, w.n2_w, w.n2_b));
                 MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
                 int splits = pick_splits(M, D, d.d_ff);
+                if ((int64_t)splits * Nw > b.part_rows) MMT_FAIL("decode: FFN partial buffer too small for this wave (plan_decoder)");
                 MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, splits));
                 MMT_TRY(ln(b.part, splits, w.l2_b, w.n3_w, w.n3_b));
             }
@@ -1155,7 +1180,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     DecBuffers lb[MAX_LANES];
     int64_t* st_tokens = nullptr; float* st_probs = nullptr;
     auto plan_all = [&]() {
-        for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16);
+        for (int i = 0; i < NL; ++i) plan_decoder(ar, d, (int64_t)Bm_lane * a.n_cand, Bm_lane, a.S, a.max_len, lb[i], bf16, e->fused_decode_rows);
         if (staged) { st_tokens = ar.get<int64_t>((size_t)a.max_len * N_total); st_probs = ar.get<float>((size_t)a.max_len * N_total); }
     };
     ar.plan = true;
@@ -1341,7 +1366,7 @@ static int run_beam(mmt_engine* e, const mmt_decode_args& a0, int K, int T, int 
     DecBuffers b;
     float* logits = nullptr; int64_t* cur_tok = nullptr; int *copy_src = nullptr, *copy_dst = nullptr;
     auto plan_all = [&]() {
-        plan_decoder(ar, d, Nw_max, Bm_wave, a.S, T, b, bf16, 2);
+        plan_decoder(ar, d, Nw_max, Bm_wave, a.S, T, b, bf16, e->fused_decode_rows, 2);
         logits = ar.get<float>((size_t)Nw_max * d.vocab);
         cur_tok = ar.get<int64_t>((size_t)Nw_max);
         copy_src = ar.get<int>((size_t)Nw_max); copy_dst = ar.get<int>((size_t)Nw_max);
@@ -1527,6 +1552,7 @@ void mmt_destroy(mmt_engine* e) {
     for (int i = 0; i < 6; ++i) if (e->enc_ev[i]) cudaEventDestroy(e->enc_ev[i]);
     for (int i = 0; i < 4; ++i) { if (e->cap_stream[i]) cudaStreamDestroy(e->cap_stream[i]); if (e->lane_ev[i]) cudaEventDestroy(e->lane_ev[i]); }
     for (int i = 0; i < 2; ++i) if (e->poll_ev[i]) cudaEventDestroy(e->poll_ev[i]);
+    if (e->last_use) cudaEventDestroy(e->last_use);
     delete e;
 }
 
@@ -1551,7 +1577,7 @@ int32_t mmt_encode(mmt_engine* e, const mmt_spectra* in, int32_t B, uint32_t mod
     if (!(mode_bits & 0xF)) MMT_FAIL("training_mode needs at least one of 1H/13C/HSQC/COSY (the reference crashes without)");
     if (!(mode_bits & MMT_MODE_MW)) MMT_FAIL("training_mode needs MW (the reference crashes without)");
     cudaStream_t s = (cudaStream_t)stream;
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, s);
     const ModeLayout L = mode_layout(e->desc, mode_bits);
     const int chunk = 256;
     for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -1585,7 +1611,7 @@ int32_t mmt_decode(mmt_engine* e, const mmt_decode_args* a, int64_t* d_tokens, f
     if (!e || !a) MMT_FAIL("null engine / args");
     if (!d_tokens) MMT_FAIL("decode: d_tokens is required");
     if (a->sampling != MMT_SAMPLE_GREEDY && a->sampling != MMT_SAMPLE_MULTINOMIAL) MMT_FAIL("bad sampling mode");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     DecodeRun r;
     r.a = a; r.mode = a->sampling; r.trg = nullptr; r.T = a->max_len; r.tokens = d_tokens; r.probs = d_probs; r.logits = nullptr;
     return run_decode(e, r, h_steps, (cudaStream_t)stream);
@@ -1594,7 +1620,7 @@ int32_t mmt_decode(mmt_engine* e, const mmt_decode_args* a, int64_t* d_tokens, f
 int32_t mmt_teacher_forced(mmt_engine* e, const mmt_decode_args* a, const int64_t* d_trg, int32_t T, float* d_logits, void* stream) {
     if (!e || !a || !d_trg || !d_logits) MMT_FAIL("null argument");
     if (T < 1) MMT_FAIL("T must be >= 1");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     DecodeRun r;
     r.a = a; r.mode = 2; r.trg = d_trg; r.T = T; r.tokens = nullptr; r.probs = nullptr; r.logits = d_logits;
     return run_decode(e, r, nullptr, (cudaStream_t)stream);
@@ -1603,14 +1629,14 @@ int32_t mmt_teacher_forced(mmt_engine* e, const mmt_decode_args* a, const int64_
 int32_t mmt_beam_search(mmt_engine* e, const mmt_decode_args* a, int32_t beam_size, int32_t gen_len, int32_t eos,
                         int64_t* d_seq, int32_t* d_len, double* d_score, float* d_probs, int32_t* h_steps, void* stream) {
     if (!e || !a || !d_seq || !d_len || !d_score || !d_probs) MMT_FAIL("null argument");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     return run_beam(e, *a, beam_size, gen_len, eos, d_seq, d_len, d_score, d_probs, h_steps, (cudaStream_t)stream);
 }
 
 int32_t mmt_spectra_equal(mmt_engine* e, const mmt_spectra* a, const mmt_spectra* b, int32_t B, uint32_t mode_bits, int32_t* h_equal, void* stream) {
     if (!e || !a || !b || !h_equal) MMT_FAIL("null argument");
     if (B <= 0) MMT_FAIL("B must be > 0");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     cudaStream_t s = (cudaStream_t)stream;
     const mmt_model_desc& d = e->desc;
     const int64_t P = d.pad_points;
@@ -1650,7 +1676,7 @@ int32_t mmt_teacher_forced_scores(mmt_engine* e, const mmt_decode_args* a, const
     if (T < 1) MMT_FAIL("T must be >= 1");
     if (a->sampling != MMT_SAMPLE_GREEDY && a->sampling != MMT_SAMPLE_MULTINOMIAL) MMT_FAIL("bad sampling mode");
     if ((d_target == nullptr) != (d_target_prob == nullptr)) MMT_FAIL("d_target and d_target_prob go together");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     mmt_decode_args a2 = *a;
     a2.stop_on_all_pad = 0;
     DecodeRun r;
@@ -1709,7 +1735,7 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
                    int64_t* d_token, float* d_prob, float* d_logits_out, void* stream) {
     if (!e || !d_x) MMT_FAIL("null argument");
     if (N <= 0) return 0;
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.x = d_x; sp.W = e->W("fc_out.weight"); sp.b = e->W("fc_out.bias"); sp.V = e->desc.vocab; sp.N = N; sp.ldn = N;
@@ -1734,7 +1760,7 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
     if (!e || !d_A || !d_W || !d_C) MMT_FAIL("null argument");
     if (K % 4) MMT_FAIL("K must be a multiple of 4");
     if (M > 0x7fffffff) MMT_FAIL("M too large");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     cudaStream_t cs = (cudaStream_t)stream;
     if (precision == MMT_PREC_BF16) {   // convert the operands to bf16 in the workspace, then one tcgen05 GEMM
         if (K % TC_BK || N % 4) MMT_FAIL("mmt_linear bf16: K must be a multiple of 64 and N of 4");
@@ -1762,7 +1788,7 @@ int32_t mmt_ffn(mmt_engine* e, const float* d_x, const float* d_w1, const float*
     if (!e || !d_x || !d_w1 || !d_b1 || !d_w2 || !d_b2 || !d_gamma || !d_beta || !d_out) MMT_FAIL("null argument");
     if (M <= 0) return 0;
     if (M > 0x7fffffff) MMT_FAIL("M too large");
-    MMT_CUDA(cudaSetDevice(e->device));
+    EngineCall call(e, (cudaStream_t)stream);
     cudaStream_t cs = (cudaStream_t)stream;
     if (splits < 1) splits = 1;
     const size_t nX = (size_t)M * D, nW = (size_t)F * D;
@@ -1801,6 +1827,7 @@ int64_t mmt_launch_count(const mmt_engine* e) { return e ? e->launches : 0; }
 
 int32_t mmt_profile_enable(mmt_engine* e, int32_t on) {
     if (!e) MMT_FAIL("null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
     for (auto& r : e->prof_records) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     e->prof_records.clear();
     e->profiling = on != 0;
@@ -1809,6 +1836,7 @@ int32_t mmt_profile_enable(mmt_engine* e, int32_t on) {
 
 int32_t mmt_profile_report(mmt_engine* e, char* buf, int64_t buf_len) {
     if (!e || !buf || buf_len < 2) MMT_FAIL("bad profile buffer");
+    std::lock_guard<std::mutex> lk(e->mu);
     MMT_CUDA(cudaSetDevice(e->device));
     MMT_CUDA(cudaDeviceSynchronize());
     struct Agg { int64_t n = 0; double ms = 0, work = 0; };

@@ -1,5 +1,6 @@
 // Host-side engine state: weight registry, workspace arena, launch helpers.
 #pragma once
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -143,6 +144,14 @@ struct mmt_engine {
     bool profiling = false;
     std::pair<cudaEvent_t, cudaEvent_t> prof_open{nullptr, nullptr};
     std::vector<ProfRecord> prof_records;
+
+    // Calls on one engine are serialised (one workspace arena, one pinned staging buffer, one graph cache): every C-ABI
+    // entry that touches the engine holds `mu` for its duration, and a call issued on a different stream than the previous
+    // one first waits (device side) for the event the previous call recorded at its end -- mmt::EngineCall in engine.cu.
+    std::mutex mu;
+    cudaEvent_t last_use = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_use_valid = false;
 
     const float* W(const std::string& name) const { return w32 + reg.slots.at(reg.index.at(name)).off; }
     const __nv_bfloat16* Wb(const float* p) const { return w16 + (p - w32); }

@@ -69,6 +69,12 @@ class MultimodalTransformer(nn.Module):
         """models_MMT_v15_4.py:803-976.  trg None -> (memory, embedding_src, src_padding_mask, fingerprint);
         else -> (output (T,N,V), fingerprint, memory, src_padding_mask)."""
         from .generate import _encode, _mask_to_bias
+        if self.training:
+            # nn.TransformerEncoder/DecoderLayer apply their default dropout=0.1 in train() whatever config.drop_out says,
+            # and the engine's outputs carry no autograd graph: a train-mode forward (either branch; CLIP/BLIP training calls
+            # the trg=None one) would silently return eval-mode, non-differentiable tensors
+            raise RuntimeError("the B200 engine is inference-only: call model.eval() first (train-mode dropout and autograd "
+                               "through the encoder/decoder stacks are not implemented)")
         data = dict(src_1H=src_1H, mask_1H=mask_1H, src_13C=src_13C, mask_13C=mask_13C, src_HSQC=src_HSQC,
                     mask_HSQC=mask_HSQC, src_COSY=src_COSY, mask_COSY=mask_COSY, src_IR=src_IR, mask_IR=mask_IR,
                     src_MF=src_MF, mask_MF=mask_MF, src_MS=src_MS, mask_MS=mask_MS, trg_MW=trg_MW)
@@ -79,8 +85,6 @@ class MultimodalTransformer(nn.Module):
         memory, mask, fingerprint, avg, emb = _encode(eng, data, self.config, want_embedding_src=True, reuse=True)
         if trg_SMI_input is None:
             return memory, emb, mask, fingerprint
-        if self.training and self.config.drop_out > 0:
-            raise RuntimeError("the B200 engine is inference-only: call model.eval() (dropout2 is not implemented)")
         logits = eng.teacher_forced(memory, _mask_to_bias(mask), trg_SMI_input, precision=prec)
         if getattr(self.config, "use_real_data", False):      # :965-971
             rd = eng.linear(avg, self.real_data_linear.weight.detach(), self.real_data_linear.bias.detach())

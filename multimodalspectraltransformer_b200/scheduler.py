@@ -74,6 +74,11 @@ def generate_sharded(model, data_dict, config, stoi, *, n_candidates=1, sampling
     else:
         tok = torch.zeros(T, 0, dtype=torch.int64, device=eng.device)
         pr = torch.zeros(T, 0, dtype=torch.float32, device=eng.device)
+        if sampling != "greedy":
+            # an empty shard draws nothing, but the unsharded run's T multinomial calls would have advanced this device's
+            # generator: keep every rank's Philox offset in step so later sharded calls still reproduce the 1-GPU draws
+            gen = torch.cuda.default_generators[eng.dev_index]
+            gen.set_offset(int(gen.get_offset()) + eng.philox_increment(B * n_candidates) * T)
     packed = eng.pack_tokens(tok) if tok.numel() else torch.zeros(T, 0, dtype=torch.uint8, device=eng.device)
     all_u8 = gather_columns(packed, B * n_candidates, per * n_candidates, group)
     tokens = eng.unpack_tokens(all_u8)

@@ -30,9 +30,13 @@ def _lengths_and_ids(tensor, eos):
     """(T,N) ids on a CUDA device -> (first-EOS position per column as list, ids as a CPU uint8/int64 array)."""
     t = tensor if tensor.dim() == 2 else tensor.unsqueeze(1)
     t = t.to(torch.int64).contiguous()
-    if not t.is_cuda:
-        raise RuntimeError("mmt_b200 post-processing expects the generated ids on the CUDA device (no CPU path)")
     T, N = t.shape
+    if not t.is_cuda:
+        # ids the caller already moved to the host (the reference's helpers take either, helper_functions_pl_v15_4.py:247-301):
+        # the scan is a host-side index computation on data that is already there -- no kernel, nothing copied back and forth
+        is_eos = (t == eos)
+        first = torch.where(is_eos.any(dim=0), is_eos.to(torch.uint8).argmax(dim=0), torch.full((N,), T, dtype=torch.int64))
+        return first.tolist(), t.numpy()
     lens = torch.empty(N, dtype=torch.int32, device=t.device)
     stream = C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
     _lib.check(_lib.lib().mmt_first_eos(t.data_ptr(), T, N, eos, lens.data_ptr(), stream))

@@ -7,8 +7,11 @@ reference uses (Python floats divided in double, ``torch.tensor`` of Python list
     normalize_*              :352-365, 456-460 (1H), 481-485 (13C), 505-509 (HSQC), 546-550 (COSY)
     load_ir                  :324-346   (_load_IR_data: mean binning with Python round(), / max)
 
-Parity status: the reference ships no fixtures for these helpers; this file is a transliteration, checked against
-the CUDA ingest kernels bit for bit (peaks) / to 1 fp32 ulp (IR bins of >= 8 samples, where numpy's pairwise
+Parity status: the reference ships no fixtures for these helpers, so this restatement is PINNED against the unmodified
+reference functions executed through the import shim (``MultimodalData._zero_pad``, ``_normalize_shifts_2D_spectra``,
+``_load_IR_data`` called unbound; oracle/make_golden_ingest.py -> tests/golden/ingest_ref.npz; checked bit for bit in
+tests/test_oracle_golden.py::test_ingest_oracle_matches_reference).  The CUDA ingest kernels are checked against this
+file and against the same golden: bit for bit (peaks) / to 1 fp32 ulp (IR bins of >= 8 samples, where numpy's pairwise
 summation order is not reproduced on the device).
 """
 import numpy as np

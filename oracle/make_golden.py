@@ -44,6 +44,10 @@ CASES = [
     dict(name="mode_ms_max_b2", B=2, seed=19, peaks="max", blank=(), mode="1H_13C_HSQC_COSY_IR_MF_MS_MW", glen=12, mlen=0),
     # MS + ablation: float masks, all ~900 keys of the memory attended (more than the attention kernels stage at once)
     dict(name="mode_ms_hsqc_b2", B=2, seed=20, peaks="realistic", blank=(), mode="HSQC_MF_MS_MW", glen=12, mlen=0),
+    # BASELINE.json config 4 by data blanking (dataloaders_pl_v15_4.py:369-392, 468-470): IR-only = all four NMR peak lists
+    # blanked (zeros + all-ones bool mask; MF + MW keep every row attended), and 1H+13C = both 2-D spectra blanked
+    dict(name="blank_ir_only_b3", B=3, seed=21, peaks="realistic", blank=("1H", "13C", "HSQC", "COSY"), mode="1H_13C_HSQC_COSY_IR_MF_MW", glen=24, mlen=8),
+    dict(name="blank_1h13c_b2", B=2, seed=22, peaks="realistic", blank=("HSQC", "COSY"), mode="1H_13C_HSQC_COSY_IR_MF_MW", glen=16, mlen=0),
 ]
 
 
