@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- generated SMILES tokens/s of the MMT candidate-generation path.
 
-    python bench.py --gpus N --steps K --warmup W            # this framework
-    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU reference arm
+    python bench.py --gpus N --steps K --warmup W                     # this framework
+    python bench.py --impl reference --gpus N --steps K --warmup W    # CPU reference arm (oracle port)
 
-Workload (BASELINE.json configs[1]): config_V8 random-init weights, greedy decode of
-256 synthetic 1H+13C+HSQC+COSY+IR(+MF+MW) spectra per GPU, 128 tokens each.  One
-"step" = encode the 256 spectra + 128 decode positions = 32,768 generated tokens per
-GPU (weak scaling: every rank owns 256 spectra; ids are all-gathered over NCCL).
-Prints ONE JSON line on rank 0 (see the task contract for the keys).
+Workload (BASELINE.json configs[2], the configuration the metric "tokens/s at 1/2/4/8 B200" is quoted on and the
+reference's production call, mmt_result_test_functions_15_4.py:504-570): config_V8 random-init weights, MULTINOMIAL
+sampling of 128 candidates for each of 1024 synthetic 1H+13C+HSQC+COSY+IR(+MF+MW) spectra, 128 tokens each
+= 131,072 sequences, 16,777,216 generated tokens per step.  STRONG scaling: the 1024 spectra are sharded over the N
+ranks by ``scheduler.generate_sharded`` (contiguous blocks, shard-invariant Philox draws), every rank encodes its
+spectra once, decodes its candidates in waves of 16,384 sequences and the ids are all-gathered over NCCL as bytes on a
+side stream (overlapping the next step).  One "step" = encode + every wave + gather for all 1024 spectra.
+
+Extra keys of the JSON line: ``config2`` (BASELINE.json configs[1]: greedy, 256 spectra per GPU x 128 tokens, weak
+scaling, resident and end to end), ``roofline`` (dominant kernel of the main workload), ``cpu_baseline`` and
+``gpu_eager_baseline`` (the oracle port of the reference's full-prefix loop on the host cores / on this B200 under torch
+eager, bounded samples), see DESIGN.md section 5.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -27,10 +35,12 @@ if ROOT not in sys.path:
 
 METRIC = "generated SMILES tokens/sec"
 UNIT = "tokens/s"
-B_PER_GPU = 256
+N_SPECTRA = 1024                # config 3: spectra in the whole job
+N_CAND = 128                    # candidates per spectrum
 MAX_LEN = 128
-REF_SAMPLE_SPECTRA = 32         # --impl reference: spectra per step (a bounded sample of the 256; BASELINE configs[0] uses 8)
-CPU_BASELINE_SPECTRA = 64       # cpu_baseline leg of the main arm: one pass, ~10-30 s of CPU work
+C2_SPECTRA_PER_GPU = 256        # config 2 (extra key): greedy, weak scaling
+REF_SAMPLE_CAND = 16            # CPU arms: candidates of ONE spectrum per step (the reference decodes one spectrum at a time)
+EAGER_SAMPLE_SPECTRA = 8        # gpu_eager_baseline: spectra x 128 candidates under torch eager
 STOI = {"<PAD>": 0, "<UNK>": 1, "<EOS>": 2, "<SOS>": 3, "<MASK>": 4}
 # algorithmic work model (SURVEY.md 8d / BASELINE.md 4)
 FLOP_ENCODE_PER_SPECTRUM = 9.50e9
@@ -44,6 +54,15 @@ def peaks():
         j = json.load(open(p))
         return dict(hbm=j["hbm_gbs"], tf=j["bf16_tflops"], tf_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), src="measured")
     return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def source_hash():
+    """sha256 over the CUDA sources: ties an ncu traffic figure under profiles/ to the build it was captured from."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "multimodalspectraltransformer_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -90,9 +109,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_tokens_per_s(n_spectra, steps=1, warmup=0, threads=None):
-    """The reference's algorithm on the host cores: the oracle port (re-runs the whole
-    prefix each step and re-projects the memory, like validate_generate_MMT_v15_4.py:744-762)."""
+# --------------------------------------------------------------------------------------------- the reference's algorithm
+def reference_flow(P, O, data_one, n_cand, cfg, device="cpu", generator=None):
+    """What the reference does for ONE spectrum (mmt_result_test_functions_15_4.py:519-535): duplicate_dict(x, n) ->
+    run_model on the n identical copies -> multinomial_sequence_multi (full prefix re-run every step, memory
+    re-projected every step).  Oracle port (oracle/mmt_oracle.py), torch ops on `device`."""
+    import torch
+    dup = {k: v.repeat(*([n_cand] + [1] * (v.dim() - 1))).to(device) for k, v in data_one.items()}
+    with torch.no_grad():
+        mem, mask, _, _ = O.encode(P, dup, cfg)
+        tok, _ = O.multinomial_sequence_multi(P, mem, mask, cfg, generator=generator)
+    return tok
+
+
+def cpu_reference_tokens_per_s(steps=1, warmup=0, threads=None):
     import torch
     from oracle import mmt_oracle as O
     from multimodalspectraltransformer_b200 import synthetic
@@ -100,56 +130,62 @@ def cpu_reference_tokens_per_s(n_spectra, steps=1, warmup=0, threads=None):
         torch.set_num_threads(threads)
     cfg = O.default_config()
     P = O.random_init_state_dict(cfg, seed=0)
-    data = synthetic.make_spectra(n_spectra, seed=1000)
-    times = []
+    times, tok = [], None
     for i in range(warmup + steps):
+        data = synthetic.make_spectra(1, seed=1000 + i)
         t0 = time.perf_counter()
-        with torch.no_grad():
-            mem, mask, _, _ = O.encode(P, data, cfg)
-            tok, _ = O.greedy_sequence(P, mem, mask, cfg)
+        tok = reference_flow(P, O, data, REF_SAMPLE_CAND, cfg)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     tokens = tok.numel()
-    return tokens / (sum(times) / len(times)), tokens, sum(times) / len(times), torch.get_num_threads()
+    sec = sum(times) / len(times)
+    return tokens / sec, tokens, sec, torch.get_num_threads()
+
+
+REF_SAMPLE_TEXT = (f"1 of the {N_SPECTRA} spectra x {REF_SAMPLE_CAND} of its {N_CAND} candidates x {MAX_LEN} tokens per step, the reference's own "
+                   "per-spectrum flow (duplicate -> encode the copies -> multinomial loop with full-prefix recompute), fp32, oracle port")
+
+
+def workload_config(n_gpus, precision, ref_sample=False):
+    c = {"workload": f"MMT config_V8 random-init, multinomial sampling, {N_SPECTRA} synthetic spectra x {N_CAND} candidates x {MAX_LEN} tokens "
+                     "(BASELINE.json configs[2]; encode + KV-cached decode in waves of 16,384 sequences + NCCL all-gather of the ids per step)",
+         "spectra_total": N_SPECTRA, "candidates": N_CAND, "max_len": MAX_LEN, "sequences_total": N_SPECTRA * N_CAND,
+         "spectra_per_gpu": (N_SPECTRA + n_gpus - 1) // n_gpus, "peaks": "realistic", "precision": precision,
+         "parallelism": f"dp{n_gpus}",
+         "l2": "no explicit flush: one step streams > 50 GB of self-attention KV pages (6.4 GB pool per 16,384-sequence wave) through the 126 MB L2"}
+    if ref_sample:
+        c["measured_sample"] = REF_SAMPLE_TEXT
+    return c
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
     try:
-        ncores = len(os.sched_getaffinity(0))
+        ncores = len(os.sched_getaffinity(0))        # torchrun exports OMP_NUM_THREADS=1 for its workers: use every core we may
     except AttributeError:
         ncores = os.cpu_count() or 1
     precision = args.precision if args.precision != "auto" else os.environ.get("MMT_DEFAULT_PRECISION", "bf16")
-    v, tokens, sec, threads = cpu_reference_tokens_per_s(REF_SAMPLE_SPECTRA, steps=max(1, args.steps), warmup=min(args.warmup, 1), threads=ncores)
-    sample = f"{REF_SAMPLE_SPECTRA} of the {B_PER_GPU} spectra x {MAX_LEN} steps per step (greedy, fp32, oracle port of the reference loop)"
+    v, tokens, sec, threads = cpu_reference_tokens_per_s(steps=max(1, args.steps), warmup=min(args.warmup, 1), threads=ncores)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(max(1, args.gpus), precision),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(max(1, args.gpus), precision, ref_sample=True),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": REF_SAMPLE_TEXT},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(n_gpus, precision):
-    return {"workload": f"MMT config_V8 random-init, greedy decode, {B_PER_GPU} synthetic spectra per GPU x {MAX_LEN} tokens "
-                        "(encode + KV-cached decode per step)", "spectra_per_gpu": B_PER_GPU, "max_len": MAX_LEN,
-            "peaks": "realistic", "precision": precision, "parallelism": f"dp{n_gpus}",
-            "l2": "explicit 256 MiB L2 flush between timed steps (untimed); per-step working set (cross-K/V + KV pool) also exceeds the 126 MB L2"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MMT_BENCH_PRECISION", "auto"), choices=["auto", "fp32", "bf16"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu / gpu-eager comparator legs")
+    ap.add_argument("--no-config2", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -172,33 +208,12 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = os.environ.get("MMT_DEFAULT_PRECISION", "bf16")      # BASELINE.json configs[1]: bf16 greedy decode
+        precision = os.environ.get("MMT_DEFAULT_PRECISION", "bf16")
     cfg = M.default_config(device=str(dev), precision=precision, max_len=MAX_LEN)
     torch.manual_seed(0)
     model = M.MultimodalTransformer(cfg).eval()
     eng = engine_for(model, cfg)
-    host = synthetic.make_spectra(B_PER_GPU, seed=1000 + rank)
-    pinned = {k: v.pin_memory() for k, v in host.items()}
-    resident = {k: v.to(dev) for k, v in host.items()}
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out_host = torch.empty(MAX_LEN, B_PER_GPU * world, dtype=torch.uint8).pin_memory()
-
-    def gather(tok):
-        packed = eng.pack_tokens(tok)
-        return scheduler.gather_columns(packed, B_PER_GPU * world, B_PER_GPU) if world > 1 else packed
-
-    def step_resident():
-        memory, mask, *_ = M.run_model(model, resident, cfg)
-        tok, pr = M.greedy_sequence(model, STOI, None, memory, mask, cfg)
-        return gather(tok)
-
-    def step_e2e():
-        data = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}     # H2D every step
-        memory, mask, *_ = M.run_model(model, data, cfg)
-        tok, pr = M.greedy_sequence(model, STOI, None, memory, mask, cfg)
-        ids = gather(tok)
-        out_host.copy_(ids, non_blocking=True)                                   # D2H of the step's result
-        return ids
+    torch.manual_seed(1234)                                             # the sampling stream (same on every rank: shard-invariant draws)
 
     def barrier():
         torch.cuda.synchronize()
@@ -206,120 +221,212 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
-        evs = []
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(k):
-            flush_buf.fill_(1)                      # L2 flush, outside the per-step event pair
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            evs.append((a, b))
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, wall
+        return ms
+
+    def timed_pipeline(issue, consume, k, flush=None):
+        """k steps; step i's gathered ids are consumed after step i+1 has been issued, so the collective (side stream) and
+        the rendezvous with the slowest rank overlap the next step.  Device time from CUDA events on the launching stream,
+        barrier + synchronize on both sides, max over ranks.  With `flush` (an L2 flush between steps) every step has its
+        own event pair and the flushes fall between the pairs."""
+        barrier()
+        t0 = time.perf_counter()
+        evs = []
+        prev = None
+        if flush is None:
+            evs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            evs[0][0].record()
+        for _ in range(k):
+            if flush is not None:
+                flush()
+                evs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                evs[-1][0].record()
+            cur = issue()
+            if prev is not None:
+                consume(prev)
+            prev = cur
+            if flush is not None:
+                evs[-1][1].record()
+        if flush is not None:
+            evs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            evs[-1][0].record()
+        consume(prev)
+        evs[-1][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)), wall
+
+    COPIED = ("src_1H", "mask_1H", "src_13C", "mask_13C", "src_HSQC", "src_HSQC", "mask_HSQC", "src_COSY", "src_COSY", "mask_COSY",
+              "src_IR", "src_MF", "mask_MF", "trg_MW", "trg_enc_SMI")      # what run_model moves to the device (HSQC / COSY twice: it also returns them)
+
+    def h2d_bytes(d):
+        return sum(d[k].numel() * d[k].element_size() for k in COPIED)
+
+    # ------------------------------------------------------------------ main workload: config 3, strong scaling
+    host = synthetic.make_spectra(N_SPECTRA, seed=1000)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    out_host = torch.empty(N_SPECTRA * N_CAND, MAX_LEN, dtype=torch.uint8).pin_memory()
+    lo, hi = scheduler.shard_bounds(N_SPECTRA, world, rank)
+
+    def issue_resident():
+        return scheduler.generate_sharded(model, resident, cfg, STOI, n_candidates=N_CAND, sampling="multinomial", async_gather=True)
+
+    def issue_e2e():        # host buffers in: generate_sharded slices this rank's spectra, run_model copies them to the device
+        return scheduler.generate_sharded(model, pinned, cfg, STOI, n_candidates=N_CAND, sampling="multinomial", async_gather=True)
+
+    def consume_resident(p):
+        p.packed()
+
+    def consume_e2e(p):     # device -> host read of the step's result (the gathered ids, bytes)
+        out_host.copy_(p.packed(), non_blocking=True)
 
     for _ in range(W):
-        step_resident()
-    for _ in range(W):
-        step_e2e()
+        consume_resident(issue_resident())
+    consume_e2e(issue_e2e())
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count()
-    ms_res, wall_res = timed(step_resident, K)
+    ms_res, wall_res = timed_pipeline(issue_resident, consume_resident, K)
     launches = eng.launch_count() - l0
-    ms_e2e, wall_e2e = timed(step_e2e, K)
+    ms_e2e, wall_e2e = timed_pipeline(issue_e2e, consume_e2e, K)
     clocks = sampler.stop() if rank == 0 else None
-
-    tokens_per_step = MAX_LEN * B_PER_GPU * world
+    if world > 1:
+        t = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        launches = int(t.item())
+    tokens_per_step = MAX_LEN * N_SPECTRA * N_CAND
     value = tokens_per_step * K / (ms_res / 1e3)
     e2e_value = tokens_per_step * K / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
-    d2h = out_host.numel() * out_host.element_size()
+    h2d = h2d_bytes(pinned)
+    d2h = out_host.numel() * out_host.element_size() * world
 
-    # ---- roofline of the dominant kernel: per-kernel-class device time, CUDA events on the launching stream
-    eng.profile(True)
-    flush_buf.fill_(1)
-    memory, mask, *_ = M.run_model(model, resident, cfg)
-    tok, _ = M.greedy_sequence(model, STOI, None, memory, mask, cfg)
-    prof = eng.profile_report()
-    eng.profile(False)
+    # ------------------------------------------------------------------ config 2 (extra key): greedy, 256 spectra per GPU, weak scaling
+    c2 = None
+    if not args.no_config2:
+        K2 = min(K, 10)
+        host2 = synthetic.make_spectra(C2_SPECTRA_PER_GPU * world, seed=2000)
+        pinned2 = {k: v.pin_memory() for k, v in host2.items()}
+        resident2 = {k: v.to(dev) for k, v in host2.items()}
+        out2 = torch.empty(C2_SPECTRA_PER_GPU * world, MAX_LEN, dtype=torch.uint8).pin_memory()
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        g_res = lambda: scheduler.generate_sharded(model, resident2, cfg, STOI, n_candidates=1, sampling="greedy", async_gather=True)
+        g_e2e = lambda: scheduler.generate_sharded(model, pinned2, cfg, STOI, n_candidates=1, sampling="greedy", async_gather=True)
+        for _ in range(W):
+            g_res().packed()
+        g_e2e().packed()
+        l0 = eng.launch_count()
+        ms2, _ = timed_pipeline(g_res, lambda p: p.packed(), K2, flush=lambda: flush_buf.fill_(1))
+        launches2 = eng.launch_count() - l0
+        ms2e, _ = timed_pipeline(g_e2e, lambda p: out2.copy_(p.packed(), non_blocking=True), K2, flush=lambda: flush_buf.fill_(1))
+        tok2 = MAX_LEN * C2_SPECTRA_PER_GPU * world
+        c2 = {"workload": f"BASELINE.json configs[1]: greedy decode, {C2_SPECTRA_PER_GPU} spectra per GPU x {MAX_LEN} tokens, weak scaling, "
+                          "explicit 256 MiB L2 flush between steps (untimed)",
+              "value": tok2 * K2 / (ms2 / 1e3), "unit": UNIT, "ms_per_step": ms2 / K2, "steps": K2, "scaling": "weak",
+              "e2e": {"value": tok2 * K2 / (ms2e / 1e3), "unit": UNIT, "ms_per_step": ms2e / K2,
+                      "h2d_bytes_per_step": h2d_bytes(pinned2),
+                      "d2h_bytes_per_step": out2.numel() * world},
+              "gpu_launches_per_rank": launches2,
+              "frac_bf16_tensor_peak": tok2 * K2 / (ms2 / 1e3) / world
+              * (FLOP_DECODE_PER_TOKEN + (FLOP_ENCODE_PER_SPECTRUM + FLOP_CROSSKV_PER_SPECTRUM) / MAX_LEN) / (peaks()["tf"] * 1e12)}
+        del flush_buf
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (rank 0's GPU)
     pk = peaks()
-    total_ms = sum(v["ms"] for v in prof.values())
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    esz = 4 if precision == "fp32" else 2       # KV-cache element size (bf16 caches in the tensor-core mode)
-    n_valid = int((~mask.bool()).sum().item()) if mask.dtype == torch.bool else mask.numel()
-    N = B_PER_GPU
-    kv_cross = n_valid * 2 * 128 * esz + n_valid * 4                  # K and V rows of the un-masked memory keys (+ key bias)
-    kv_self = N * ((MAX_LEN + 1) / 2) * 2 * 128 * esz                 # mean over steps of the self-attention cache read
-    attn_w = (3 * 128 * 128 + 3 * 128 * 128 + 13 * 128) * 4           # in_proj, out_proj, cross q / out proj, vectors (read once)
-    alg_bytes = {
-        # one decoder layer, one position: cross K/V + self K/V + weights + x in / x2 out (fp32 + bf16)
-        "decode_attn": kv_cross + kv_self + attn_w + N * 128 * (4 + 4 + 2),
-        "decode_cross_attention": kv_cross + N * 128 * 4 * 2,
-        "decode_self_attention": kv_self + N * 3 * 128 * 4 + N * 128 * 4,
-        "bias_res_layernorm": None, "sample_tokens": None,
-    }
-    d = prof[dom]
-    per_launch_ms = d["ms"] / d["launches"]
-    if d.get("flops", 0) > 0:
-        achieved = d["flops"] / d["launches"] / (per_launch_ms * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved / pk["tf"],
-                "traffic": None, "peak_source": pk["src"] + " bf16 burst", "note": "fp32 SIMT check-mode GEMM measured against the bf16 tensor peak" if precision == "fp32" else ""}
-    elif alg_bytes.get(dom):
-        achieved = alg_bytes[dom] / (per_launch_ms * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                "traffic": None, "peak_source": pk["src"]}
-    else:
-        roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
-    try:     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        if dom in tj and precision == "bf16":
-            roof["traffic"] = tj[dom]["dram_bytes_read"] + tj[dom]["dram_bytes_write"]
-            roof["traffic_source"] = "profiles/r01_ncu_traffic.json (one ncu --set full capture of this command)"
-            roof["algorithmic_bytes_per_launch"] = alg_bytes.get(dom)
-    except (OSError, ValueError, KeyError):
-        pass
-    roof["share_of_step"] = d["ms"] / total_ms if total_ms else None
-    roof["launch_us"] = per_launch_ms * 1e3
-    roof["kernels"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-
-    line = None
+    roof = None
     if rank == 0:
-        flop_per_token = FLOP_DECODE_PER_TOKEN + (FLOP_ENCODE_PER_SPECTRUM + FLOP_CROSSKV_PER_SPECTRUM) / MAX_LEN
+        wave = min(128, hi - lo)
+        data_w = {k: v[:wave] for k, v in resident.items()}
+        eng.profile(True)
+        memory, mask, *_ = M.run_model(model, data_w, cfg)
+        M.multinomial_sequence_multi(model, memory, mask, STOI, cfg, n_candidates=N_CAND)
+        prof = eng.profile_report()
+        eng.profile(False)
+        total_ms = sum(v["ms"] for v in prof.values())
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        esz = 4 if precision == "fp32" else 2
+        Nw = wave * N_CAND
+        n_valid = int((~mask.bool()).sum().item()) if mask.dtype == torch.bool else mask.numel()
+        kv_self = Nw * ((MAX_LEN + 1) / 2) * 2 * 128 * esz                # mean over positions of the cache read (t + 1 rows of K and V)
+        kv_cross = n_valid * 2 * 128 * esz + n_valid * 4                  # shared by the 128 candidates of a spectrum
+        alg_bytes = {
+            # per launch = one decoder layer, one position, one wave: DESIGN.md section 5
+            "decode_self_attention": kv_self + Nw * 2 * 128 * esz + Nw * 3 * 128 * 4 + Nw * 128 * 2,   # cache read + append + qkv in + att out
+            "decode_layer": kv_self + Nw * 2 * 128 * esz + kv_cross + Nw * 128 * (4 + 4 + 2),
+            "decode_cross_attention": kv_cross + Nw * 128 * 4 + Nw * 128 * 2,
+            "decode_attn": kv_cross + kv_self + Nw * 128 * (4 + 4 + 2),
+        }
+        d = prof[dom]
+        per_launch_ms = d["ms"] / d["launches"]
+        if d.get("flops", 0) > 0:
+            achieved = d["flops"] / d["launches"] / (per_launch_ms * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s", "frac": achieved / pk["tf"],
+                    "traffic": None, "peak_source": pk["src"] + " bf16 burst"}
+        elif alg_bytes.get(dom):
+            achieved = alg_bytes[dom] / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                    "traffic": None, "peak_source": pk["src"], "algorithmic_bytes_per_launch": alg_bytes[dom]}
+        else:
+            roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+        roof["profile_mode"] = (f"one wave ({wave} spectra x {N_CAND} candidates = {Nw} sequences x {MAX_LEN} positions) + its encode, eager launches "
+                                "bracketed by CUDA events on the launching stream (the timed loop replays the same kernels as CUDA graphs)")
+        try:     # DRAM bytes per launch from an ncu --set full capture -- only if it was taken from THIS build of the kernels
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+            if tj.get("source_hash") == source_hash() and dom in tj.get("kernels", {}):
+                kj = tj["kernels"][dom]
+                roof["traffic"] = kj["dram_bytes_read"] + kj["dram_bytes_write"]
+                roof["traffic_source"] = f"profiles/r02_ncu_traffic.json ({kj.get('note', 'ncu --set full')}; same source hash as this build)"
+            else:
+                roof["traffic_source"] = "none: profiles/r02_ncu_traffic.json was captured from another build (source hash differs)"
+        except (OSError, ValueError, KeyError):
+            pass
+        roof["share_of_step"] = d["ms"] / total_ms if total_ms else None
+        roof["launch_us"] = per_launch_ms * 1e3
+        roof["kernels"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    if rank == 0:
+        flop_per_token = FLOP_DECODE_PER_TOKEN + (FLOP_ENCODE_PER_SPECTRUM + FLOP_CROSSKV_PER_SPECTRUM) / (N_CAND * MAX_LEN)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic", "config": workload_config(world, precision),
                 "frac_bf16_tensor_peak": value / world * flop_per_token / (pk["tf"] * 1e12),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "wall_s": {"resident": wall_res, "e2e": wall_e2e}}
+        if c2 is not None:
+            line["config2"] = c2
         if world == 1 and not args.no_cpu_baseline:
-            # informational, outside every timed region: one candidate wave of BASELINE.json config 3 (multinomial, 128 spectra x
-            # 128 candidates sharing each spectrum's cross K/V = 16,384 sequences x 128 tokens, decode only, memory resident)
-            try:
-                mem128, mask128 = memory[:, :128], mask[:128]
-                stoi = {"<SOS>": 3}
-                M.multinomial_sequence_multi(model, mem128, mask128, stoi, cfg, n_candidates=128)
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-                M.multinomial_sequence_multi(model, mem128, mask128, stoi, cfg, n_candidates=128)
-                ev1.record()
-                torch.cuda.synchronize()
-                ms3 = ev0.elapsed_time(ev1)
-                line["config3_wave"] = {"value": 128 * 128 * MAX_LEN / (ms3 * 1e-3), "unit": UNIT, "ms": ms3,
-                                        "workload": "multinomial decode, 128 spectra x 128 candidates x 128 tokens (one 16,384-sequence wave of config 3)"}
-            except Exception as exc:      # never let the extra measurement cost the bench line
-                line["config3_wave"] = {"error": str(exc)[:200]}
-            v, toks, sec, threads = cpu_reference_tokens_per_s(CPU_BASELINE_SPECTRA, steps=1, warmup=0)
+            try:     # the reference's algorithm under torch eager on this same B200 (library kernels): how much is the GPU, how much the engine
+                from oracle import mmt_oracle as O
+                ocfg = O.default_config()
+                Pd = {k: v.to(dev) for k, v in O.random_init_state_dict(ocfg, seed=0).items()}
+                d8 = synthetic.make_spectra(EAGER_SAMPLE_SPECTRA, seed=1000)
+                dup = {k: v.repeat_interleave(N_CAND, dim=0).to(dev) for k, v in d8.items()}
+                with torch.no_grad():
+                    O.encode(Pd, {k: v[:N_CAND] for k, v in dup.items()}, ocfg)             # warm-up (cuBLAS handles, kernels)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    mem, msk, _, _ = O.encode(Pd, dup, ocfg)
+                    tok_e, _ = O.multinomial_sequence_multi(Pd, mem, msk, ocfg)
+                    torch.cuda.synchronize()
+                    sec = time.perf_counter() - t0
+                v_eager = tok_e.numel() / sec
+                line["gpu_eager_baseline"] = {
+                    "value": v_eager, "unit": UNIT, "kind": "port", "seconds": sec,
+                    "sample": f"{EAGER_SAMPLE_SPECTRA} of the {N_SPECTRA} spectra x {N_CAND} candidates x {MAX_LEN} tokens in ONE batch of {EAGER_SAMPLE_SPECTRA * N_CAND} sequences "
+                              "(8x the reference's own batch), fp32, oracle port of the reference's loop (encode the duplicated copies, full-prefix "
+                              "decoder re-run and memory re-projection every step) as torch 2.11 eager ops on this B200",
+                    "engine_over_eager": value / v_eager}
+                del Pd, dup, mem, msk
+            except Exception as exc:      # never let a comparator cost the bench line
+                line["gpu_eager_baseline"] = {"error": str(exc)[:200]}
+            v, toks, sec, threads = cpu_reference_tokens_per_s(steps=1, warmup=0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{CPU_BASELINE_SPECTRA} of the {B_PER_GPU} spectra x {MAX_LEN} greedy steps ({toks} tokens, {sec:.1f} s) of the same workload, "
-                                              "oracle port of the reference's full-prefix loop on the host cores"}
+                                    "sample": REF_SAMPLE_TEXT + f" ({toks} tokens, {sec:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -216,6 +216,13 @@ uint64_t mmt_philox_increment(int64_t numel, int32_t sm_count, int32_t max_threa
 int32_t mmt_pack_tokens_u8(const int64_t* d_tokens, int64_t n, uint8_t* d_out, void* stream);
 int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, void* stream);
 
+/* The same payload in SEQUENCE-MAJOR order: (T,N) i64 ids -> (N,T) u8, and back.  Ranks own contiguous blocks of
+ * sequences, so an all-gather of (N_local,T) blocks lands directly in the final (N_total,T) order -- no re-layout copy
+ * after the collective (the time-major form interleaves the ranks' columns).  The inverse reads `N` rows of the
+ * gathered (>= N, T) buffer and writes the caller-facing (T,N) i64 tensor (tiled transposes through shared memory). */
+int32_t mmt_pack_tokens_u8_seqmajor(const int64_t* d_tokens, int32_t T, int64_t N, uint8_t* d_out, void* stream);
+int32_t mmt_unpack_tokens_u8_seqmajor(const uint8_t* d_in, int32_t T, int64_t N, int64_t* d_tokens, void* stream);
+
 /* ---- ragged ingest (the data format in front of the path) -------------------------- */
 
 /* Replaces MultimodalData._zero_pad + the per-modality normalisation of __getitem__
@@ -245,6 +252,20 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
                    uint64_t philox_seed, uint64_t philox_offset, int64_t seq_index_base, int64_t N_total,
                    int32_t rng_sm_count, int32_t rng_max_threads_per_sm,
                    int64_t* d_token, float* d_prob, float* d_logits_out, void* stream);
+
+/* The Exp(1) variates torch's CUDA `exponential_` writes (ATen DistributionTemplates.h:427-441 through
+ * torch.multinomial's fast path): d_q[i] = the variate at linear element elem_base + i of a
+ * tensor of numel_total elements under generator state (seed, offset) on a device with sm_count SMs of
+ * max_threads_per_sm threads.  Lets a test assert BIT equality with torch.empty(...).exponential_(). */
+int32_t mmt_exponential(uint64_t philox_seed, uint64_t philox_offset, int64_t elem_base, int64_t n, int64_t numel_total,
+                        int32_t sm_count, int32_t max_threads_per_sm, float* d_q, void* stream);
+
+/* torch.multinomial(p, 1) on caller-supplied probabilities d_p (N,V) f32: token = first arg-max of p / q with q as
+ * above (rows seq_index_base .. seq_index_base+N of a logical (N_total,V) call).  With torch's own p as input the
+ * ids must equal torch.multinomial's exactly -- separates the RNG stream from probability round-off. */
+int32_t mmt_sample_probs(const float* d_p, int64_t N, int32_t V, uint64_t philox_seed, uint64_t philox_offset,
+                         int64_t seq_index_base, int64_t N_total, int32_t sm_count, int32_t max_threads_per_sm,
+                         int64_t* d_token, void* stream);
 
 /* C[M,N] = act(A[M,K] . W[N,K]^T + bias) in the requested precision
  * (fp32 SIMT or bf16 tcgen05); act: 0 none, 1 ReLU. */

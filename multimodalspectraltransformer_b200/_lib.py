@@ -24,7 +24,7 @@ EXPORTS = [
     "mmt_abi_version", "mmt_last_error", "mmt_weight_count", "mmt_weight_name", "mmt_weight_numel",
     "mmt_weight_offset", "mmt_weight_total", "mmt_create", "mmt_destroy", "mmt_memory_len",
     "mmt_mask_is_float", "mmt_encode", "mmt_spectra_equal", "mmt_decode", "mmt_teacher_forced", "mmt_teacher_forced_scores", "mmt_beam_search", "mmt_philox_increment",
-    "mmt_pack_tokens_u8", "mmt_unpack_tokens_u8", "mmt_first_eos", "mmt_ingest_peaks", "mmt_ingest_ir", "mmt_sample", "mmt_linear", "mmt_ffn", "mmt_launch_count",
+    "mmt_pack_tokens_u8", "mmt_unpack_tokens_u8", "mmt_pack_tokens_u8_seqmajor", "mmt_unpack_tokens_u8_seqmajor", "mmt_first_eos", "mmt_ingest_peaks", "mmt_ingest_ir", "mmt_sample", "mmt_exponential", "mmt_sample_probs", "mmt_linear", "mmt_ffn", "mmt_launch_count",
     "mmt_profile_enable", "mmt_profile_report",
 ]
 
@@ -157,11 +157,15 @@ def lib():
     L.mmt_philox_increment.argtypes = [i64, i32, i32]; L.mmt_philox_increment.restype = u64
     L.mmt_pack_tokens_u8.argtypes = [vp, i64, vp, vp]; L.mmt_pack_tokens_u8.restype = i32
     L.mmt_unpack_tokens_u8.argtypes = [vp, i64, vp, vp]; L.mmt_unpack_tokens_u8.restype = i32
+    L.mmt_pack_tokens_u8_seqmajor.argtypes = [vp, i32, i64, vp, vp]; L.mmt_pack_tokens_u8_seqmajor.restype = i32
+    L.mmt_unpack_tokens_u8_seqmajor.argtypes = [vp, i32, i64, vp, vp]; L.mmt_unpack_tokens_u8_seqmajor.restype = i32
     L.mmt_ingest_peaks.argtypes = [vp, vp, i32, i32, C.c_double, C.c_double, i32, vp, vp, vp]; L.mmt_ingest_peaks.restype = i32
     L.mmt_ingest_ir.argtypes = [vp, vp, i32, i32, vp, vp]; L.mmt_ingest_ir.restype = i32
     L.mmt_first_eos.argtypes = [vp, i32, i64, i32, vp, vp]; L.mmt_first_eos.restype = i32
     L.mmt_sample.argtypes = [vp, vp, i64, f32, i32, u64, u64, i64, i64, i32, i32, vp, vp, vp, vp]
     L.mmt_sample.restype = i32
+    L.mmt_exponential.argtypes = [u64, u64, i64, i64, i64, i32, i32, vp, vp]; L.mmt_exponential.restype = i32
+    L.mmt_sample_probs.argtypes = [vp, i64, i32, u64, u64, i64, i64, i32, i32, vp, vp]; L.mmt_sample_probs.restype = i32
     L.mmt_linear.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]; L.mmt_linear.restype = i32
     L.mmt_ffn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]; L.mmt_ffn.restype = i32
     L.mmt_launch_count.argtypes = [vp]; L.mmt_launch_count.restype = i64

@@ -1153,7 +1153,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     if ((a.stride_s % 4) || (a.stride_b % 4) || ((uintptr_t)a.d_memory % 16)) MMT_FAIL("decode: memory must be 16-byte aligned with strides that are multiples of 4 floats");
     const int64_t N_total = (int64_t)a.Bm * a.n_cand;
     // waves: bound the self-attention KV pool (fp32: max_len*6*2*128*4 B per sequence)
-    const int64_t max_wave_seqs = 16384;
+    const int64_t max_wave_seqs = e->max_wave_seqs;
     int Bm_wave = (int)std::max<int64_t>(1, std::min<int64_t>(a.Bm, max_wave_seqs / a.n_cand));
     const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
     if (a.precision != MMT_PREC_FP32 && a.precision != MMT_PREC_BF16) MMT_FAIL("decode: bad precision");
@@ -1519,6 +1519,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (const char* v = getenv("MMT_FFN_SPLITS")) { int k = atoi(v); if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) e->ffn_splits_override = k; }
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
+    if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };
     if (cudaMalloc(&e->w32, n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc weights failed");
@@ -1702,6 +1703,21 @@ int32_t mmt_unpack_tokens_u8(const uint8_t* d_in, int64_t n, int64_t* d_tokens, 
     return 0;
 }
 
+int32_t mmt_pack_tokens_u8_seqmajor(const int64_t* d_tokens, int32_t T, int64_t N, uint8_t* d_out, void* stream) {
+    if (N <= 0 || T <= 0) return 0;
+    if (!d_tokens || !d_out) MMT_FAIL("null argument");
+    pack_tokens_u8_seqmajor<<<dim3((unsigned)((N + 31) / 32), (unsigned)((T + 31) / 32)), 256, 0, (cudaStream_t)stream>>>(d_tokens, T, N, d_out);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+int32_t mmt_unpack_tokens_u8_seqmajor(const uint8_t* d_in, int32_t T, int64_t N, int64_t* d_tokens, void* stream) {
+    if (N <= 0 || T <= 0) return 0;
+    if (!d_in || !d_tokens) MMT_FAIL("null argument");
+    unpack_tokens_u8_seqmajor<<<dim3((unsigned)((N + 31) / 32), (unsigned)((T + 31) / 32)), 256, 0, (cudaStream_t)stream>>>(d_in, T, N, d_tokens);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int32_t mmt_ingest_peaks(const double* d_values, const int64_t* d_offsets, int32_t B, int32_t cols, double div0, double div1,
                          int32_t pad_points, float* d_src, float* d_mask, void* stream) {
     if (!d_values || !d_offsets || !d_src || !d_mask) MMT_FAIL("null argument");
@@ -1753,6 +1769,33 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
     prof_pre(e, cs);
     sample_tokens<<<(unsigned)((N + 7) / 8), 256, 0, cs>>>(sp);
     return check_launch(e, "sample_tokens", cs);
+}
+
+int32_t mmt_exponential(uint64_t philox_seed, uint64_t philox_offset, int64_t elem_base, int64_t n, int64_t numel_total,
+                        int32_t sm_count, int32_t max_threads_per_sm, float* d_q, void* stream) {
+    if (!d_q) MMT_FAIL("null argument");
+    if (n <= 0) return 0;
+    if (sm_count <= 0 || max_threads_per_sm < 256 || numel_total < elem_base + n || elem_base < 0) MMT_FAIL("mmt_exponential: bad geometry");
+    RngGeom g;
+    g.seed = philox_seed; g.offset = philox_offset; g.numel = numel_total; g.threads = torch_rng_threads(numel_total, sm_count, max_threads_per_sm);
+    exponential_fill<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, elem_base, n, d_q);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int32_t mmt_sample_probs(const float* d_p, int64_t N, int32_t V, uint64_t philox_seed, uint64_t philox_offset,
+                         int64_t seq_index_base, int64_t N_total, int32_t sm_count, int32_t max_threads_per_sm,
+                         int64_t* d_token, void* stream) {
+    if (!d_p || !d_token) MMT_FAIL("null argument");
+    if (N <= 0) return 0;
+    if (V < 1 || sm_count <= 0 || max_threads_per_sm < 256 || seq_index_base < 0) MMT_FAIL("mmt_sample_probs: bad geometry");
+    const int64_t Nrng = N_total > 0 ? N_total : N;
+    if (Nrng < seq_index_base + N) MMT_FAIL("mmt_sample_probs: N_total smaller than seq_index_base + N");
+    RngGeom g;
+    g.seed = philox_seed; g.offset = philox_offset; g.numel = Nrng * V; g.threads = torch_rng_threads(g.numel, sm_count, max_threads_per_sm);
+    sample_from_probs<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_p, N, V, g, seq_index_base, d_token);
+    MMT_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const float* d_bias, float* d_C,

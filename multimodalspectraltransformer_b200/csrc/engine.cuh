@@ -118,6 +118,7 @@ struct mmt_engine {
     int64_t launches = 0;
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
+    int max_wave_seqs = 16384;         // sequences decoded together; larger runs go wave by wave (bounds the self-attention KV pool; MMT_MAX_WAVE_SEQS overrides)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int64_t launches_per_group; uint64_t stamp; };
     std::vector<GraphEntry> graph_cache;   // instantiated decode-step graphs of single-wave runs (staged outputs), keyed by what their nodes bake in

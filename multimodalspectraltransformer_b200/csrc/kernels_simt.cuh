@@ -1381,6 +1381,32 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
     }
 }
 
+// q[i] = the Exp(1) variate torch's exponential_ writes at linear element base + i (unit-test hook, mmt_exponential)
+__global__ void __launch_bounds__(256) exponential_fill(RngGeom g, int64_t base, int64_t n, float* q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[i] = torch_exponential_at(g, base + i);
+}
+
+// token[n] = first arg-max over v of p[n][v] / q[(base + n) * V + v]   (torch.multinomial(p, 1) on given probabilities)
+__global__ void __launch_bounds__(256) sample_from_probs(const float* p, int64_t N, int V, RngGeom g, int64_t seq_base, int64_t* token) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    float best = MMT_NEG_INF;
+    int bi = 0x7fffffff;
+    for (int v = lane; v < V; v += 32) {
+        const float r = p[n * V + v] / torch_exponential_at(g, (seq_base + n) * V + v);
+        if (r > best) { best = r; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) token[n] = bi;
+}
+
 // len[n] = index of the first `eos` in column n of tokens (T, N), or T when there is none
 // (the truncation rule of helper_functions_pl_v15_4.py:272-301, 390-419).  One thread per sequence; rows are
 // contiguous over n, so every step of the scan is a coalesced read.
@@ -1469,6 +1495,29 @@ __global__ void pack_tokens_u8(const int64_t* in, int64_t n, uint8_t* out) {
 __global__ void unpack_tokens_u8(const uint8_t* in, int64_t n, int64_t* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int64_t)in[i];
+}
+// (T,N) i64 -> (N,T) u8 and (N,T) u8 -> (T,N) i64: 32 x 32 tiles through shared memory, both sides coalesced
+__global__ void __launch_bounds__(256) pack_tokens_u8_seqmajor(const int64_t* in, int T, int64_t N, uint8_t* out) {
+    __shared__ uint8_t tile[32][33];
+    const int64_t n0 = (int64_t)blockIdx.x * 32;
+    const int t0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        if (t0 + r < T && n0 + tx < N) tile[r][tx] = (uint8_t)in[(int64_t)(t0 + r) * N + n0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (n0 + r < N && t0 + tx < T) out[(n0 + r) * T + t0 + tx] = tile[tx][r];
+}
+__global__ void __launch_bounds__(256) unpack_tokens_u8_seqmajor(const uint8_t* in, int T, int64_t N, int64_t* out) {
+    __shared__ uint8_t tile[32][33];
+    const int64_t n0 = (int64_t)blockIdx.x * 32;
+    const int t0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        if (n0 + r < N && t0 + tx < T) tile[r][tx] = in[(n0 + r) * T + t0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (t0 + r < T && n0 + tx < N) out[(int64_t)(t0 + r) * N + n0 + tx] = (int64_t)tile[tx][r];
 }
 __global__ void f32_to_bf16(const float* in, int64_t n, __nv_bfloat16* out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

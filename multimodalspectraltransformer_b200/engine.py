@@ -299,6 +299,22 @@ class Engine:
                                      lg.data_ptr() if lg is not None else None, self._stream()))
         return tok, pr, lg
 
+    def exponential(self, n, *, seed, offset, elem_base=0, numel_total=0):
+        """The Exp(1) variates torch.empty(numel_total).exponential_() holds at [elem_base, elem_base + n) (test hook)."""
+        q = torch.empty(n, device=self.device, dtype=torch.float32)
+        _lib.check(self.L.mmt_exponential(seed, offset, elem_base, n, numel_total or n, self.sm_count, self.max_threads_per_sm,
+                                          q.data_ptr(), self._stream()))
+        return q
+
+    def sample_probs(self, p, *, seed, offset, seq_index_base=0, n_total=0):
+        """torch.multinomial(p, 1) on given probabilities p (N,V) under generator state (seed, offset) (test hook)."""
+        p = p.to(self.device, torch.float32).contiguous()
+        N, V = p.shape
+        tok = torch.empty(N, device=self.device, dtype=torch.int64)
+        _lib.check(self.L.mmt_sample_probs(p.data_ptr(), N, V, seed, offset, seq_index_base, n_total, self.sm_count,
+                                           self.max_threads_per_sm, tok.data_ptr(), self._stream()))
+        return tok
+
     def linear(self, A, W, bias=None, act=0, precision="fp32"):
         A = A.to(self.device, torch.float32).contiguous()
         W = W.to(self.device, torch.float32).contiguous()
@@ -322,6 +338,23 @@ class Engine:
         tokens = tokens.contiguous()
         out = torch.empty(tokens.shape, device=self.device, dtype=torch.uint8)
         _lib.check(self.L.mmt_pack_tokens_u8(tokens.data_ptr(), tokens.numel(), out.data_ptr(), self._stream()))
+        return out
+
+    def pack_tokens_seqmajor(self, tokens, out=None):
+        """(T,N) i64 ids -> (N,T) u8 (the scheduler's all-gather payload: rank blocks land in their final order)."""
+        tokens = tokens.contiguous()
+        T, N = tokens.shape
+        if out is None:
+            out = torch.empty(N, T, device=self.device, dtype=torch.uint8)
+        _lib.check(self.L.mmt_pack_tokens_u8_seqmajor(tokens.data_ptr(), T, N, out.data_ptr(), self._stream()))
+        return out
+
+    def unpack_tokens_seqmajor(self, packed, n):
+        """First ``n`` rows of a (>= n, T) u8 buffer -> (T,n) i64."""
+        packed = packed.contiguous()
+        T = packed.shape[1]
+        out = torch.empty(T, n, device=self.device, dtype=torch.int64)
+        _lib.check(self.L.mmt_unpack_tokens_u8_seqmajor(packed.data_ptr(), T, n, out.data_ptr(), self._stream()))
         return out
 
     def unpack_tokens(self, packed):

@@ -266,16 +266,20 @@ def teacher_forced_logits(P, memory, mask, tokens, config):
     return F.linear(out, P["fc_out.weight"], P["fc_out.bias"])
 
 
-def _decode_loop(P, memory, mask, config, pick, stop_on_all_pad, sos=3, max_len=None):
+def _decode_loop(P, memory, mask, config, pick, stop_on_all_pad, sos=3, max_len=None, margins=None):
     """Shared body of greedy_sequence / multinomial_sequence(_multi): every step
     re-runs the decoder on the whole prefix and samples from position -1
-    (validate_generate_MMT_v15_4.py:744-764, 861-875)."""
+    (validate_generate_MMT_v15_4.py:744-764, 861-875).  ``margins`` (a list) receives, per step, the (N,) top-2 logit
+    margin of position -1 relative to the row's max |logit| (test bookkeeping for the near-tie rules; not reference code)."""
     N = memory.shape[1]
     dev = memory.device
     tokens = torch.full((1, N), sos, dtype=torch.long, device=dev)
     probs = []
     for _ in range(max_len or config.max_len):
         logits = teacher_forced_logits(P, memory, mask, tokens, config)
+        if margins is not None:
+            top2 = torch.topk(logits[-1], 2, dim=1).values
+            margins.append((top2[:, 0] - top2[:, 1]) / logits[-1].abs().amax(dim=1))
         p = torch.softmax(logits[-1] / config.temperature, dim=1)
         nxt = pick(p)
         probs.append(p.gather(1, nxt.unsqueeze(1)).squeeze(1))
@@ -289,6 +293,13 @@ def greedy_sequence(P, memory, mask, config, max_len=None):
     """validate_generate_MMT_v15_4.py:723-775 -> ((T,N) i64, (T-1,N) f32)."""
     tok, pr = _decode_loop(P, memory, mask, config, lambda p: torch.argmax(p, dim=1), True, max_len=max_len)
     return tok, pr[1:]
+
+
+def greedy_sequence_with_margins(P, memory, mask, config, max_len=None):
+    """greedy_sequence plus the relative top-2 logit margin of every pick: ((T,N) i64, (T-1,N) f32, (T,N) f32)."""
+    m = []
+    tok, pr = _decode_loop(P, memory, mask, config, lambda p: torch.argmax(p, dim=1), True, max_len=max_len, margins=m)
+    return tok, pr[1:], torch.stack(m)
 
 
 def multinomial_sequence(P, memory, mask, config, generator=None, max_len=None):

@@ -84,12 +84,41 @@ def test_sampler_multinomial_reproduces_torch_philox_stream(N):
     inc = gen.get_offset() - off
     assert inc == s["eng"].philox_increment(N)
     tok, pr, _ = s["eng"].sample(x, sampling="multinomial", seed=seed, offset=off)
+    # (a) the RNG stream alone: torch's own probabilities through our Philox mapping -> torch's ids, all of them
+    assert torch.equal(s["eng"].sample_probs(p, seed=seed, offset=off), want)
+    # (b) the fused kernel computes fc_out + softmax itself (fp32 FMA order differs from cuBLAS by an ulp or two): every id
+    # that differs from torch's must be a near-tie of p / q under torch's OWN p and q, never a different draw
     agree = (tok == want).float().mean().item()
     assert agree > 0.9995, agree
+    bad = torch.nonzero(tok != want)[:, 0]
+    if bad.numel():
+        q = s["eng"].exponential(N * 43, seed=seed, offset=off).view(N, 43)
+        r = (p / q)[bad]
+        r_want, r_mine = r.gather(1, want[bad, None])[:, 0], r.gather(1, tok[bad, None])[:, 0]
+        assert bool(((r_want - r_mine).abs() <= 1e-5 * r_want).all()), (bad.tolist(), r_want.tolist(), r_mine.tolist())
     # shard invariance: rows [lo,hi) sampled alone, placed inside the N-row call
     lo, hi = N // 3, N // 3 + 50
     tok_s, _, _ = s["eng"].sample(x[lo:hi], sampling="multinomial", seed=seed, offset=off, seq_index_base=lo, n_total=N)
     assert torch.equal(tok_s, tok[lo:hi])
+
+
+@pytest.mark.parametrize("numel", [43 * 128, 43 * 5000, 43 * 20000, 43 * 40000, 43 * 131072, 1000003])
+def test_exponential_variates_bit_equal_torch(numel):
+    """The Exp(1) variates behind torch.multinomial: bit equality with exponential_() on this device
+    in all launch-geometry regimes (single float4 component; .y/.z/.w; second loop iteration; config 3's 131,072 x 43
+    with its offset increment of 20), at a non-zero generator offset, plus a window placed inside the big tensor."""
+    s = setup()
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.manual_seed(31337)
+    torch.empty(7, device="cuda").normal_()             # offset off zero
+    seed, off = gen.initial_seed(), gen.get_offset()
+    want = torch.empty(numel, device="cuda").exponential_(1)
+    assert gen.get_offset() - off == s["eng"].L.mmt_philox_increment(numel, s["eng"].sm_count, s["eng"].max_threads_per_sm)
+    got = s["eng"].exponential(numel, seed=seed, offset=off)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    lo = numel // 2 + 3
+    win = s["eng"].exponential(1000, seed=seed, offset=off, elem_base=lo, numel_total=numel)
+    assert torch.equal(win, want[lo:lo + 1000])
 
 
 def test_philox_numpy_restatement_matches_device():

@@ -28,13 +28,18 @@ def _worker(rank, world, port, B, k, T, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from multimodalspectraltransformer_b200.scheduler import shard_bounds, gather_columns
+    from multimodalspectraltransformer_b200.scheduler import shard_bounds, gather_columns, gather_rows, PendingTokens
     full = (torch.arange(T * B * k) % 43).reshape(T, B * k).to(torch.uint8)
     lo, hi = shard_bounds(B, world, rank)
     local = full[:, lo * k:hi * k].contiguous()
     per = (B + world - 1) // world
     out = gather_columns(local, B * k, per * k)
     ok = bool(torch.equal(out, full))
+    # the scheduler's own payload: sequence-major (n_local, T) blocks land in the final order, no re-layout
+    rows = gather_rows(local.t().contiguous(), per * k)
+    ok = ok and tuple(rows.shape) == (world * per * k, T) and bool(torch.equal(rows[:B * k], full.t()))
+    pend = PendingTokens(None, rows, None, B * k, T)
+    ok = ok and bool(torch.equal(pend.tokens(), full.to(torch.int64))) and bool(torch.equal(pend.packed(), full.t()))
     pr = gather_columns(local.float(), B * k, per * k)
     ok = ok and bool(torch.equal(pr, full.float()))
     q.put((rank, ok))
