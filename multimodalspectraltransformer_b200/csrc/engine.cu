@@ -1003,6 +1003,8 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
         return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W), pdl_u);
     };
+    // low-order weight term of the decoder FFN (experiment knob MMT_DEC_FFN_SINGLE=1: hi term only)
+    auto dlo = [&](const float* w) -> const __nv_bfloat16* { return e->dec_ffn_single ? nullptr : e->Wlo(w); };
     int ffn_splits = 1;
     if (fused) {
         if (dh != 8 || H != DA_H) MMT_FAIL("decoder must have 16 heads of dim 8");
@@ -1052,7 +1054,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 FfnParams f = ffn_params(M, d.d_ff);
                 f.b1 = w.l1_b; f.splits = ffn_splits; f.out_f32 = b.part; f.part_stride = Nw * D;
                 f.dbg = (e->da_dbg && l == 3) ? e->da_dbg + 2048 * 16 : nullptr;
-                MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s, pdl));
+                MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_STORE, s, pdl));
             } else {
                 MMT_TRY(gemm(b.x, D, w.l1_w, w.l1_b, b.h, d.d_ff, D, 1, 1));
                 MMT_TRY(gemm(b.h, d.d_ff, w.l2_w, nullptr, b.part, D, d.d_ff, 0, ffn_splits));
@@ -1096,12 +1098,12 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 if (M >= 2048) {
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.bias = w.l2_b; f.res = b.x; f.gamma = w.n3_w; f.beta = w.n3_b; f.out_f32 = b.x; f.out_b16 = b.x16;
-                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_LN, s, pdl_u));
+                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_LN, s, pdl_u));
                 } else {   // few rows: split F over the grid, reduce the partials in the LayerNorm kernel
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.splits = MAX_SPLITS; f.out_f32 = b.part; f.part_stride = Nw * D;
                     if ((int64_t)f.splits * Nw > b.part_rows) MMT_FAIL("decode: FFN partial buffer too small for this wave (plan_decoder)");
-                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), e->Wlo(w.l1_w), e->Wb(w.l2_w), e->Wlo(w.l2_w), TC_EPI_STORE, s, pdl_u));
+                    MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_STORE, s, pdl_u));
                     MMT_TRY(ln(b.part, f.splits, w.l2_b, w.n3_w, w.n3_b));
                 }
             } else {
@@ -1519,6 +1521,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (const char* v = getenv("MMT_FFN_SPLITS")) { int k = atoi(v); if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) e->ffn_splits_override = k; }
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
+    if (getenv("MMT_DEC_FFN_SINGLE")) e->dec_ffn_single = true;
     if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };

@@ -119,6 +119,7 @@ struct mmt_engine {
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     int max_wave_seqs = 16384;         // sequences decoded together; larger runs go wave by wave (bounds the self-attention KV pool; MMT_MAX_WAVE_SEQS overrides)
+    bool dec_ffn_single = false;       // experiment (MMT_DEC_FFN_SINGLE=1): decoder FFN with the hi weight term only
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int64_t launches_per_group; uint64_t stamp; };
     std::vector<GraphEntry> graph_cache;   // instantiated decode-step graphs of single-wave runs (staged outputs), keyed by what their nodes bake in
