@@ -485,7 +485,8 @@ static int encoder_layer_bf16(mmt_engine* e, EncGroupRun* gr, int ng, int Bc, in
         } else {
             p.out_f32 = gr[i].X; p.out_b16 = gr[i].x16;
         }
-        MMT_TRY(launch_ffn(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), e->Wlo(gr[i].w->l1_w), e->Wb(gr[i].w->l2_w), e->Wlo(gr[i].w->l2_w), TC_EPI_LN, s));
+        const bool one = e->enc_ffn_single;      // hi weight term only (the lo term of the FFN weights does not show in the error)
+        MMT_TRY(launch_ffn(e, p, gr[i].x16, D, e->Wb(gr[i].w->l1_w), one ? nullptr : e->Wlo(gr[i].w->l1_w), e->Wb(gr[i].w->l2_w), one ? nullptr : e->Wlo(gr[i].w->l2_w), TC_EPI_LN, s));
     }
     return 0;
 }
@@ -1003,7 +1004,9 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
         return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W), pdl_u);
     };
-    // low-order weight term of the decoder FFN (experiment knob MMT_DEC_FFN_SINGLE=1: hi term only)
+    // The decoder FFN runs on the hi term of the bf16 weight split alone: measured on the 12 golden cases the lo term changes
+    // the worst logit error from 5.75e-3 to 5.76e-3 of the row scale (profiles/r02_bf16_error.md) for twice the tensor work.
+    // MMT_DEC_FFN_TWO_TERM=1 restores it.
     auto dlo = [&](const float* w) -> const __nv_bfloat16* { return e->dec_ffn_single ? nullptr : e->Wlo(w); };
     int ffn_splits = 1;
     if (fused) {
@@ -1098,6 +1101,10 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 if (M >= 2048) {
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.bias = w.l2_b; f.res = b.x; f.gamma = w.n3_w; f.beta = w.n3_b; f.out_f32 = b.x; f.out_b16 = b.x16;
+                    if (getenv("MMT_FFN_DEBUG")) {     // phase stamps of the layer-3 FFN launch (printed by run_decode)
+                        if (!e->ffn_dbg) { MMT_CUDA(cudaMallocManaged(&e->ffn_dbg, 4096 * 16 * sizeof(long long))); memset(e->ffn_dbg, 0, 4096 * 16 * sizeof(long long)); }
+                        f.dbg = l == 3 ? e->ffn_dbg : nullptr;
+                    }
                     MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_LN, s, pdl_u));
                 } else {   // few rows: split F over the grid, reduce the partials in the LayerNorm kernel
                     FfnParams f = ffn_params(M, d.d_ff);
@@ -1171,6 +1178,11 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         if (fused && e->use_graph && !e->profiling) {
             NL = std::min(std::min(e->decode_lanes, MAX_LANES), Bm_wave);
             while (NL > 1 && Nwave / NL < 32) --NL;
+        } else if (!fused && bf16 && e->use_graph && !e->profiling && Nwave >= 4096) {
+            // Large waves: the step alternates HBM-bound kernels (self-attention over the KV pages) with tensor-bound ones
+            // (the FFN), each leaving the other resource idle.  Two lanes -- independent halves of the wave as parallel
+            // branches of the step graph -- let one half's attention stream pages while the other half's FFN runs.
+            NL = std::min(std::min(e->decode_lanes_large, MAX_LANES), Bm_wave);
         }
     }
     const int Bm_lane = (Bm_wave + NL - 1) / NL;
@@ -1321,6 +1333,15 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     if ((r.mode == 0) && a.stop_on_all_pad && n_waves > 1)
         for (int q = 0; q < r.T; ++q) if (nonpad_total[q] == 0) { steps_done = q + 1; break; }
     if (h_steps) *h_steps = steps_done;
+    if (e->ffn_dbg) {  // MMT_FFN_DEBUG: un-fused FFN launch of layer 3, last position
+        MMT_CUDA(cudaStreamSynchronize(s));
+        for (int bshow : {0, 64, 127}) {
+            const long long* d = e->ffn_dbg + bshow * 16;
+            fprintf(stderr, "ffn_fused_tc<LN> CTA %d: setup %lld | first acc1 %lld | first convert %lld | chunks 8..15:", bshow, d[1] - d[0], d[2] - d[1], d[3] - d[2]);
+            for (int i = 9; i <= 15; ++i) fprintf(stderr, " %lld", d[i] - d[i - 1]);
+            fprintf(stderr, " | start->acc2 %lld | tmem->stage %lld | LN rows %lld | total %lld\n", d[4] - d[0], d[5] - d[4], d[6] - d[5], d[7] - d[0]);
+        }
+    }
     if (e->da_dbg) {   // MMT_DA_DEBUG: phase timestamps (SM cycles) of the last decode_attn launch of layer 3
         MMT_CUDA(cudaStreamSynchronize(s));
         const int blocks = (int)std::min<int64_t>(4096, (std::min<int64_t>(N_total, max_wave_seqs) + DA_R - 1) / DA_R);
@@ -1521,7 +1542,9 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (const char* v = getenv("MMT_FFN_SPLITS")) { int k = atoi(v); if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) e->ffn_splits_override = k; }
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
-    if (getenv("MMT_DEC_FFN_SINGLE")) e->dec_ffn_single = true;
+    if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
+    if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
+    if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));
     if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };

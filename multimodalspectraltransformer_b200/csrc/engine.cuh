@@ -119,7 +119,8 @@ struct mmt_engine {
     bool use_graph = true;             // replay the decode step as a CUDA graph (MMT_NO_GRAPH=1 disables)
     int fused_decode_rows = 2048;      // waves of at most this many sequences take the fused row-local decoder kernels (MMT_FUSED_DECODE_ROWS overrides; 0 disables)
     int max_wave_seqs = 16384;         // sequences decoded together; larger runs go wave by wave (bounds the self-attention KV pool; MMT_MAX_WAVE_SEQS overrides)
-    bool dec_ffn_single = false;       // experiment (MMT_DEC_FFN_SINGLE=1): decoder FFN with the hi weight term only
+    bool enc_ffn_single = false;       // experiment (MMT_ENC_FFN_SINGLE=1): encoder FFN with the hi weight term only
+    bool dec_ffn_single = true;        // decoder FFN on the hi weight term only (MMT_DEC_FFN_TWO_TERM=1: both terms)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int64_t launches_per_group; uint64_t stamp; };
     std::vector<GraphEntry> graph_cache;   // instantiated decode-step graphs of single-wave runs (staged outputs), keyed by what their nodes bake in
@@ -136,6 +137,8 @@ struct mmt_engine {
     cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only streams, one per decode lane (the caller's stream may be the legacy default stream)
     cudaEvent_t lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};       // fork / join events of the lane branches
     int decode_lanes = 2;              // concurrent lanes of a small decode wave (MMT_DECODE_LANES overrides)
+    int decode_lanes_large = 1;        // concurrent lanes of a large (un-fused) bf16 wave (MMT_DECODE_LANES_LARGE overrides)
+    long long* ffn_dbg = nullptr;      // MMT_FFN_DEBUG phase timestamps of the un-fused FFN (managed memory)
     long long* da_dbg = nullptr;       // MMT_DA_DEBUG phase timestamps (managed memory)
     bool da_ready = false;             // decode_attn shared-memory attribute set
     bool tc_ready = false;             // tcgen05 path initialised (driver entry point + smem attributes)

@@ -8,7 +8,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-constexpr int CL = 16, THREADS = 1024;
+constexpr int THREADS = 1024;
 constexpr int SMEM = 214 * 1024;
 
 __device__ __forceinline__ void cluster_sync() {
@@ -27,6 +27,7 @@ __device__ __forceinline__ void st_remote_v2(uint32_t addr, float2 v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1) probe(long long* out, int iters) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* xg = smem;                 // [32][256 B]
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(THREADS, 1) probe(long long* out, int iters) {
     for (int i = 0; i < iters; ++i) cluster_sync();
     long long t1 = clock64();
     for (int i = 0; i < iters; ++i) {         // all-gather: warp w < 16 writes this CTA's two rows into CTA w
-        if (warp < CL) {
+        if (warp < CL) {  // (rows of the CTAs beyond the cluster size do not exist)
             const int r = lane >> 4, ch = lane & 15;
             st_remote_v4(map_remote(xg + (2 * c + r) * 256 + ch * 16, warp), make_uint4(i, c, r, ch));
         }
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(THREADS, 1) probe(long long* out, int iters) {
         const int mt = warp >> 4, nt = warp & 15, g = lane >> 2, t = lane & 3;
         for (int hh = 0; hh < 2; ++hh) {
             const int R = mt * 16 + g + hh * 8;
-            st_remote_v2(map_remote(recv + ((c * 2) + (R & 1)) * 128 + nt * 8 + 2 * t, R >> 1), make_float2((float)i, (float)R));
+            if (R < 2 * CL) st_remote_v2(map_remote(recv + ((c * 2) + (R & 1)) * 128 + nt * 8 + 2 * t, R >> 1), make_float2((float)i, (float)R));
         }
         cluster_sync();
     }
@@ -60,29 +61,32 @@ __global__ void __launch_bounds__(THREADS, 1) probe(long long* out, int iters) {
     }
 }
 
+template <int CL>
+void run(int ncl) {
+    cudaFuncSetAttribute(probe<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(probe<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncl * CL); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int maxc = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, probe<CL>, &cfg);
+    printf("cluster size %d x %d clusters: cudaOccupancyMaxActiveClusters -> %d (%s)\n", CL, ncl, maxc, cudaGetErrorString(e));
+    long long* d; cudaMalloc(&d, ncl * CL * 4 * sizeof(long long));
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    int iters = 200;
+    cudaLaunchKernelEx(&cfg, probe<CL>, d, iters);
+    cudaEventRecord(a); cudaLaunchKernelEx(&cfg, probe<CL>, d, iters); cudaEventRecord(b);
+    e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    static long long h[4 * 1024]; cudaMemcpy(h, d, ncl * CL * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    printf("  launch %s, %.1f us total; CTA 0: cluster.sync %lld cyc | all-gather+sync %lld | scatter+sync %lld ; last CTA: %lld %lld %lld\n",
+           cudaGetErrorString(e), ms * 1e3, h[0], h[1], h[2], h[(ncl * CL - 1) * 4], h[(ncl * CL - 1) * 4 + 1], h[(ncl * CL - 1) * 4 + 2]);
+    cudaFree(d);
+}
+
 int main() {
-    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    cudaFuncSetAttribute(probe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    for (int ncl : {8, 9}) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ncl * CL); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int maxc = -1;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, probe, &cfg);
-        printf("clusters=%d: cudaOccupancyMaxActiveClusters -> %d (%s)\n", ncl, maxc, cudaGetErrorString(e));
-        long long* d; cudaMalloc(&d, ncl * CL * 4 * sizeof(long long));
-        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-        int iters = 200;
-        cudaLaunchKernelEx(&cfg, probe, d, iters);
-        cudaEventRecord(a); cudaLaunchKernelEx(&cfg, probe, d, iters); cudaEventRecord(b);
-        e = cudaDeviceSynchronize();
-        float ms = 0; cudaEventElapsedTime(&ms, a, b);
-        long long h[4 * 16 * 9]; cudaMemcpy(h, d, ncl * CL * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
-        printf("  launch %s, %.1f us total; CTA 0: cluster.sync %lld cyc | all-gather+sync %lld | scatter+sync %lld ; last CTA: %lld %lld %lld\n",
-               cudaGetErrorString(e), ms * 1e3, h[0], h[1], h[2], h[(ncl * CL - 1) * 4], h[(ncl * CL - 1) * 4 + 1], h[(ncl * CL - 1) * 4 + 2]);
-        cudaFree(d);
-    }
+    run<16>(7); run<16>(8); run<8>(16); run<8>(18); run<4>(32); run<2>(64);
     return 0;
 }
