@@ -125,6 +125,9 @@ def generate_sharded(model, data_dict, config, stoi, *, n_candidates=1, sampling
     T = int(config.max_len)
     eng = engine_for(model, config)
     if hi > lo:
+        # host buffers: move this rank's shard with asynchronous copies (pinned memory makes them truly asynchronous), so the
+        # host keeps launching instead of draining the stream at every tensor the way a blocking .to(device) does
+        local = {k: (v if v.is_cuda else v.to(eng.device, non_blocking=True)) for k, v in local.items()}
         memory, mask, *_ = G.run_model(model, local, config)
         if sampling == "greedy":
             # stop_on_all_pad is a whole-batch property: decide it after the gather
