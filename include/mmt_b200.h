@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MMT_ABI_VERSION 1
+#define MMT_ABI_VERSION 2
 
 typedef struct mmt_engine mmt_engine;
 
@@ -276,10 +276,11 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
  * -> LayerNorm; torch TransformerEncoderLayer._ff_block + norm2, models_MMT_v15_4.py:510-541) in
  * the bf16 tensor-core mode:  d_out = LN(d_x + W2 relu(W1 bf16(d_x) + b1) + b2) * gamma + beta,
  * d_x / d_out (M,128) f32, W1 (F,128), W2 (128,F).  splits > 1 exercises the split-F partial path
- * the small-batch decoder uses. */
+ * the small-batch decoder uses.  weight_terms: 2 = W as the two-term bf16 split W_hi + W_lo (encoder layers),
+ * 1 = W_hi alone (decoder layers; the kernel variant with the deeper GEMM1 / convert / GEMM2 pipeline). */
 int32_t mmt_ffn(mmt_engine* e, const float* d_x, const float* d_w1, const float* d_b1, const float* d_w2,
                 const float* d_b2, const float* d_gamma, const float* d_beta, float* d_out,
-                int64_t M, int32_t F, int32_t splits, void* stream);
+                int64_t M, int32_t F, int32_t splits, int32_t weight_terms, void* stream);
 
 /* launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t mmt_launch_count(const mmt_engine* e);

@@ -167,11 +167,11 @@ def lib():
     L.mmt_exponential.argtypes = [u64, u64, i64, i64, i64, i32, i32, vp, vp]; L.mmt_exponential.restype = i32
     L.mmt_sample_probs.argtypes = [vp, i64, i32, u64, u64, i64, i64, i32, i32, vp, vp]; L.mmt_sample_probs.restype = i32
     L.mmt_linear.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]; L.mmt_linear.restype = i32
-    L.mmt_ffn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]; L.mmt_ffn.restype = i32
+    L.mmt_ffn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]; L.mmt_ffn.restype = i32
     L.mmt_launch_count.argtypes = [vp]; L.mmt_launch_count.restype = i64
     L.mmt_profile_enable.argtypes = [vp, i32]; L.mmt_profile_enable.restype = i32
     L.mmt_profile_report.argtypes = [vp, C.c_char_p, i64]; L.mmt_profile_report.restype = i32
-    if L.mmt_abi_version() != 1:
+    if L.mmt_abi_version() != 2:
         raise RuntimeError("libmmt_b200.so ABI version mismatch")
     _LIB = L
     return L

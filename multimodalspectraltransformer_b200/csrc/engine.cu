@@ -165,8 +165,10 @@ static int tc_init(mmt_engine* e) {
     const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES_WSPLIT + 1024;
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
-    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_BYTES));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<1>()));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<1>()));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<0>()));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<0>()));
     e->tc_ready = true;
     return 0;
 }
@@ -246,9 +248,15 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
         MMT_TRY(make_tmap(&p.tmW2lo, W2lo, D, p.F, p.F));
     }
     dim3 grid(p.splits, (p.M + TC_BM - 1) / TC_BM);
+    if (const char* v = getenv("MMT_FFN_KNOCK")) p.knock = atoi(v);
     prof_pre(e, s);
-    if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN>, grid, dim3(FF_THREADS), FF_SMEM_BYTES, s, pdl, p);
-    else launch_kernel(ffn_fused_tc<TC_EPI_STORE>, grid, dim3(FF_THREADS), FF_SMEM_BYTES, s, pdl, p);
+    if (p.wsplit) {
+        if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), s, pdl, p);
+        else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), s, pdl, p);
+    } else {   // hi term only: the deeper pipeline variant
+        if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
+        else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
+    }
     return check_launch(e, "ffn_fused_tc", s, 4.0 * p.M * D * p.F);
 }
 
@@ -1853,7 +1861,8 @@ int32_t mmt_linear(mmt_engine* e, const float* d_A, const float* d_W, const floa
 }
 
 int32_t mmt_ffn(mmt_engine* e, const float* d_x, const float* d_w1, const float* d_b1, const float* d_w2, const float* d_b2,
-                const float* d_gamma, const float* d_beta, float* d_out, int64_t M, int32_t F, int32_t splits, void* stream) {
+                const float* d_gamma, const float* d_beta, float* d_out, int64_t M, int32_t F, int32_t splits, int32_t weight_terms, void* stream) {
+    if (weight_terms != 1 && weight_terms != 2) MMT_FAIL("mmt_ffn: weight_terms must be 1 or 2");
     if (!e || !d_x || !d_w1 || !d_b1 || !d_w2 || !d_b2 || !d_gamma || !d_beta || !d_out) MMT_FAIL("null argument");
     if (M <= 0) return 0;
     if (M > 0x7fffffff) MMT_FAIL("M too large");
@@ -1879,10 +1888,10 @@ int32_t mmt_ffn(mmt_engine* e, const float* d_x, const float* d_w1, const float*
     p.b1 = d_b1; p.splits = splits;
     if (splits == 1) {
         p.bias = d_b2; p.res = d_x; p.gamma = d_gamma; p.beta = d_beta; p.out_f32 = d_out;
-        return launch_ffn(e, p, X16, D, W1h, W1l, W2h, W2l, TC_EPI_LN, cs);
+        return launch_ffn(e, p, X16, D, W1h, weight_terms == 2 ? W1l : nullptr, W2h, weight_terms == 2 ? W2l : nullptr, TC_EPI_LN, cs);
     }
     p.out_f32 = part; p.part_stride = (int64_t)nX;
-    MMT_TRY(launch_ffn(e, p, X16, D, W1h, W1l, W2h, W2l, TC_EPI_STORE, cs));
+    MMT_TRY(launch_ffn(e, p, X16, D, W1h, weight_terms == 2 ? W1l : nullptr, W2h, weight_terms == 2 ? W2l : nullptr, TC_EPI_STORE, cs));
     LnParams q;
     memset(&q, 0, sizeof(q));
     q.splits = p.splits; q.part_stride = (int64_t)nX; q.eps = 1e-5f;

@@ -25,25 +25,57 @@
 // than M/128): each CTA handles F/64/splits chunks and writes a raw fp32 partial; the consumer
 // (decode_attn / sample_tokens prologue, or bias_res_layernorm) reduces them in a fixed order.
 //
-// warp 0: TMA producers (two lanes) | warp 1: MMA issuer (one lane) + TMEM alloc (512 cols) | warps 2-9: epilogue
-// (two epilogue warps per TMEM lane quarter: with one warp per scheduler the conversion is a latency chain)
+// warp 0: TMA producer (one lane) | warp 1: GEMM1 issuer (one lane) + TMEM alloc (512 cols) | warps 2-9: epilogue
+// (two epilogue warps per TMEM lane quarter: with one warp per scheduler the conversion is a latency chain) | warp 10:
+// GEMM2 issuer (one lane).  Two issuing threads because the chunk loop is bound by the ISSUER's own serial control
+// instructions, not by the tensor pipe: per 64-column chunk one thread spent ~1.1 K cycles in three mbarrier waits, two
+// tcgen05 fences and the commits (measured with every MMA, TMA load and conversion removed, profiles/r02_ffn_pipeline.md)
+// around ~0.5 K cycles of MMA time; GEMM1 and GEMM2 write different accumulators, so their issue streams are independent.
+//
+// Two variants (template WS).  WS = 1: two-term weights as above, acc1 / H double-buffered, two-stage weight rings
+// (TMEM: 2 x 128 + 256 columns; 192 KB of shared memory).  WS = 0: the hi term alone (decoder FFN).  The
+// freed TMEM columns and shared memory buy a deeper pipeline: acc1 / H triple-buffered and GEMM1 issued TWO chunks
+// ahead of GEMM2, so the ~900-cycle conversion of a chunk (TMEM -> bias + ReLU -> bf16 -> swizzled smem -> proxy fence)
+// no longer sits between the two GEMMs of the same chunk on the tensor pipe, and four-stage weight rings of 16 KB
+// stages keep two more chunks of weights in flight (measured chunk cadence of the two-buffer pipeline: ~1.6 K cycles
+// against ~0.7 K of operand-read / tensor time, profiles/r02_ffn_pipeline.md).
 #pragma once
 #include "kernels_tc.cuh"
 
 namespace mmt {
 
 constexpr int FF_CH = 64;                                  // hidden columns per chunk
-constexpr int FF_THREADS = TC_THREADS;                     // 2 + 8 epilogue warps
+constexpr int FF_THREADS = TC_THREADS + 32;                // producer + GEMM1 issuer + 8 epilogue warps + GEMM2 issuer
+constexpr int FF_G2_WARP = 2 + TC_EPI_WARPS;               // warp 10 (the epilogue warps must be 2-9: TMEM lane quarter = warp id % 4)
 constexpr int FF_X_BYTES = 2 * TC_SLAB_BYTES;              // X: two K slabs of [128 rows x 64]
 constexpr int FF_H_BYTES = TC_SLAB_BYTES;                  // one H buffer: [128 rows x 64] bf16
 constexpr int FF_W1_HALF = FF_CH * 128;                    // 8 KB: 64 rows x 128 B (one term of one K slab)
 constexpr int FF_W1_STAGE = 2 * TC_SLAB_BYTES;             // W1 chunk: 2 K slabs of [64 hi rows ; 64 lo rows] x 64 k = 32 KB
 constexpr int FF_W2_STAGE = 2 * TC_SLAB_BYTES;             // W2 chunk: [128 hi rows ; 128 lo rows] x 64 k = 32 KB
 constexpr int FF_MAX_F = 2048;
-// dynamic smem: X (32 KB) | H (2 x 16 KB) | W1 ring (2 x 32 KB) | W2 ring (2 x 32 KB) + alignment slack
-constexpr int FF_SMEM_BYTES = FF_X_BYTES + 2 * FF_H_BYTES + 2 * FF_W1_STAGE + 2 * FF_W2_STAGE + 1024;
-static_assert(2 * FF_W1_STAGE + 2 * FF_W2_STAGE >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
-constexpr uint32_t FF_TMEM_COLS = 512;                     // acc1: 2 x (64 hi + 64 lo) | acc2: 128 hi + 128 lo
+// per-variant pipeline geometry
+template <int WS> struct FfCfg;
+template <> struct FfCfg<1> {          // two-term weights
+    static constexpr int NB = 2, NS = 2;                                   // acc1 / H buffers, weight ring stages
+    static constexpr int W1_STAGE = FF_W1_STAGE, W2_STAGE = FF_W2_STAGE;   // 32 KB each (hi | lo)
+    static constexpr int W1_SLAB = TC_SLAB_BYTES;                          // K slab stride inside a W1 stage
+    static constexpr int ACC1_STRIDE = 2 * FF_CH, ACC2_COL = 256;          // TMEM columns
+};
+template <> struct FfCfg<0> {          // hi term only: deeper pipeline in the freed TMEM / shared memory
+    static constexpr int NB = 3, NS = 4;
+    static constexpr int W1_STAGE = FF_W1_STAGE / 2, W2_STAGE = FF_W2_STAGE / 2;   // 16 KB each
+    static constexpr int W1_SLAB = FF_W1_HALF;                             // 8 KB: [64 rows x 64 k]
+    static constexpr int ACC1_STRIDE = FF_CH, ACC2_COL = 256;
+};
+// dynamic smem: X (32 KB) | H (NB x 16 KB) | W1 ring | W2 ring + alignment slack
+template <int WS> constexpr int ff_smem_bytes() {
+    return FF_X_BYTES + FfCfg<WS>::NB * FF_H_BYTES + FfCfg<WS>::NS * (FfCfg<WS>::W1_STAGE + FfCfg<WS>::W2_STAGE) + 1024;
+}
+constexpr int FF_SMEM_BYTES = ff_smem_bytes<1>();
+static_assert(FfCfg<1>::NS * (FfCfg<1>::W1_STAGE + FfCfg<1>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
+static_assert(FfCfg<0>::NS * (FfCfg<0>::W1_STAGE + FfCfg<0>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
+static_assert(ff_smem_bytes<0>() <= 227 * 1024 && ff_smem_bytes<1>() <= 227 * 1024, "shared memory budget");
+constexpr uint32_t FF_TMEM_COLS = 512;                     // WS=1: acc1 2 x (64 hi + 64 lo) | acc2 128 hi + 128 lo;  WS=0: acc1 3 x 64 | acc2 128 at column 256
 
 struct FfnParams {
     CUtensorMap tmX;                 // X  [M,128] bf16, box {64,128}
@@ -62,6 +94,8 @@ struct FfnParams {
     int S_in; int64_t stride_b, stride_s, off;
     const int* out_rows;             // optional explicit output rows (LayerNorm epilogue, ragged encoder)
     long long* dbg;                  // optional [CTA][16] phase timestamps (MMT_DA_DEBUG)
+    int knock;                       // timing experiments only (MMT_FFN_KNOCK, results garbage): 1 no weight TMA after the first ring fill,
+                                     // 2 no conversion work, 4 no MMAs
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -86,17 +120,25 @@ __device__ __forceinline__ void epi_tmem2_to_stage(uint32_t tmem_acc, int q, int
     }
 }
 
-template <int EPI>
+template <int EPI, int WS>
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
+    typedef FfCfg<WS> C;
+    constexpr int NB = C::NB, NS = C::NS;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t x_full, w1_full[2], w1_empty[2], w2_full[2], w2_empty[2], acc1_full[2], h_full[2], h_empty[2], acc2_full;
+    // "GEMM1 of chunk i retired" frees a W1 stage AND publishes acc1; "GEMM2 of chunk j retired" frees a W2 stage AND an H
+    // buffer: one tcgen05.commit each (a commit costs the issuing thread a few hundred cycles), on barrier rings of
+    // R = lcm(NS, NB) slots so that every waiter (whatever its buffer count) finds chunk i's barrier at slot i % R
+    constexpr int R = 12;
+    static_assert(R % NS == 0 && R % NB == 0, "barrier ring must be a multiple of both buffer counts");
+    __shared__ __align__(8) uint64_t x_full, w1_full[NS], w2_full[NS], h_full[NB], g1_done[R], g2_done[R], acc2_full;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sB1[FF_MAX_F];     // this CTA's slice of b1: one load at kernel start instead of an L2 round trip in every chunk's conversion
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space
     uint8_t* sX = smem;
     uint8_t* sH = sX + FF_X_BYTES;
-    uint8_t* sW = sH + 2 * FF_H_BYTES;   // W1 ring; the two rings together also hold the final staging tile
-    uint8_t* sW2 = sW + 2 * FF_W1_STAGE;
+    uint8_t* sW = sH + NB * FF_H_BYTES;   // W1 ring; the two rings together also hold the final staging tile
+    uint8_t* sW2 = sW + NS * C::W1_STAGE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, m0 = blockIdx.y * TC_BM;
     const int n = (p.F / FF_CH) / p.splits;      // chunks of this CTA (host guarantees divisibility, n >= 1)
@@ -108,23 +150,24 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW1); tma_prefetch_desc(&p.tmW2);
-        if (p.wsplit) { tma_prefetch_desc(&p.tmW1lo); tma_prefetch_desc(&p.tmW2lo); }
+        if (WS) { tma_prefetch_desc(&p.tmW1lo); tma_prefetch_desc(&p.tmW2lo); }
         mbar_init(&x_full, 1); mbar_init(&acc2_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1);
-            mbar_init(&acc1_full[s], 1);
-            mbar_init(&h_full[s], TC_EPI_WARPS * 32); mbar_init(&h_empty[s], 1);
-        }
+        for (int s = 0; s < NS; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w2_full[s], 1); }
+        for (int s = 0; s < NB; ++s) mbar_init(&h_full[s], TC_EPI_WARPS);     // one arrival per epilogue warp (256 arrivals on one barrier serialise)
+        for (int s = 0; s < R; ++s) { mbar_init(&g1_done[s], 1); mbar_init(&g2_done[s], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, FF_TMEM_COLS);
+    if (warp >= 2 && warp < FF_G2_WARP)       // b1 is a decode-loop constant: no PDL wait needed
+        for (int i = threadIdx.x - 64; i < n * (FF_CH / 4); i += TC_EPI_WARPS * 32)
+            reinterpret_cast<float4*>(sB1)[i] = __ldg(reinterpret_cast<const float4*>(p.b1 + (size_t)c0 * FF_CH) + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t tmem_acc2 = tmem_base + 256;          // acc1[b] at columns [128 b, 128 b + 128): hi 64 | lo 64
+    const uint32_t tmem_acc2 = tmem_base + C::ACC2_COL;   // acc1[b] at columns [ACC1_STRIDE b, +ACC1_STRIDE): hi 64 (| lo 64)
     // N of the MMAs: both terms stacked, or the hi half alone
-    const int n1 = p.wsplit ? 2 * FF_CH : FF_CH, n2 = p.wsplit ? 2 * TC_BN : TC_BN;
+    constexpr int n1 = WS ? 2 * FF_CH : FF_CH, n2 = WS ? 2 * TC_BN : TC_BN;
     if (threadIdx.x == 64) FF_STAMP(1);
 
     if (warp == 0) {
@@ -133,68 +176,73 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             tma_load_2d(sX, &p.tmX, &x_full, 0, m0);
             tma_load_2d(sX + TC_SLAB_BYTES, &p.tmX, &x_full, TC_BK, m0);
         };
-        if (lane == 0) {                  // W1 ring (decode-loop constants only: runs ahead of the PDL wait)
+        // ONE producer lane feeds both weight rings.  (Two lanes of this warp each running its own loop of blocking mbarrier
+        // waits stall each other: a lane parked in try_wait holds the warp, measured ~1.1 K cycles per chunk with nothing
+        // else in the loop.)  Order per chunk: W1(i) as soon as GEMM1(i - NS) retired, then W2(i) once GEMM2(i - NS) retired.
+        if (lane == 0) {
             for (int i = 0; i < n; ++i) {
-                const int s = i & 1, c = c0 + i;
-                mbar_wait(&w1_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&w1_full[s], p.wsplit ? FF_W1_STAGE : FF_W1_STAGE / 2);
-                uint8_t* w = sW + (size_t)s * FF_W1_STAGE;          // K slab ks: rows 0-63 hi, rows 64-127 lo
-                tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
-                tma_load_2d(w + TC_SLAB_BYTES, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
-                if (p.wsplit) {
-                    tma_load_2d(w + FF_W1_HALF, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
-                    tma_load_2d(w + TC_SLAB_BYTES + FF_W1_HALF, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
-                }
+                const int s = i % NS, c = c0 + i;
+                if (i == min(n, NS)) { pdl_wait(); load_x(); }      // the first ring fill is decode-loop constants only: ahead of the PDL wait
+                if (i >= NS) mbar_wait(&g1_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM1 of the stage's previous chunk retired
+                if (!((p.knock & 1) && i >= NS)) {
+                    mbar_arrive_expect_tx(&w1_full[s], C::W1_STAGE);
+                    uint8_t* w = sW + (size_t)s * C::W1_STAGE;          // K slab ks at ks * W1_SLAB: rows 0-63 hi (, rows 64-127 lo)
+                    tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
+                    tma_load_2d(w + C::W1_SLAB, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
+                    if (WS) {
+                        tma_load_2d(w + FF_W1_HALF, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
+                        tma_load_2d(w + C::W1_SLAB + FF_W1_HALF, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
+                    }
+                } else mbar_arrive(&w1_full[s]);
+                if (i >= NS) mbar_wait(&g2_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM2 of the stage's previous chunk retired
+                if (!((p.knock & 1) && i >= NS)) {
+                    mbar_arrive_expect_tx(&w2_full[s], C::W2_STAGE);
+                    uint8_t* w = sW2 + (size_t)s * C::W2_STAGE;         // rows 0-127 hi (, rows 128-255 lo)
+                    tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
+                    if (WS) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
+                } else mbar_arrive(&w2_full[s]);
             }
-        } else if (lane == 1) {           // W2 ring, and X once the producer of X has finished (PDL)
-            for (int i = 0; i < n; ++i) {
-                const int s = i & 1, c = c0 + i;
-                if (i == min(n, 2)) { pdl_wait(); load_x(); }
-                mbar_wait(&w2_empty[s], (((uint32_t)i >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&w2_full[s], p.wsplit ? FF_W2_STAGE : FF_W2_STAGE / 2);
-                uint8_t* w = sW2 + (size_t)s * FF_W2_STAGE;         // rows 0-127 hi, rows 128-255 lo
-                tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
-                if (p.wsplit) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
-            }
-            if (n <= 2) { pdl_wait(); load_x(); }      // short loops never reached the in-loop wait
+            if (n <= NS) { pdl_wait(); load_x(); }     // short loops never reached the in-loop wait
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc1 = umma_idesc_bf16(TC_BM, n1);
-            const uint32_t idesc2 = umma_idesc_bf16(TC_BM, n2);
             const uint32_t x_addr = smem_u32(sX);
-            // acc2 += H[j&1] . [W2_hi ; W2_lo][:, chunk j]^T
-            auto gemm2 = [&](int j) {
-                const int b = j & 1;
-                mbar_wait(&w2_full[b], ((uint32_t)j >> 1) & 1u);
-                mbar_wait(&h_full[b], ((uint32_t)j >> 1) & 1u);
-                tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(sH + (size_t)b * FF_H_BYTES));
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(sW2 + (size_t)b * FF_W2_STAGE));
-#pragma unroll
-                for (int k = 0; k < FF_CH / 16; ++k)
-                    umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&w2_empty[b]);     // W2 stage b reusable
-                umma_commit(&h_empty[b]);      // H buffer b reusable
-            };
+            // GEMM1 issue stream: acc1[i % NB] = X . [W1_hi (; W1_lo)][chunk i]^T.  The accumulator buffer is free once the
+            // conversion of chunk i - NB has read it (h_full of that chunk).
             mbar_wait(&x_full, 0);
             for (int i = 0; i < n; ++i) {
-                const int s = i & 1;
-                mbar_wait(&w1_full[s], ((uint32_t)i >> 1) & 1u);
+                const int s = i % NS;
+                mbar_wait(&w1_full[s], ((uint32_t)(i / NS)) & 1u);
+                if (i >= NB) mbar_wait(&h_full[i % NB], ((uint32_t)((i - NB) / NB)) & 1u);
                 tc_fence_after();
-                const uint32_t w1 = smem_u32(sW + (size_t)s * FF_W1_STAGE);
-                const uint32_t acc1 = tmem_base + (uint32_t)(s * 2 * FF_CH);
+                const uint32_t w1 = smem_u32(sW + (size_t)s * C::W1_STAGE);
+                const uint32_t acc1 = tmem_base + (uint32_t)((i % NB) * C::ACC1_STRIDE);
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
                     const uint64_t adesc = umma_desc_sw128(x_addr + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
-                    const uint64_t bdesc = umma_desc_sw128(w1 + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
-                    umma_bf16(acc1, adesc, bdesc, idesc1, k > 0 ? 1u : 0u);
+                    const uint64_t bdesc = umma_desc_sw128(w1 + (k >> 2) * C::W1_SLAB) + (uint64_t)(2 * (k & 3));
+                    if (!(p.knock & 4) || i < NB) umma_bf16(acc1, adesc, bdesc, idesc1, k > 0 ? 1u : 0u);
                 }
-                umma_commit(&acc1_full[s]);
-                umma_commit(&w1_empty[s]);     // W1 stage s reusable as soon as this GEMM1 retires
-                if (i > 0) gemm2(i - 1);
+                umma_commit(&g1_done[i % R]);  // acc1 of chunk i complete; its W1 stage reusable
             }
-            gemm2(n - 1);
+        }
+    } else if (warp == FF_G2_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc2 = umma_idesc_bf16(TC_BM, n2);
+            // GEMM2 issue stream: acc2 += H[j % NB] . [W2_hi (; W2_lo)][:, chunk j]^T
+            for (int j = 0; j < n; ++j) {
+                const int b = j % NB, sw = j % NS;
+                mbar_wait(&w2_full[sw], ((uint32_t)(j / NS)) & 1u);
+                mbar_wait(&h_full[b], ((uint32_t)(j / NB)) & 1u);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128(smem_u32(sH + (size_t)b * FF_H_BYTES));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(sW2 + (size_t)sw * C::W2_STAGE));
+#pragma unroll
+                for (int k = 0; k < FF_CH / 16; ++k)
+                    if (!(p.knock & 4) || j == 0) umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&g2_done[j % R]);  // W2 stage and H buffer of chunk j reusable
+            }
             umma_commit(&acc2_full);
         }
     } else {
@@ -203,42 +251,42 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         for (int i = 0; i < n; ++i) {
-            const int b = i & 1;
-            // bias slice of this chunk (a decode-loop constant): in registers before the accumulator is ready
-            float4 bb[8];
-            const float4* bsrc = reinterpret_cast<const float4*>(p.b1 + (size_t)(c0 + i) * FF_CH + hf * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bb[j] = __ldg(bsrc + j);
-            mbar_wait(&acc1_full[b], ((uint32_t)i >> 1) & 1u);
+            const int b = i % NB;
+            const float4* bb = reinterpret_cast<const float4*>(sB1 + i * FF_CH + hf * 32);     // bias slice of this chunk (shared memory)
+            mbar_wait(&g1_done[i % R], ((uint32_t)(i / R)) & 1u);
             tc_fence_after();
             if (threadIdx.x == 64 && i == 0) FF_STAMP(2);
             uint32_t pk[16];
-            {
+            if ((p.knock & 2) && i > 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = 0x3c003c00u;
+            } else {
                 uint32_t r[32], rl[32];
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 2 * FF_CH + hf * 32);
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * C::ACC1_STRIDE + hf * 32);
                 tmem_ld_32x32(t0, r);
-                if (p.wsplit) tmem_ld_32x32(t0 + FF_CH, rl);
+                if (WS) tmem_ld_32x32(t0 + FF_CH, rl);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]), v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
-                    if (p.wsplit) { v0 += __uint_as_float(rl[4 * j]); v1 += __uint_as_float(rl[4 * j + 1]); v2 += __uint_as_float(rl[4 * j + 2]); v3 += __uint_as_float(rl[4 * j + 3]); }
+                    if (WS) { v0 += __uint_as_float(rl[4 * j]); v1 += __uint_as_float(rl[4 * j + 1]); v2 += __uint_as_float(rl[4 * j + 2]); v3 += __uint_as_float(rl[4 * j + 3]); }
                     v0 = fmaxf(v0 + bb[j].x, 0.f); v1 = fmaxf(v1 + bb[j].y, 0.f); v2 = fmaxf(v2 + bb[j].z, 0.f); v3 = fmaxf(v3 + bb[j].w, 0.f);
                     __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
                     pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
                     pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
                 }
             }
-            mbar_wait(&h_empty[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
+            if (i >= NB) mbar_wait(&g2_done[(i - NB) % R], ((uint32_t)((i - NB) / R)) & 1u);      // GEMM2 of the buffer's previous chunk retired
             uint8_t* hrow = sH + (size_t)b * FF_H_BYTES + (size_t)row * 128;
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {    // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
                 const int cj = hf * 4 + c4;
                 *reinterpret_cast<uint4*>(hrow + ((cj ^ (row & 7)) << 4)) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
             }
-            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-            tc_fence_before();
-            mbar_arrive(&h_full[b]);
+            if (!(p.knock & 8)) fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+            if (!(p.knock & 16)) tc_fence_before();
+            __syncwarp();                      // every lane's stores are fenced before the warp's single arrival
+            if (lane == 0) mbar_arrive(&h_full[b]);
             if (threadIdx.x == 64 && i == 0) FF_STAMP(3);
             if (threadIdx.x == 64 && i >= 8 && i < 16) FF_STAMP(i);     // steady-state chunk cadence
         }
@@ -247,7 +295,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         mbar_wait(&acc2_full, 0);
         tc_fence_after();
         if (threadIdx.x == 64) FF_STAMP(4);
-        if (p.wsplit) epi_tmem2_to_stage(tmem_acc2, q, hf, lane, stage_q);
+        if (WS) epi_tmem2_to_stage(tmem_acc2, q, hf, lane, stage_q);
         else epi_tmem_to_stage<TC_BN>(tmem_acc2, q, hf, lane, stage_q);
         epi_bar_sync();
         if (threadIdx.x == 64) FF_STAMP(5);

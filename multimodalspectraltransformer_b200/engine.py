@@ -326,12 +326,13 @@ class Engine:
                                      out.data_ptr(), M, N, K, act, _PREC[precision], self._stream()))
         return out
 
-    def ffn(self, x, w1, b1, w2, b2, gamma, beta, splits=1):
-        """LN(x + W2 relu(W1 bf16(x) + b1) + b2): the fused tensor-core FFN block, stand-alone."""
+    def ffn(self, x, w1, b1, w2, b2, gamma, beta, splits=1, weight_terms=2):
+        """LN(x + W2 relu(W1 bf16(x) + b1) + b2): the fused tensor-core FFN block, stand-alone (weight_terms: 2 = hi + lo
+        bf16 terms, 1 = hi term only, the decoder's variant)."""
         t = [v.to(self.device, torch.float32).contiguous() for v in (x, w1, b1, w2, b2, gamma, beta)]
         M, F = t[0].shape[0], t[1].shape[0]
         out = torch.empty_like(t[0])
-        _lib.check(self.L.mmt_ffn(self.h, *[v.data_ptr() for v in t], out.data_ptr(), M, F, splits, self._stream()))
+        _lib.check(self.L.mmt_ffn(self.h, *[v.data_ptr() for v in t], out.data_ptr(), M, F, splits, weight_terms, self._stream()))
         return out
 
     def pack_tokens(self, tokens):

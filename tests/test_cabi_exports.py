@@ -23,7 +23,7 @@ def test_header_symbols_all_exported():
 
 def test_library_loads_and_weight_table_matches_reference_state_dict():
     L = _lib.lib()
-    assert L.mmt_abi_version() == 1
+    assert L.mmt_abi_version() == 2
     from multimodalspectraltransformer_b200.engine import _desc_from
     from multimodalspectraltransformer_b200.config import default_config
     d = _desc_from(default_config())

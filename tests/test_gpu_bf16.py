@@ -111,12 +111,15 @@ def test_multinomial_bf16_candidates():
     assert torch.equal(tok, tok2)        # deterministic for a fixed seed
 
 
+@pytest.mark.parametrize("terms", [2, 1])
 @pytest.mark.parametrize("M,F,splits", [(256, 2048, 1), (256, 2048, 16), (256, 2048, 32), (77, 2048, 8), (1000, 2048, 1),
-                                         (4097, 2048, 1), (130, 512, 2), (128, 64, 1),
+                                         (4097, 2048, 1), (130, 512, 2), (128, 64, 1), (300, 128, 1), (300, 192, 1), (300, 320, 1),
                                          (40001, 2048, 1)])     # >= 2 tiles per SM: two row tiles per CTA, odd tile count
-def test_ffn_fused_tcgen05(M, F, splits):
+def test_ffn_fused_tcgen05(M, F, splits, terms):
     """Fused FFN kernel == fp64 evaluation of the same contract: bf16(x) . (W1_hi + W1_lo), bias, ReLU, hidden
-    rounded to bf16, . (W2_hi + W2_lo), + b2 + x (fp32 residual), LayerNorm."""
+    rounded to bf16, . (W2_hi + W2_lo), + b2 + x (fp32 residual), LayerNorm.  terms = 1: the hi weight term only (the
+    decoder's kernel variant: triple-buffered acc1 / H, GEMM1 two chunks ahead, four-stage weight rings; F = 64 ... 320
+    covers chunk counts below, at and above the pipeline depth)."""
     s = setup()
     g = torch.Generator().manual_seed(M * 3 + F + splits)
     x = torch.randn(M, 128, generator=g).cuda()
@@ -126,11 +129,11 @@ def test_ffn_fused_tcgen05(M, F, splits):
     b2 = (0.1 * torch.randn(128, generator=g)).cuda()
     gamma = (1 + 0.1 * torch.randn(128, generator=g)).cuda()
     beta = (0.1 * torch.randn(128, generator=g)).cuda()
-    out = s["eng"].ffn(x, w1, b1, w2, b2, gamma, beta, splits=splits)
+    out = s["eng"].ffn(x, w1, b1, w2, b2, gamma, beta, splits=splits, weight_terms=terms)
 
     def two_term(w):
         hi = w.bfloat16()
-        return hi.double() + (w - hi.float()).bfloat16().double()
+        return hi.double() + ((w - hi.float()).bfloat16().double() if terms == 2 else 0.0)
     h = torch.relu(x.bfloat16().double() @ two_term(w1).T + b1.double())
     h = h.float().bfloat16().double()
     y = x.double() + h @ two_term(w2).T + b2.double()

@@ -566,7 +566,19 @@ def test_decode_is_invariant_to_lanes_graphs_pdl_and_repeats(precision):
         assert torch.equal(tok, tok0)
         torch.testing.assert_close(pr, pr0, atol=1e-5, rtol=0)
     else:
-        assert float((tok == tok0).float().mean()) > 0.97               # bf16 projections vs fp32-accumulated bf16-weight FMA
+        # bf16 tcgen05 projections vs fp32-accumulated bf16-weight FMA: the two kernel families differ by bf16 round-off, so a
+        # free-running sequence may leave the other family's ids -- but only at a near-tie: where the fp32 logits of the
+        # shared prefix have a top-2 margin below 2e-2 of the row scale (the north_star tolerance, applied to both sides)
+        mem32, _, kb32, *_ = s["eng"].encode(data, mode, "fp32")
+        trg = torch.cat([torch.full((1, tok0.shape[1]), 3, dtype=torch.int64, device=tok0.device), tok0[:-1]], dim=0)
+        lg = s["eng"].teacher_forced(mem32, kb32, trg, precision="fp32")
+        top2 = torch.topk(lg, 2, dim=2).values
+        margin = (top2[..., 0] - top2[..., 1]) / lg.abs().amax(dim=2)
+        ne = tok != tok0
+        for n in torch.nonzero(ne.any(dim=0))[:, 0].tolist():
+            t = int(torch.nonzero(ne[:, n])[0])
+            assert float(margin[t, n]) < 2e-2, (n, t, float(margin[t, n]))
+        assert float((tok[:8] == tok0[:8]).float().mean()) > 0.97
 
 
 def test_multinomial_cached_graph_follows_the_generator():
