@@ -1155,7 +1155,11 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         sp.pbias = pw.l2_b; sp.pgamma = pw.n3_w; sp.pbeta = pw.n3_b; sp.eps = 1e-5f;
     }
     prof_pre(e, s);
-    launch_kernel(sample_tokens, dim3((unsigned)((Nw + 7) / 8)), dim3(256), 0, s, pdl || pdl_u, sp);
+    {   // rows per CTA and pass: 2 when the input is still spread over FFN2 partials, else 8; at most four resident waves of CTAs
+        const int rpc = sp.part ? 2 : 8;
+        const int64_t groups = (Nw + rpc - 1) / rpc;
+        launch_kernel(sample_tokens, dim3((unsigned)std::min<int64_t>(groups, (int64_t)e->sm_count * 4)), dim3(256), 0, s, pdl || pdl_u, sp);
+    }
     MMT_TRY(check_launch(e, "sample_tokens", s));
     return 0;
 }
@@ -1801,7 +1805,7 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
     sp.advance = 0;
     cudaStream_t cs = (cudaStream_t)stream;
     prof_pre(e, cs);
-    sample_tokens<<<(unsigned)((N + 7) / 8), 256, 0, cs>>>(sp);
+    sample_tokens<<<(unsigned)std::min<int64_t>((N + 7) / 8, (int64_t)e->sm_count * 4), 256, 0, cs>>>(sp);
     return check_launch(e, "sample_tokens", cs);
 }
 

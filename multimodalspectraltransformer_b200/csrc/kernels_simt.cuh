@@ -1272,9 +1272,16 @@ struct SampleParams {
     const float* pbias; const float* pgamma; const float* pbeta; float eps;
 };
 
+// CTA = 8 warps.  Rows are taken in groups of `rpc` per CTA, grid-stride: a CTA stages fc_out once and keeps sampling
+// groups (large waves: 2048 CTAs each re-loading the 22 KB matrix cost more than the sampling itself).  rpc = 8: one warp
+// per row.  rpc = 2 (fused decoder path, whose input is still spread over the FFN2 split partials): four warps per row,
+// each with a quarter of the partials in flight at once -- the reduction is an L2 round trip per pass, so its depth sets
+// the kernel's latency on the 13-kernel chain of a small wave.
 __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ SampleParams p) {
     __shared__ float Ws[VOCAB_MAX * (D + 1)];
     __shared__ __align__(16) float xs[8][D];
+    __shared__ __align__(16) float psum[8][D];
+    __shared__ int s_nonpad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();
     // fc_out weights -> padded smem rows (independent of the step: issued before anything else)
@@ -1283,92 +1290,120 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
         float* dst = Ws + (i / (D / 4)) * (D + 1) + (i % (D / 4)) * 4;
         dst[0] = w.x; dst[1] = w.y; dst[2] = w.z; dst[3] = w.w;
     }
+    if (threadIdx.x == 0) s_nonpad = 0;
     pdl_wait();
     const int t = p.ctl.step ? *p.ctl.step : 0;
-    const int64_t n = (int64_t)blockIdx.x * 8 + warp;
-    if (n < p.N) {
-        float4 v = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+    const int rpc = p.part ? 2 : 8;                 // rows per CTA and pass
+    const int wpr = 8 / rpc;                        // warps per row in the input phase
+    int my_nonpad = 0;
+    for (int64_t base = (int64_t)blockIdx.x * rpc; base < p.N; base += (int64_t)gridDim.x * rpc) {
+        {   // ---- input rows -> xs
+            const int r = warp / wpr, sl = warp % wpr;
+            const int64_t n = base + r;
+            if (n < p.N) {
+                if (p.part) {
+                    // slice sl sums partials sl, sl + wpr, ... (all in flight together), fixed order
+                    float4 q[8];
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k0 = sl; k0 < p.splits; k0 += 8 * wpr) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int k = k0 + u * wpr;
+                            q[u] = (k < p.splits) ? *reinterpret_cast<const float4*>(p.part + (int64_t)k * p.part_stride + n * D + lane * 4)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { a.x += q[u].x; a.y += q[u].y; a.z += q[u].z; a.w += q[u].w; }
+                    }
+                    *reinterpret_cast<float4*>(&psum[warp][lane * 4]) = a;
+                } else if (sl == 0) {
+                    *reinterpret_cast<float4*>(&xs[r][lane * 4]) = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+                }
+            }
+        }
         if (p.part) {
-            float4 s = *reinterpret_cast<const float4*>(p.pbias + lane * 4);
-            for (int k0 = 0; k0 < p.splits; k0 += 8) {     // 8 partials in flight per pass, fixed summation order
-                float4 q[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    q[u] = (k0 + u < p.splits) ? *reinterpret_cast<const float4*>(p.part + (int64_t)(k0 + u) * p.part_stride + n * D + lane * 4)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { s.x += q[u].x; s.y += q[u].y; s.z += q[u].z; s.w += q[u].w; }
+            __syncthreads();
+            if (warp < rpc && base + warp < p.N) {   // x <- LN3(x + b2 + sum of the slices), slices in fixed order
+                const int64_t n = base + warp;
+                float4 v = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+                float4 sum = *reinterpret_cast<const float4*>(p.pbias + lane * 4);
+                for (int j = 0; j < wpr; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(&psum[warp * wpr + j][lane * 4]);
+                    sum.x += q.x; sum.y += q.y; sum.z += q.z; sum.w += q.w;
+                }
+                v = ln_row(make_float4(v.x + sum.x, v.y + sum.y, v.z + sum.z, v.w + sum.w), p.pgamma, p.pbeta, p.eps, lane);
+                *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = v;
             }
-            v = ln_row(make_float4(v.x + s.x, v.y + s.y, v.z + s.z, v.w + s.w), p.pgamma, p.pbeta, p.eps, lane);
         }
-        *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = v;
-    }
-    __syncthreads();
-    int picked_nonpad = 0;
-    if (n < p.N) {
-        const int v0 = lane, v1 = lane + 32;
-        float a0 = 0.f, a1 = 0.f;
-        const float* w0 = Ws + v0 * (D + 1);
-        const float* w1 = Ws + (v1 < p.V ? v1 : 0) * (D + 1);
+        __syncthreads();
+        const int64_t n = base + warp;
+        if (warp < rpc && n < p.N) {
+            const int v0 = lane, v1 = lane + 32;
+            float a0 = 0.f, a1 = 0.f;
+            const float* w0 = Ws + v0 * (D + 1);
+            const float* w1 = Ws + (v1 < p.V ? v1 : 0) * (D + 1);
 #pragma unroll 8
-        for (int k = 0; k < D; ++k) {
-            float xv = xs[warp][k];
-            a0 = fmaf(xv, w0[k], a0);
-            a1 = fmaf(xv, w1[k], a1);
-        }
-        const bool ok0 = v0 < p.V, ok1 = v1 < p.V;
-        float lg0 = ok0 ? a0 + p.b[v0] : MMT_NEG_INF;
-        float lg1 = ok1 ? a1 + p.b[v1] : MMT_NEG_INF;
-        if (p.logits) {
-            float* out = p.logits + ((int64_t)t * p.ldn + n) * p.V;
-            if (ok0) out[v0] = lg0;
-            if (ok1) out[v1] = lg1;
-        }
-        if (p.mode != 2) {
-            float z0 = ok0 ? lg0 / p.temperature : MMT_NEG_INF;
-            float z1 = ok1 ? lg1 / p.temperature : MMT_NEG_INF;
-            float mx = warp_max(fmaxf(z0, z1));
-            float e0 = ok0 ? expf(z0 - mx) : 0.f;
-            float e1 = ok1 ? expf(z1 - mx) : 0.f;
-            float sum = warp_sum(e0 + e1);
-            float p0 = e0 / sum, p1 = e1 / sum;
-            if (p.target) {       // probability of the given token (validate_generate_MMT_v15_4.py:372-374)
-                const int64_t tg = p.target[(int64_t)t * p.ldn + n];
-                const float a = __shfl_sync(0xffffffffu, p0, (int)(tg & 31)), b = __shfl_sync(0xffffffffu, p1, (int)(tg & 31));
-                if (lane == 0) p.target_prob[(int64_t)t * p.ldn + n] = (tg < 0 || tg >= p.V) ? 0.f : (tg < 32 ? a : b);
+            for (int k = 0; k < D; ++k) {
+                float xv = xs[warp][k];
+                a0 = fmaf(xv, w0[k], a0);
+                a1 = fmaf(xv, w1[k], a1);
             }
-            float r0 = p0, r1 = p1;
-            if (p.mode == 1) {
-                RngGeom g = p.rng;
-                if (p.rng_dev) { g.seed = p.rng_dev[0]; g.offset = p.rng_dev[1]; }
-                g.offset += (uint64_t)t * p.rng_inc;
-                int64_t li = (p.seq_index_base + n) * p.V;
-                if (ok0) r0 = p0 / torch_exponential_at(g, li + v0);
-                if (ok1) r1 = p1 / torch_exponential_at(g, li + v1);
+            const bool ok0 = v0 < p.V, ok1 = v1 < p.V;
+            float lg0 = ok0 ? a0 + p.b[v0] : MMT_NEG_INF;
+            float lg1 = ok1 ? a1 + p.b[v1] : MMT_NEG_INF;
+            if (p.logits) {
+                float* out = p.logits + ((int64_t)t * p.ldn + n) * p.V;
+                if (ok0) out[v0] = lg0;
+                if (ok1) out[v1] = lg1;
             }
-            // argmax with lowest-index ties (torch argmax / multinomial)
-            float best = ok0 ? r0 : MMT_NEG_INF;
-            int bi = ok0 ? v0 : 0x7fffffff;
-            float bp = p0;
-            if (ok1 && (r1 > best)) { best = r1; bi = v1; bp = p1; }
+            if (p.mode != 2) {
+                float z0 = ok0 ? lg0 / p.temperature : MMT_NEG_INF;
+                float z1 = ok1 ? lg1 / p.temperature : MMT_NEG_INF;
+                float mx = warp_max(fmaxf(z0, z1));
+                float e0 = ok0 ? expf(z0 - mx) : 0.f;
+                float e1 = ok1 ? expf(z1 - mx) : 0.f;
+                float sum = warp_sum(e0 + e1);
+                float p0 = e0 / sum, p1 = e1 / sum;
+                if (p.target) {       // probability of the given token (validate_generate_MMT_v15_4.py:372-374)
+                    const int64_t tg = p.target[(int64_t)t * p.ldn + n];
+                    const float a = __shfl_sync(0xffffffffu, p0, (int)(tg & 31)), b = __shfl_sync(0xffffffffu, p1, (int)(tg & 31));
+                    if (lane == 0) p.target_prob[(int64_t)t * p.ldn + n] = (tg < 0 || tg >= p.V) ? 0.f : (tg < 32 ? a : b);
+                }
+                float r0 = p0, r1 = p1;
+                if (p.mode == 1) {
+                    RngGeom g = p.rng;
+                    if (p.rng_dev) { g.seed = p.rng_dev[0]; g.offset = p.rng_dev[1]; }
+                    g.offset += (uint64_t)t * p.rng_inc;
+                    int64_t li = (p.seq_index_base + n) * p.V;
+                    if (ok0) r0 = p0 / torch_exponential_at(g, li + v0);
+                    if (ok1) r1 = p1 / torch_exponential_at(g, li + v1);
+                }
+                // argmax with lowest-index ties (torch argmax / multinomial)
+                float best = ok0 ? r0 : MMT_NEG_INF;
+                int bi = ok0 ? v0 : 0x7fffffff;
+                float bp = p0;
+                if (ok1 && (r1 > best)) { best = r1; bi = v1; bp = p1; }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                float op = __shfl_xor_sync(0xffffffffu, bp, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bp = op; }
-            }
-            if (lane == 0) {
-                if (p.tokens) p.tokens[(int64_t)t * p.ldn + n] = bi;
-                if (p.probs) p.probs[(int64_t)t * p.ldn + n] = bp;
-                picked_nonpad = (bi != 0);
+                for (int o = 16; o > 0; o >>= 1) {
+                    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    float op = __shfl_xor_sync(0xffffffffu, bp, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bp = op; }
+                }
+                if (lane == 0) {
+                    if (p.tokens) p.tokens[(int64_t)t * p.ldn + n] = bi;
+                    if (p.probs) p.probs[(int64_t)t * p.ldn + n] = bp;
+                    my_nonpad += (bi != 0);
+                }
             }
         }
+        __syncthreads();          // xs / psum are rewritten by the next group
     }
     if (p.advance || p.ctl.nonpad) {
-        const int cta_nonpad = __syncthreads_count(picked_nonpad);   // one atomic per CTA, not per sequence
-        if (threadIdx.x == 0) {
-            if (p.ctl.nonpad && cta_nonpad) atomicAdd(p.ctl.nonpad + t, cta_nonpad);
+        if (my_nonpad) atomicAdd(&s_nonpad, my_nonpad);
+        __syncthreads();
+        if (threadIdx.x == 0) {   // one global atomic per CTA, not per sequence
+            if (p.ctl.nonpad && s_nonpad) atomicAdd(p.ctl.nonpad + t, s_nonpad);
             if (p.advance) {
                 __threadfence();
                 int done = atomicAdd(p.ctl.done_ctas, 1);

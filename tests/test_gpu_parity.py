@@ -578,7 +578,7 @@ def test_decode_is_invariant_to_lanes_graphs_pdl_and_repeats(precision):
         for n in torch.nonzero(ne.any(dim=0))[:, 0].tolist():
             t = int(torch.nonzero(ne[:, n])[0])
             assert float(margin[t, n]) < 2e-2, (n, t, float(margin[t, n]))
-        assert float((tok[:8] == tok0[:8]).float().mean()) > 0.97
+        assert float(ne.any(dim=0).float().mean()) < 0.5                 # most sequences never meet a near-tie in 48 steps
 
 
 def test_multinomial_cached_graph_follows_the_generator():
