@@ -1174,7 +1174,11 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     if ((a.stride_s % 4) || (a.stride_b % 4) || ((uintptr_t)a.d_memory % 16)) MMT_FAIL("decode: memory must be 16-byte aligned with strides that are multiples of 4 floats");
     const int64_t N_total = (int64_t)a.Bm * a.n_cand;
     // waves: bound the self-attention KV pool (fp32: max_len*6*2*128*4 B per sequence)
-    const int64_t max_wave_seqs = e->max_wave_seqs;
+    // Sequences decoded together.  A wave's KV pool is 393 KB per sequence in bf16 (6 layers x 8 pages x 8 KB; twice that in
+    // fp32), so the default is 65,536 sequences = 25.8 GB in bf16 and 32,768 in fp32.  Larger waves amortise the ~31 kernel
+    // boundaries of an un-fused step: measured 1376 -> 1214 us per position and 16,384 sequences going from waves of
+    // 16,384 to 65,536 (profiles/r02_config3.md); 131,072 in one wave is within 1 % of that for twice the pool.
+    const int64_t max_wave_seqs = e->max_wave_seqs > 0 ? e->max_wave_seqs : (a.precision == MMT_PREC_BF16 ? 65536 : 32768);
     int Bm_wave = (int)std::max<int64_t>(1, std::min<int64_t>(a.Bm, max_wave_seqs / a.n_cand));
     const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
     if (a.precision != MMT_PREC_FP32 && a.precision != MMT_PREC_BF16) MMT_FAIL("decode: bad precision");
@@ -1557,7 +1561,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));
-    if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));
+    if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));     // 0 / unset: by precision
     if (n_floats != e->reg.total) { delete e; MMT_FAIL("weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(build_registry(*desc).total)); }
     auto fail = [&](const std::string& m) { mmt_destroy(e); g_last_error = m; return 1; };
     if (cudaMalloc(&e->w32, n_floats * sizeof(float)) != cudaSuccess) return fail("cudaMalloc weights failed");

@@ -2,9 +2,10 @@
 
     config 2   greedy, 256 spectra x 128 tokens: fp32 check mode ids == the CPU oracle for all 256 columns;
                bf16 tensor-core mode under north_star's margin rule
-    config 3   multinomial, 1024 spectra x 128 candidates (131,072 sequences, 8 waves of 16,384, Philox offset
-               increment 20 per step), 16 positions: offset bookkeeping, shard invariance, and a subset of every
-               wave against the oracle loop run on the device with the bit-exact Exp(1) variates
+    config 3   multinomial, 1024 spectra x 128 candidates (131,072 sequences in waves of 65,536 (bf16) / 32,768 (fp32),
+               Philox offset increment 20 per step), 16 positions: offset bookkeeping, shard invariance, and spectra
+               of the first, a middle and the last wave against the oracle loop run on the device with the bit-exact
+               Exp(1) variates
     config 5   max peak counts (582 attended memory rows per spectrum) + 128 tokens, 64 spectra, fp32 and bf16
     ADVICE r1  bf16 runs whose last wave is short (16,384 + 1,024 sequences; 600 x 16 beam slots)
 
@@ -37,6 +38,20 @@ def setup():
 
 def cfg_for(**over):
     return setup()["M"].default_config(device="cuda", **over)
+
+
+def model_with(monkeypatch, **env):
+    """A second model with the same seeded weights whose engine is created under the given MMT_* knobs."""
+    M = setup()["M"]
+    from multimodalspectraltransformer_b200.engine import engine_for
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    torch.manual_seed(0)
+    m = M.MultimodalTransformer(cfg_for()).eval()
+    engine_for(m, cfg_for())                  # the engine reads its knobs at creation
+    for k in env:
+        monkeypatch.delenv(k)
+    return m
 
 
 def oracle_greedy(tag, B, seed, peaks):
@@ -124,7 +139,7 @@ def test_config5_max_peaks_128_tokens_fp32_and_bf16():
 # ------------------------------------------------------------------------------------------------ config 3
 @pytest.mark.parametrize("precision,floor", [("fp32", 0.95), ("bf16", 0.6)])
 def test_config3_eight_waves_multinomial_131072_sequences(precision, floor):
-    """1024 spectra x 128 candidates, multinomial, 16 positions: eight waves of 16,384 sequences, numel = 131,072 x 43
+    """1024 spectra x 128 candidates, multinomial, 16 positions: two (bf16) / four (fp32) waves, numel = 131,072 x 43
     > 4 x 1,212,416 -> Philox loop iterations 0..4, offset += 20 per step.  fp32 check mode and the bf16 bench mode."""
     s = setup()
     from multimodalspectraltransformer_b200 import synthetic
@@ -181,20 +196,9 @@ def test_config3_waves_equal_single_wave(monkeypatch):
     data = synthetic.make_spectra(300, seed=3113)
     T, K = 12, 16
 
-    def model_with(**env):
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        torch.manual_seed(0)
-        m = M.MultimodalTransformer(cfg_for()).eval()
-        from multimodalspectraltransformer_b200.engine import engine_for
-        engine_for(m, cfg_for())                  # the engine reads its knobs at creation
-        for k in env:
-            monkeypatch.delenv(k)
-        return m
-
-    m_one = model_with(MMT_FUSED_DECODE_ROWS="0")
-    m_waves = model_with(MMT_FUSED_DECODE_ROWS="0", MMT_MAX_WAVE_SEQS="1024")
-    m_fused_waves = model_with(MMT_MAX_WAVE_SEQS="1024")
+    m_one = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0")
+    m_waves = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_MAX_WAVE_SEQS="1024")
+    m_fused_waves = model_with(monkeypatch, MMT_MAX_WAVE_SEQS="1024")
     for prec in ("fp32", "bf16"):
         cfg = cfg_for(precision=prec, max_len=T)
         memory, mask, *_ = M.run_model(s["model"], data, cfg)
@@ -216,10 +220,10 @@ def test_config3_waves_equal_single_wave(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ ADVICE r1 (high)
-def test_bf16_short_last_wave_16384_plus_1024():
-    """136 spectra x 128 candidates = 16,384 + 1,024 sequences in bf16: the short last wave takes the fused split-F path
-    whose partial buffer used to be sized for the planned (large) wave only.  Its columns must equal the same 8 spectra
-    decoded alone."""
+def test_bf16_short_last_wave_16384_plus_1024(monkeypatch):
+    """136 spectra x 128 candidates in waves of 16,384 = 16,384 + 1,024 sequences in bf16: the short last wave takes the
+    fused split-F path whose partial buffer used to be sized for the planned (large) wave only.  Its columns must equal
+    the same 8 spectra decoded alone."""
     s = setup()
     from multimodalspectraltransformer_b200 import synthetic
     M = s["M"]
@@ -227,8 +231,9 @@ def test_bf16_short_last_wave_16384_plus_1024():
     data = synthetic.make_spectra(B, seed=1361)
     cfg = cfg_for(precision="bf16", max_len=T)
     memory, mask, *_ = M.run_model(s["model"], data, cfg)
+    m16k = model_with(monkeypatch, MMT_MAX_WAVE_SEQS="16384")
     torch.manual_seed(5)
-    tok, pr = M.multinomial_sequence_multi(s["model"], memory, mask, STOI, cfg, n_candidates=K)
+    tok, pr = M.multinomial_sequence_multi(m16k, memory, mask, STOI, cfg, n_candidates=K)
     torch.manual_seed(5)
     tok_s, pr_s = M.multinomial_sequence_multi(s["model"], memory[:, 128:], mask[128:], STOI, cfg, n_candidates=K,
                                                seq_index_base=128 * K, n_total=B * K)
