@@ -196,8 +196,9 @@ static TcGemmParams tc_params(int M, int N, int K) {
 
 // A [M,K] bf16 (row pitch lda), W [N,K] bf16 (dense), optional low-order weight term Wlo; the
 // rest of `p` is filled by the caller
+struct TcChain { const __nv_bfloat16 *W, *Wlo; const float* bias; float* out; int64_t ld; };
 static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int epi, cudaStream_t s,
-                     const __nv_bfloat16* Wlo = nullptr, bool pdl = false) {
+                     const __nv_bfloat16* Wlo = nullptr, bool pdl = false, const TcChain* chain = nullptr) {
     if (p.M <= 0) return 0;
     MMT_TRY(tc_init(e));
     if (p.K % TC_BK || p.N % 4) MMT_FAIL("tcgen05 GEMM needs K % 64 == 0 and N % 4 == 0");
@@ -212,7 +213,14 @@ static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int
     MMT_TRY(make_tmap(&p.tmA, A, p.M, p.K, lda));
     MMT_TRY(make_tmap(&p.tmW, W, p.N, p.K, p.K));
     if (p.wsplit) MMT_TRY(make_tmap(&p.tmW2, Wlo, p.N, p.K, p.K));
-    const size_t smem = (size_t)std::max(p.stages * (p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES), TC_STAGING_BYTES) + 1024;
+    size_t smem = (size_t)std::max(p.stages * (p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES), TC_STAGING_BYTES) + 1024;
+    if (chain) {
+        if (epi != TC_EPI_LN || !chain->W || !chain->Wlo || !chain->bias || !chain->out) MMT_FAIL("chained projection needs the LayerNorm epilogue and a two-term weight");
+        p.chain = 1; p.chain_bias = chain->bias; p.chain_out = chain->out; p.ld_chain = chain->ld;
+        MMT_TRY(make_tmap(&p.tmC, chain->W, D, D, D));
+        MMT_TRY(make_tmap(&p.tmC2, chain->Wlo, D, D, D));
+        smem = ((smem - 1024 + 1023) & ~size_t(1023)) + TC_CHAIN_BYTES + 1024;
+    }
     dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
     prof_pre(e, s);
     if (epi == TC_EPI_LN) launch_kernel(gemm_bf16_tc<TC_EPI_LN>, grid, dim3(TC_THREADS), smem, s, pdl, p);
@@ -1006,11 +1014,12 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         p.splits = splits; p.part_stride = Nw * D;
         return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s, e->Wlo(W), pdl_u);
     };
-    auto tc_ln = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, int K, const float* gamma, const float* beta) -> int {
+    auto tc_ln = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, int K, const float* gamma, const float* beta,
+                     const TcChain* chain = nullptr) -> int {
         TcGemmParams p = tc_params(M, D, K);
         p.bias = bias; p.res = b.x; p.gamma = gamma; p.beta = beta;
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W), pdl_u);
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W), pdl_u, chain);
     };
     // The decoder FFN runs on the hi term of the bf16 weight split alone: measured on the 12 golden cases the lo term changes
     // the worst logit error from 5.75e-3 to 5.76e-3 of the row scale (profiles/r02_bf16_error.md) for twice the tensor work.
@@ -1091,8 +1100,16 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             else decode_self_attention_g8<8, float><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_self_attention", s));
             if (bf16) {
-                MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
-                MMT_TRY(tc(b.x16, D, w.ca_in_w, w.ca_in_b, b.qc, nullptr, D, D, 0, 1));
+                // out-proj + LN1 and the cross-attention query projection as one launch -- for waves up to 24,576 rows: the chained
+                // kernel holds 192 KB of shared memory (one CTA per SM instead of three), which costs more than the saved launch
+                // once there are several tiles per SM (measured: 1383 -> 1357 us per position at 16,384 rows, 4851 -> 4901 at 65,536)
+                if (e->use_gemm_chain && Nw <= 24576) {
+                    const TcChain ch{e->Wb(w.ca_in_w), e->Wlo(w.ca_in_w), w.ca_in_b, b.qc, D};
+                    MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b, &ch));
+                } else {
+                    MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
+                    MMT_TRY(tc(b.x16, D, w.ca_in_w, w.ca_in_b, b.qc, nullptr, D, D, 0, 1));
+                }
             } else {
                 MMT_TRY(gemm(b.att, D, w.out_w, nullptr, b.part, D, D, 0, 1));
                 MMT_TRY(ln(b.part, 1, w.out_b, w.n1_w, w.n1_b));
@@ -1559,6 +1576,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
+    if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));
     if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));     // 0 / unset: by precision

@@ -98,9 +98,6 @@ struct FfnParams {
                                      // 2 no conversion work, 4 no MMAs
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // TMEM -> staging tile for an accumulator stored as two 128-column halves (hi | lo): the halves are summed on the way
 __device__ __forceinline__ void epi_tmem2_to_stage(uint32_t tmem_acc, int q, int hf, int lane, float* stage_q) {

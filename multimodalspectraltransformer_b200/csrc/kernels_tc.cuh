@@ -56,7 +56,14 @@ struct TcGemmParams {
     // output row map (in rows): (r / S_in) * stride_b + (r % S_in) * stride_s + off
     int S_in; int64_t stride_b, stride_s, off;
     const int* out_rows;      // optional explicit output row per input row (ragged encoder), overrides the affine map
+    // Chained projection (LayerNorm epilogue only): chain_out[r] = bf16(LN output row r) . Wc^T + chain_bias, Wc [128,128] as a
+    // two-term bf16 split.  The decoder's "out-proj + LN1" and "cross-attention query projection" as ONE launch: the
+    // normalised rows go to shared memory as the A operand of a second MMA instead of round-tripping through HBM.
+    int chain;
+    CUtensorMap tmC, tmC2;    // Wc hi / lo, box {64,128}, SWIZZLE_128B
+    const float* chain_bias; float* chain_out; int64_t ld_chain;
 };
+constexpr int TC_CHAIN_BYTES = 6 * TC_SLAB_BYTES;        // A2 (2 K slabs) | Wc hi (2) | Wc lo (2) = 96 KB
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,6 +73,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -209,8 +219,10 @@ struct RowStep {
 };
 
 // out[map(r)] = LN(stage[r] + bias + res[r]) * gamma + beta for the warp's 32 rows (N == 128)
+// a2 != nullptr: the normalised rows are also written as bf16 into a 128B-swizzled K-major operand tile (two K slabs of
+// [128 rows x 64]); a2_row0 = tile-local index of the warp's first row
 template <class P>
-__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int nrows, int lane) {
+__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int nrows, int lane, uint8_t* a2 = nullptr, int a2_row0 = 0) {
     const int col = lane * 4;
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + col);
@@ -251,6 +263,10 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
                 const int64_t orow = p.out_rows ? (int64_t)p.out_rows[row0 + i0 + u] : map.next();
                 if (out32) *reinterpret_cast<float4*>(out32 + orow * ld32) = o;
                 if (out16) *reinterpret_cast<uint2*>(out16 + orow * ld16) = pack_bf16x4(o);
+                if (a2) {     // column 4 lane .. 4 lane + 3: slab lane / 16, 16-byte chunk (lane % 16) / 2 (XOR row & 7), half lane & 1
+                    const int rt = a2_row0 + i0 + u;
+                    *reinterpret_cast<uint2*>(a2 + (lane >> 4) * TC_SLAB_BYTES + rt * 128 + (((((lane & 15) >> 1) ^ (rt & 7))) << 4) + ((lane & 1) << 3)) = pack_bf16x4(o);
+                }
             }
         }
     }
@@ -309,10 +325,12 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
     __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t chain_w_bar, chain_a_bar, chain_acc_bar;
     __shared__ uint32_t tmem_slot;
 
     // 1024-byte alignment by pointer arithmetic on the shared array (keeps the shared address space: LDS/STS, not generic)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const bool chain = EPI == TC_EPI_LN && p.chain;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM;
     const int split = blockIdx.z;
@@ -323,6 +341,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
     const int num_kb = kb_end - kb_begin;      // host guarantees >= 1
 
     const int stage_bytes = p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES;
+    // chained projection: its operands live behind the stage ring / staging tile
+    uint8_t* sC = smem + ((max(p.stages * stage_bytes, TC_STAGING_BYTES) + 1023) & ~1023);
+    const uint32_t tmem_cols = chain ? 2 * TC_BN : TC_BN;
     pdl_launch_dependents();     // programmatic dependent launch (un-fused decode step): barrier / TMEM set-up overlaps the predecessor's tail
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
@@ -330,9 +351,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
         if (p.wsplit) tma_prefetch_desc(&p.tmW2);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
+        if (chain) { tma_prefetch_desc(&p.tmC); tma_prefetch_desc(&p.tmC2); mbar_init(&chain_w_bar, 1); mbar_init(&chain_a_bar, TC_EPI_WARPS); mbar_init(&chain_acc_bar, 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, TC_BN);
+    if (warp == 1) tmem_alloc(&tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -340,6 +362,13 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
+            if (chain) {             // the chained weights are decode-loop constants: in flight before the PDL wait
+                mbar_arrive_expect_tx(&chain_w_bar, 4 * TC_SLAB_BYTES);
+                for (int ks = 0; ks < 2; ++ks) {
+                    tma_load_2d(sC + (2 + ks) * TC_SLAB_BYTES, &p.tmC, &chain_w_bar, ks * TC_BK, 0);
+                    tma_load_2d(sC + (4 + ks) * TC_SLAB_BYTES, &p.tmC2, &chain_w_bar, ks * TC_BK, 0);
+                }
+            }
             pdl_wait();              // A is the predecessor's output
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % p.stages;
@@ -375,6 +404,22 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
                 umma_commit(&empty_bar[s]);            // smem slot reusable once these MMAs retire
             }
             umma_commit(&tmem_full_bar);               // accumulator complete
+            if (chain) {     // second product on the normalised rows the epilogue warps put into shared memory (same K-slab / term order as a stand-alone launch)
+                mbar_wait(&chain_w_bar, 0);
+                mbar_wait(&chain_a_bar, 0);
+                tc_fence_after();
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(sC + ks * TC_SLAB_BYTES));
+#pragma unroll
+                    for (int t2 = 0; t2 < 2; ++t2) {
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(sC + (2 + 2 * t2 + ks) * TC_SLAB_BYTES));
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            umma_bf16(tmem_base + TC_BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks > 0 || t2 > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&chain_acc_bar);
+            }
         }
     } else {
         // ---------------- epilogue: 8 warps, warp (id % 4) owns TMEM lanes [32*(id%4), +32), two warps per quarter
@@ -386,14 +431,29 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
         epi_tmem_to_stage<TC_BN>(tmem_base, q, hf, lane, stage_q);
         epi_bar_sync();
         const float* st = stage_q + (hf * 16) * TC_LDS;
-        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane);
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane, chain ? sC : nullptr, q * 32 + hf * 16);
         else epi_rows_store(p, st, m0 + q * 32 + hf * 16, 16, n0, split, lane);
+        if (chain) {
+            fence_proxy_async_smem();          // the A2 rows (generic-proxy stores) -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&chain_a_bar);
+            mbar_wait(&chain_acc_bar, 0);      // (implies every epilogue warp is done with the staging tile)
+            tc_fence_after();
+            epi_tmem_to_stage<TC_BN>(tmem_base + TC_BN, q, hf, lane, stage_q);
+            epi_bar_sync();
+            const int r0 = m0 + q * 32 + hf * 16, rows = min(16, p.M - r0);
+            const float4 cb = *reinterpret_cast<const float4*>(p.chain_bias + lane * 4);
+            for (int i = 0; i < rows; ++i) {
+                const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS + lane * 4);
+                *reinterpret_cast<float4*>(p.chain_out + (int64_t)(r0 + i) * p.ld_chain + lane * 4) = make_float4(a.x + cb.x, a.y + cb.y, a.z + cb.z, a.w + cb.w);
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TC_BN);
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 

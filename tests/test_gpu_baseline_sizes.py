@@ -261,3 +261,23 @@ def test_bf16_beam_600_items_16_beams_short_last_wave():
         a, b = beams[512 + i], alone[i]
         assert [x[1] for x in a] == [x[1] for x in b], i
         np.testing.assert_allclose([x[0] for x in a], [x[0] for x in b], rtol=1e-6)
+
+
+def test_chained_projection_equals_two_launches(monkeypatch):
+    """The un-fused decode step issues "out-proj + LN1" and the cross-attention query projection as ONE tcgen05 launch (the
+    normalised rows feed a second MMA from shared memory): bit for bit the two-launch result, for a ragged row count (partial
+    last tile, split-F FFN path) and for a multi-tile wave."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    M = s["M"]
+    m_chain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0")
+    m_plain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_NO_GEMM_CHAIN="1")
+    for B, K, T in ((41, 7, 10), (300, 16, 6)):
+        data = synthetic.make_spectra(B, seed=700 + B)
+        cfg = cfg_for(precision="bf16", max_len=T)
+        memory, mask, *_ = M.run_model(s["model"], data, cfg)
+        out = []
+        for m in (m_chain, m_plain):
+            torch.manual_seed(11)
+            out.append(M.multinomial_sequence_multi(m, memory, mask, STOI, cfg, n_candidates=K))
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), (B, K)
