@@ -238,8 +238,9 @@ static FfnParams ffn_params(int M, int F) {
 
 // Fused FFN (kernels_ffn.cuh): X [M,128] bf16 (row pitch ldx); W1 [F,128] / W2 [128,F] as bf16 hi (+ lo) terms.
 // splits == 1 with epi == TC_EPI_LN: out = LN(res + b2 + FFN(X)); splits > 1: raw partials to out_f32.
+struct FfnPro { const __nv_bfloat16 *W, *Wlo; const float *bias, *gamma, *beta; float* out; };
 static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W1, const __nv_bfloat16* W1lo,
-                      const __nv_bfloat16* W2, const __nv_bfloat16* W2lo, int epi, cudaStream_t s, bool pdl = false) {
+                      const __nv_bfloat16* W2, const __nv_bfloat16* W2lo, int epi, cudaStream_t s, bool pdl = false, const FfnPro* pro = nullptr) {
     if (p.M <= 0) return 0;
     MMT_TRY(tc_init(e));
     if (p.F % FF_CH || p.F > FF_MAX_F || p.F < FF_CH) MMT_FAIL("fused FFN needs d_ff % 64 == 0 and d_ff <= 2048");
@@ -254,6 +255,13 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
     if (p.wsplit) {
         MMT_TRY(make_tmap(&p.tmW1lo, W1lo, p.F, D, D, FF_CH));
         MMT_TRY(make_tmap(&p.tmW2lo, W2lo, D, p.F, p.F));
+    }
+    if (pro) {
+        if (epi != TC_EPI_LN || p.splits != 1 || !pro->W || !pro->Wlo || !pro->out || p.res != pro->out)
+            MMT_FAIL("fused FFN prologue needs the LayerNorm epilogue, a two-term weight and the residual buffer as its output");
+        p.pro = 1; p.pro_bias = pro->bias; p.pro_gamma = pro->gamma; p.pro_beta = pro->beta; p.pro_out = pro->out;
+        MMT_TRY(make_tmap(&p.tmP, pro->W, D, D, D));
+        MMT_TRY(make_tmap(&p.tmPlo, pro->Wlo, D, D, D));
     }
     dim3 grid(p.splits, (p.M + TC_BM - 1) / TC_BM);
     if (const char* v = getenv("MMT_FFN_KNOCK")) p.knock = atoi(v);
@@ -1122,7 +1130,8 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             else decode_cross_attention<8, float><<<attn_blocks, 256, 0, s>>>(b.qc, reinterpret_cast<const float*>(ckv), a.S, b.nk, b.row_start, b.kbias_c, a.n_cand, Nw, H, scale, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_cross_attention", s));
             if (bf16) {
-                MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
+                const bool ffn_pro = e->use_ffn_prologue && M >= 2048;     // cross-attention out-projection + norm2 as the FFN kernel's prologue
+                if (!ffn_pro) MMT_TRY(tc_ln(b.att16, D, w.ca_out_w, w.ca_out_b, D, w.n2_w, w.n2_b));
                 if (M >= 2048) {
                     FfnParams f = ffn_params(M, d.d_ff);
                     f.b1 = w.l1_b; f.bias = w.l2_b; f.res = b.x; f.gamma = w.n3_w; f.beta = w.n3_b; f.out_f32 = b.x; f.out_b16 = b.x16;
@@ -1130,6 +1139,10 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                         if (!e->ffn_dbg) { MMT_CUDA(cudaMallocManaged(&e->ffn_dbg, 4096 * 16 * sizeof(long long))); memset(e->ffn_dbg, 0, 4096 * 16 * sizeof(long long)); }
                         f.dbg = l == 3 ? e->ffn_dbg : nullptr;
                     }
+                    if (ffn_pro) {
+                        const FfnPro pr{e->Wb(w.ca_out_w), e->Wlo(w.ca_out_w), w.ca_out_b, w.n2_w, w.n2_b, b.x};
+                        MMT_TRY(launch_ffn(e, f, b.att16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_LN, s, pdl_u, &pr));
+                    } else
                     MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_LN, s, pdl_u));
                 } else {   // few rows: split F over the grid, reduce the partials in the LayerNorm kernel
                     FfnParams f = ffn_params(M, d.d_ff);
@@ -1577,6 +1590,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
     if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
+    if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));
     if (const char* v = getenv("MMT_MAX_WAVE_SEQS")) e->max_wave_seqs = std::max(1, atoi(v));     // 0 / unset: by precision

@@ -94,6 +94,13 @@ struct FfnParams {
     int S_in; int64_t stride_b, stride_s, off;
     const int* out_rows;             // optional explicit output rows (LayerNorm epilogue, ragged encoder)
     long long* dbg;                  // optional [CTA][16] phase timestamps (MMT_DA_DEBUG)
+    // Prologue (LayerNorm-epilogue variant only): X is not the FFN input but the attention output of the block before it;
+    // the kernel first computes  x = LN(res + X . Wp^T + pro_bias) * pro_gamma + pro_beta  (the decoder's cross-attention
+    // out-projection + norm2), writes it to pro_out (fp32, the residual of the FFN's own LayerNorm) and to the X tile in shared
+    // memory (bf16), then runs the FFN on it: one launch and one HBM round trip of the activations less per layer.
+    int pro;
+    CUtensorMap tmP, tmPlo;          // Wp [128,128] bf16 hi / lo, box {64,128}
+    const float *pro_bias, *pro_gamma, *pro_beta; float* pro_out;
     int knock;                       // timing experiments only (MMT_FFN_KNOCK, results garbage): 1 no weight TMA after the first ring fill,
                                      // 2 no conversion work, 4 no MMAs
 };
@@ -117,6 +124,12 @@ __device__ __forceinline__ void epi_tmem2_to_stage(uint32_t tmem_acc, int q, int
     }
 }
 
+// the fields epi_rows_ln reads, for the prologue's LayerNorm
+struct LnView {
+    const float *bias, *gamma, *beta, *res; float* out_f32; __nv_bfloat16* out_b16; int64_t ld_f32, ld_b16; int M; float eps;
+    const int* out_rows; int S_in; int64_t stride_b, stride_s, off;
+};
+
 template <int EPI, int WS>
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
     typedef FfCfg<WS> C;
@@ -128,6 +141,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     constexpr int R = 12;
     static_assert(R % NS == 0 && R % NB == 0, "barrier ring must be a multiple of both buffer counts");
     __shared__ __align__(8) uint64_t x_full, w1_full[NS], w2_full[NS], h_full[NB], g1_done[R], g2_done[R], acc2_full;
+    __shared__ __align__(8) uint64_t pro_w_full, pro_acc_full, x2_ready;
+    const bool pro = EPI == TC_EPI_LN && p.pro;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sB1[FF_MAX_F];     // this CTA's slice of b1: one load at kernel start instead of an L2 round trip in every chunk's conversion
 
@@ -152,6 +167,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         for (int s = 0; s < NS; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w2_full[s], 1); }
         for (int s = 0; s < NB; ++s) mbar_init(&h_full[s], TC_EPI_WARPS);     // one arrival per epilogue warp (256 arrivals on one barrier serialise)
         for (int s = 0; s < R; ++s) { mbar_init(&g1_done[s], 1); mbar_init(&g2_done[s], 1); }
+        if (pro) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmPlo); mbar_init(&pro_w_full, 1); mbar_init(&pro_acc_full, 1); mbar_init(&x2_ready, TC_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, FF_TMEM_COLS);
@@ -177,9 +193,20 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         // waits stall each other: a lane parked in try_wait holds the warp, measured ~1.1 K cycles per chunk with nothing
         // else in the loop.)  Order per chunk: W1(i) as soon as GEMM1(i - NS) retired, then W2(i) once GEMM2(i - NS) retired.
         if (lane == 0) {
+            if (pro) {
+                // prologue weights (decode-loop constants) into the still idle W2 ring, then the attention output tile; the
+                // weight rings start only when the prologue is over: its staging tile lies over them
+                mbar_arrive_expect_tx(&pro_w_full, 4 * TC_SLAB_BYTES);
+                for (int ks = 0; ks < 2; ++ks) {
+                    tma_load_2d(sW2 + ks * TC_SLAB_BYTES, &p.tmP, &pro_w_full, ks * TC_BK, 0);
+                    tma_load_2d(sW2 + (2 + ks) * TC_SLAB_BYTES, &p.tmPlo, &pro_w_full, ks * TC_BK, 0);
+                }
+                pdl_wait(); load_x();
+                mbar_wait(&x2_ready, 0);
+            }
             for (int i = 0; i < n; ++i) {
                 const int s = i % NS, c = c0 + i;
-                if (i == min(n, NS)) { pdl_wait(); load_x(); }      // the first ring fill is decode-loop constants only: ahead of the PDL wait
+                if (!pro && i == min(n, NS)) { pdl_wait(); load_x(); }      // the first ring fill is decode-loop constants only: ahead of the PDL wait
                 if (i >= NS) mbar_wait(&g1_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM1 of the stage's previous chunk retired
                 if (!((p.knock & 1) && i >= NS)) {
                     mbar_arrive_expect_tx(&w1_full[s], C::W1_STAGE);
@@ -199,7 +226,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                     if (WS) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
                 } else mbar_arrive(&w2_full[s]);
             }
-            if (n <= NS) { pdl_wait(); load_x(); }     // short loops never reached the in-loop wait
+            if (!pro && n <= NS) { pdl_wait(); load_x(); }     // short loops never reached the in-loop wait
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -208,6 +235,24 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             // GEMM1 issue stream: acc1[i % NB] = X . [W1_hi (; W1_lo)][chunk i]^T.  The accumulator buffer is free once the
             // conversion of chunk i - NB has read it (h_full of that chunk).
             mbar_wait(&x_full, 0);
+            if (pro) {       // acc2 = X . [Wp_hi ; Wp_lo]^T as two accumulating passes per K slab (the order of a stand-alone launch)
+                mbar_wait(&pro_w_full, 0);
+                tc_fence_after();
+                const uint32_t idescP = umma_idesc_bf16(TC_BM, TC_BN);
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t adesc = umma_desc_sw128(x_addr + ks * TC_SLAB_BYTES);
+#pragma unroll
+                    for (int t2 = 0; t2 < 2; ++t2) {
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(sW2 + (2 * t2 + ks) * TC_SLAB_BYTES));
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idescP, (ks > 0 || t2 > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&pro_acc_full);
+                mbar_wait(&x2_ready, 0);       // the epilogue warps have replaced the X tile by the normalised rows
+                tc_fence_after();
+            }
             for (int i = 0; i < n; ++i) {
                 const int s = i % NS;
                 mbar_wait(&w1_full[s], ((uint32_t)(i / NS)) & 1u);
@@ -247,6 +292,19 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         // the two warps of a quarter split the chunk's 64 columns
         const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
+        if (pro) {
+            mbar_wait(&pro_acc_full, 0);
+            tc_fence_after();
+            float* stage_p = reinterpret_cast<float*>(sW) + (q * 32) * TC_LDS;
+            epi_tmem_to_stage<TC_BN>(tmem_acc2, q, hf, lane, stage_p);
+            epi_bar_sync();
+            LnView v{p.pro_bias, p.pro_gamma, p.pro_beta, p.res, p.pro_out, nullptr, D, D, p.M, p.eps, nullptr, p.M > 0 ? p.M : 1, 0, 1, 0};
+            epi_rows_ln(v, stage_p + (hf * 16) * TC_LDS, m0 + q * 32 + hf * 16, 16, lane, sX, q * 32 + hf * 16);
+            fence_proxy_async_smem();          // the rewritten X tile -> visible to the tensor core
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x2_ready);
+        }
         for (int i = 0; i < n; ++i) {
             const int b = i % NB;
             const float4* bb = reinterpret_cast<const float4*>(sB1 + i * FF_CH + hf * 32);     // bias slice of this chunk (shared memory)

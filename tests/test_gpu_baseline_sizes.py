@@ -265,14 +265,15 @@ def test_bf16_beam_600_items_16_beams_short_last_wave():
 
 def test_chained_projection_equals_two_launches(monkeypatch):
     """The un-fused decode step issues "out-proj + LN1" and the cross-attention query projection as ONE tcgen05 launch (the
-    normalised rows feed a second MMA from shared memory): bit for bit the two-launch result, for a ragged row count (partial
-    last tile, split-F FFN path) and for a multi-tile wave."""
+    normalised rows feed a second MMA from shared memory), and for >= 2048 rows the cross-attention out-projection + norm2
+    as a prologue of the fused FFN kernel: bit for bit the separate-launch result, for a ragged row count (partial last
+    tile, split-F FFN path), a multi-tile wave and a wave whose last tile is partial (19 x 128 = 2432 rows)."""
     s = setup()
     from multimodalspectraltransformer_b200 import synthetic
     M = s["M"]
     m_chain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0")
-    m_plain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_NO_GEMM_CHAIN="1")
-    for B, K, T in ((41, 7, 10), (300, 16, 6)):
+    m_plain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_NO_GEMM_CHAIN="1", MMT_NO_FFN_PROLOGUE="1")
+    for B, K, T in ((41, 7, 10), (300, 16, 6), (19, 128, 5)):
         data = synthetic.make_spectra(B, seed=700 + B)
         cfg = cfg_for(precision="bf16", max_len=T)
         memory, mask, *_ = M.run_model(s["model"], data, cfg)
