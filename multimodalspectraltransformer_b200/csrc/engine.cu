@@ -998,7 +998,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     // griddepcontrol.wait before it touches its predecessor's output; the LayerNorm-only kernel has no hook and is launched plainly)
     // Only for moderate waves: measured 50.2 -> 45.2 ms for a beam search over 2560 slots, but 1426 -> 1473 us per position at
     // 16,384 sequences, where the early-scheduled CTAs take SM resources from a predecessor that is throughput-bound.
-    const bool pdl_u = !fused && bf16 && e->use_pdl && !e->profiling && Nw <= 4096;
+    const bool pdl_u = !fused && bf16 && e->use_pdl && !e->profiling && Nw <= e->pdl_rows;
     // x = LN(x + bias + sum_s part[s]) (separate kernel; fp32 mode and split-K FFN2)
     auto ln = [&](const float* part, int splits, const float* bias, const float* gamma, const float* beta) -> int {
         LnParams q;
@@ -1589,6 +1589,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
+    if (const char* v = getenv("MMT_PDL_ROWS")) e->pdl_rows = atoi(v);
     if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
     if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;

@@ -135,6 +135,7 @@ struct mmt_engine {
     cudaStream_t enc_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t enc_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int graph_steps = 16;              // decode positions captured per CUDA graph (MMT_GRAPH_STEPS overrides)
+    int pdl_rows = 4096;               // un-fused bf16 step: programmatic dependent launch through the kernel chain for waves up to this many rows (MMT_PDL_ROWS overrides)
     bool use_pdl = true;               // programmatic dependent launch between the kernels of a fused decode step (MMT_NO_PDL=1 disables)
     cudaStream_t cap_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // capture-only streams, one per decode lane (the caller's stream may be the legacy default stream)
     cudaEvent_t lane_ev[4] = {nullptr, nullptr, nullptr, nullptr};       // fork / join events of the lane branches

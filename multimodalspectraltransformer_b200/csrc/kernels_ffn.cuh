@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     __shared__ __align__(8) uint64_t pro_w_full, pro_acc_full, x2_ready;
     const bool pro = EPI == TC_EPI_LN && p.pro;
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float sB1[FF_MAX_F];     // this CTA's slice of b1: one load at kernel start instead of an L2 round trip in every chunk's conversion
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space
     uint8_t* sX = smem;
@@ -171,9 +170,6 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, FF_TMEM_COLS);
-    if (warp >= 2 && warp < FF_G2_WARP)       // b1 is a decode-loop constant: no PDL wait needed
-        for (int i = threadIdx.x - 64; i < n * (FF_CH / 4); i += TC_EPI_WARPS * 32)
-            reinterpret_cast<float4*>(sB1)[i] = __ldg(reinterpret_cast<const float4*>(p.b1 + (size_t)c0 * FF_CH) + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -204,27 +200,36 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                 pdl_wait(); load_x();
                 mbar_wait(&x2_ready, 0);
             }
-            for (int i = 0; i < n; ++i) {
-                const int s = i % NS, c = c0 + i;
-                if (!pro && i == min(n, NS)) { pdl_wait(); load_x(); }      // the first ring fill is decode-loop constants only: ahead of the PDL wait
-                if (i >= NS) mbar_wait(&g1_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM1 of the stage's previous chunk retired
-                if (!((p.knock & 1) && i >= NS)) {
-                    mbar_arrive_expect_tx(&w1_full[s], C::W1_STAGE);
-                    uint8_t* w = sW + (size_t)s * C::W1_STAGE;          // K slab ks at ks * W1_SLAB: rows 0-63 hi (, rows 64-127 lo)
-                    tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
-                    tma_load_2d(w + C::W1_SLAB, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
-                    if (WS) {
-                        tma_load_2d(w + FF_W1_HALF, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
-                        tma_load_2d(w + C::W1_SLAB + FF_W1_HALF, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
-                    }
-                } else mbar_arrive(&w1_full[s]);
-                if (i >= NS) mbar_wait(&g2_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM2 of the stage's previous chunk retired
-                if (!((p.knock & 1) && i >= NS)) {
-                    mbar_arrive_expect_tx(&w2_full[s], C::W2_STAGE);
-                    uint8_t* w = sW2 + (size_t)s * C::W2_STAGE;         // rows 0-127 hi (, rows 128-255 lo)
-                    tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
-                    if (WS) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
-                } else mbar_arrive(&w2_full[s]);
+            // W1(i) is needed LA = NB - 1 chunks before W2(i) (GEMM1 runs that far ahead of GEMM2), and its stage frees earlier
+            // (GEMM1(i - NS) retires before GEMM2(i - NS - LA)): the loop issues W1 LA chunks ahead so that no wait of one ring
+            // delays a load of the other.
+            constexpr int LA_P = NB - 1;
+            for (int it = 0; it < n + LA_P; ++it) {
+                if (it < n) {
+                    const int i = it, s = i % NS, c = c0 + i;
+                    if (!pro && i == min(n, NS)) { pdl_wait(); load_x(); }      // the first ring fill is decode-loop constants only: ahead of the PDL wait
+                    if (i >= NS) mbar_wait(&g1_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM1 of the stage's previous chunk retired
+                    if (!((p.knock & 1) && i >= NS)) {
+                        mbar_arrive_expect_tx(&w1_full[s], C::W1_STAGE);
+                        uint8_t* w = sW + (size_t)s * C::W1_STAGE;          // K slab ks at ks * W1_SLAB: rows 0-63 hi (, rows 64-127 lo)
+                        tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
+                        tma_load_2d(w + C::W1_SLAB, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
+                        if (WS) {
+                            tma_load_2d(w + FF_W1_HALF, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
+                            tma_load_2d(w + C::W1_SLAB + FF_W1_HALF, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
+                        }
+                    } else mbar_arrive(&w1_full[s]);
+                }
+                if (it >= LA_P) {
+                    const int i = it - LA_P, s = i % NS, c = c0 + i;
+                    if (i >= NS) mbar_wait(&g2_done[(i - NS) % R], ((uint32_t)((i - NS) / R)) & 1u);     // GEMM2 of the stage's previous chunk retired
+                    if (!((p.knock & 1) && i >= NS)) {
+                        mbar_arrive_expect_tx(&w2_full[s], C::W2_STAGE);
+                        uint8_t* w = sW2 + (size_t)s * C::W2_STAGE;         // rows 0-127 hi (, rows 128-255 lo)
+                        tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
+                        if (WS) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
+                    } else mbar_arrive(&w2_full[s]);
+                }
             }
             if (!pro && n <= NS) { pdl_wait(); load_x(); }     // short loops never reached the in-loop wait
         }
@@ -307,7 +312,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         }
         for (int i = 0; i < n; ++i) {
             const int b = i % NB;
-            const float4* bb = reinterpret_cast<const float4*>(sB1 + i * FF_CH + hf * 32);     // bias slice of this chunk (shared memory)
+            // bias slice of this chunk (a decode-loop constant): in registers before the accumulator is ready
+            float4 bb[8];
+            const float4* bsrc = reinterpret_cast<const float4*>(p.b1 + (size_t)(c0 + i) * FF_CH + hf * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bb[j] = __ldg(bsrc + j);
             mbar_wait(&g1_done[i % R], ((uint32_t)(i / R)) & 1u);
             tc_fence_after();
             if (threadIdx.x == 64 && i == 0) FF_STAMP(2);
