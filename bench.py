@@ -336,6 +336,31 @@ def main():
               * (FLOP_DECODE_PER_TOKEN + (FLOP_ENCODE_PER_SPECTRUM + FLOP_CROSSKV_PER_SPECTRUM) / MAX_LEN) / (peaks()["tf"] * 1e12)}
         del flush_buf
 
+    # ------------------------------------------------------------------ config 5 (extra key): max peak counts, greedy, 512 spectra per GPU
+    c5 = None
+    if not args.no_config2:
+        K5 = min(K, 5)
+        res5 = {k: v.to(dev) for k, v in synthetic.make_spectra(512, seed=5000 + rank, peaks="max").items()}
+        def step5():
+            memory, mask, *_ = M.run_model(model, res5, cfg)
+            tok, _ = M.greedy_sequence(model, STOI, None, memory, mask, cfg)
+            return tok
+        for _ in range(2):
+            step5()
+        barrier()
+        a5, b5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a5.record()
+        for _ in range(K5):
+            step5()
+        b5.record()
+        barrier()
+        ms5 = max_over_ranks(a5.elapsed_time(b5))
+        c5 = {"workload": "BASELINE.json configs[4] per-GPU share: 512 spectra with every peak slot valid (582 attended memory rows each), greedy, "
+                          f"{MAX_LEN} tokens, encode + decode per step, inputs resident, weak scaling",
+              "value": 512 * MAX_LEN * world * K5 / (ms5 / 1e3), "unit": UNIT, "ms_per_step": ms5 / K5, "steps": K5, "scaling": "weak",
+              "hbm_floor_note": "cross K/V of 512 x 582 rows x 6 layers in bf16 = 915 MB per position: 140 us per position at the measured HBM peak"}
+        del res5
+
     # ------------------------------------------------------------------ roofline of the dominant kernel (rank 0's GPU)
     pk = peaks()
     roof = None
@@ -399,6 +424,8 @@ def main():
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "wall_s": {"resident": wall_res, "e2e": wall_e2e}}
         if c2 is not None:
             line["config2"] = c2
+        if c5 is not None:
+            line["config5"] = c5
         if world == 1 and not args.no_cpu_baseline:
             try:     # the reference's algorithm under torch eager on this same B200 (library kernels): how much is the GPU, how much the engine
                 from oracle import mmt_oracle as O

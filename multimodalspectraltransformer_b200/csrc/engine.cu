@@ -1100,11 +1100,16 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             const LayerW& w = e->dec[l];
             char* pool = b.kv_pool + (size_t)l * b.pool_pages * 2 * PAGE_TOKENS * D * b.kv_esz;
             const char* ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz;
-            if (bf16) MMT_TRY(tc(b.x16, D, w.in_w, w.in_b, b.qkv, nullptr, 3 * D, D, 0, 1));
-            else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
+            if (bf16) {   // K | V columns of the projection land in the cache pages directly; the fp32 row keeps only Q
+                TcGemmParams p = tc_params(M, 3 * D, D);
+                p.bias = w.in_b; p.out_f32 = b.qkv; p.ld_f32 = 3 * D;
+                p.kv_append = e->use_kv_epilogue ? 1 : 0; p.kv_pool = reinterpret_cast<__nv_bfloat16*>(pool); p.block_table = b.block_table; p.pps = pps; p.step = step; p.kv_heads = H;
+                MMT_TRY(launch_tc(e, p, b.x16, D, e->Wb(w.in_w), TC_EPI_STORE, s, e->Wlo(w.in_w), pdl_u));
+            } else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
             prof_pre(e, s);
             const unsigned sa_blocks = (unsigned)((Nw * (H / 4) + 7) / 8);     // a warp per (sequence, 4 heads)
-            if (bf16) launch_args(decode_self_attention_g8<8, __nv_bfloat16>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
+            if (bf16 && e->use_kv_epilogue) launch_args(decode_self_attention_g8<8, __nv_bfloat16, false>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
+            else if (bf16) launch_args(decode_self_attention_g8<8, __nv_bfloat16>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
             else decode_self_attention_g8<8, float><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_self_attention", s));
             if (bf16) {
@@ -1591,6 +1596,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
     if (const char* v = getenv("MMT_PDL_ROWS")) e->pdl_rows = atoi(v);
     if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
+    if (getenv("MMT_NO_KV_EPILOGUE")) e->use_kv_epilogue = false;
     if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));

@@ -973,7 +973,8 @@ __global__ void __launch_bounds__(256) decode_self_attention(const float* qkv, K
 // leaves most lanes without a key and still pays a five-stage reduction of ten values; here the reduction is three
 // stages over eight lanes (8-value reduce-scatter: lane kl ends up with output dimension kl, so a warp stores 32
 // consecutive outputs) and the wave needs a quarter of the warps.  Online softmax, two keys per lane in flight.
-template <int DH, typename KVT>
+// APPEND = false: K / V of position t are already in the cache (written by the QKV projection's epilogue, kernels_tc.cuh).
+template <int DH, typename KVT, bool APPEND = true>
 __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv, KVT* kv_pool, const int* block_table,
                                                                 int pages_per_seq, int64_t N, int H, float scale,
                                                                 const int* step, float* out, __nv_bfloat16* out16) {
@@ -991,12 +992,12 @@ __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv
     constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
     const int* bt = block_table + n * pages_per_seq;
     const float* row = qkv + n * (3 * D) + h * DH;
-    {   // append K,V of position t: lane (hq, kl) writes element kl of its head's K and V rows
+    if (APPEND) {   // append K,V of position t: lane (hq, kl) writes element kl of its head's K and V rows
         KVT* page = kv_pool + (int64_t)bt[t / PAGE_TOKENS] * PAGE_ELEMS;
         KV::st(page + ((0 * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + kl, row[D + kl]);
         KV::st(page + ((1 * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + kl, row[2 * D + kl]);
+        __syncwarp();
     }
-    __syncwarp();
     float q[DH], acc[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) { q[d] = row[d] * scale; acc[d] = 0.f; }

@@ -56,6 +56,10 @@ struct TcGemmParams {
     // output row map (in rows): (r / S_in) * stride_b + (r % S_in) * stride_s + off
     int S_in; int64_t stride_b, stride_s, off;
     const int* out_rows;      // optional explicit output row per input row (ragged encoder), overrides the affine map
+    // Decoder self-attention QKV projection (N = 384): columns 128.. (K, V of the new position) go straight into the paged bf16
+    // KV cache of the layer -- page block_table[row * pps + t / 16], slot t % 16, t = *step -- instead of an fp32 row the
+    // attention kernel would re-read and append; only the Q columns are stored to out_f32.
+    int kv_append; __nv_bfloat16* kv_pool; const int* block_table; int pps; const int* step; int kv_heads;
     // Chained projection (LayerNorm epilogue only): chain_out[r] = bf16(LN output row r) . Wc^T + chain_bias, Wc [128,128] as a
     // two-term bf16 split.  The decoder's "out-proj + LN1" and "cross-attention query projection" as ONE launch: the
     // normalised rows go to shared memory as the A operand of a second MMA instead of round-tripping through HBM.
@@ -272,6 +276,20 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
     }
 }
 
+// the KV-append fields exist in TcGemmParams only (the fused FFN shares this epilogue and has none)
+__device__ __forceinline__ bool epi_kv_append(const TcGemmParams& p) { return p.kv_append != 0; }
+__device__ __forceinline__ const int* epi_kv_step(const TcGemmParams& p) { return p.step; }
+__device__ __forceinline__ int epi_kv_heads(const TcGemmParams& p) { return p.kv_heads; }
+__device__ __forceinline__ __nv_bfloat16* epi_kv_pool(const TcGemmParams& p) { return p.kv_pool; }
+__device__ __forceinline__ const int* epi_kv_bt(const TcGemmParams& p) { return p.block_table; }
+__device__ __forceinline__ int epi_kv_pps(const TcGemmParams& p) { return p.pps; }
+template <class P> __device__ __forceinline__ bool epi_kv_append(const P&) { return false; }
+template <class P> __device__ __forceinline__ const int* epi_kv_step(const P&) { return nullptr; }
+template <class P> __device__ __forceinline__ int epi_kv_heads(const P&) { return 1; }
+template <class P> __device__ __forceinline__ __nv_bfloat16* epi_kv_pool(const P&) { return nullptr; }
+template <class P> __device__ __forceinline__ const int* epi_kv_bt(const P&) { return nullptr; }
+template <class P> __device__ __forceinline__ int epi_kv_pps(const P&) { return 0; }
+
 // out[map(r)][n0 + ...] = act(stage[r] + bias) for the warp's 32 rows; split > 0 partials are raw sums
 template <class P>
 __device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, int row0, int nrows, int n0, int split, int lane) {
@@ -300,6 +318,22 @@ __device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, i
             if (p.out_b16) *reinterpret_cast<uint2*>(p.out_b16 + o) = pack_bf16x4(v);
             o += dh;
             if (++j == S) { j = 0; o += wrap; }
+        }
+        return;
+    }
+    if (epi_kv_append(p) && col >= D) {      // K | V of position t -> cache page (4 consecutive head dims per lane: 8 bytes)
+        const int t = *epi_kv_step(p);
+        const int kv = (col - D) / D, cc = col % D, H = epi_kv_heads(p), dh = D / H;
+        const int h = cc / dh, d0 = cc % dh;
+        __nv_bfloat16* const pool = epi_kv_pool(p);
+        const int* bt = epi_kv_bt(p);
+        const int pps = epi_kv_pps(p);
+#pragma unroll 4
+        for (int i = 0; i < rows; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS);
+            const float4 v = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
+            const int64_t page = bt[(int64_t)(row0 + i) * pps + t / PAGE_TOKENS];
+            *reinterpret_cast<uint2*>(pool + page * (2 * PAGE_TOKENS * D) + ((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * dh + d0) = pack_bf16x4(v);
         }
         return;
     }

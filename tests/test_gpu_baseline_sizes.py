@@ -272,7 +272,7 @@ def test_chained_projection_equals_two_launches(monkeypatch):
     from multimodalspectraltransformer_b200 import synthetic
     M = s["M"]
     m_chain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0")
-    m_plain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_NO_GEMM_CHAIN="1", MMT_NO_FFN_PROLOGUE="1")
+    m_plain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_NO_GEMM_CHAIN="1", MMT_NO_FFN_PROLOGUE="1", MMT_NO_KV_EPILOGUE="1")
     for B, K, T in ((41, 7, 10), (300, 16, 6), (19, 128, 5)):
         data = synthetic.make_spectra(B, seed=700 + B)
         cfg = cfg_for(precision="bf16", max_len=T)

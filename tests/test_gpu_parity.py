@@ -386,6 +386,14 @@ def test_token_pack_roundtrip():
     t = torch.randint(0, 43, (128, 77), device="cuda")
     p = s["eng"].pack_tokens(t)
     assert p.dtype == torch.uint8 and torch.equal(s["eng"].unpack_tokens(p), t)
+    # sequence-major form (the scheduler's all-gather payload): (T,N) i64 -> (N,T) u8 and back, ragged tile edges
+    for T, N in ((128, 77), (1, 1), (33, 1000), (128, 16384 + 5)):
+        t = torch.randint(0, 43, (T, N), device="cuda")
+        q = s["eng"].pack_tokens_seqmajor(t)
+        assert q.dtype == torch.uint8 and tuple(q.shape) == (N, T) and torch.equal(q, t.t().to(torch.uint8))
+        assert torch.equal(s["eng"].unpack_tokens_seqmajor(q, N), t)
+        pad = torch.cat([q, torch.zeros(7, T, dtype=torch.uint8, device="cuda")])      # a gathered buffer with padded tail rows
+        assert torch.equal(s["eng"].unpack_tokens_seqmajor(pad, N), t)
 
 
 def test_errors_are_loud():
