@@ -1133,8 +1133,8 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
 // projected memory (run_batch_gen_val_MMT_v15_4.py:93-158 decodes 128 candidates per spectrum), so per (spectrum, head)
 // the scores are a real [n_cand x 8] . [8 x keys] product and the output a [n_cand x keys] . [keys x 8] one.  One CTA
 // per (head, spectrum) stages that head's K (row-major) and V (transposed) once; a warp owns 16 candidates: Q.K^T on
-// mma.sync m16n8k8, P.V on m16n8k16, online softmax in the log2 domain on the accumulator layout.  Q and P enter as
-// two-term bf16 splits (K and V are bf16 already), so the result equals the SIMT kernel's to fp32 round-off.
+// mma.sync m16n8k8, P.V on m16n8k16, online softmax in the log2 domain on the accumulator layout.  Q enters as a
+// two-term bf16 split (K and V are bf16 already): the scores equal the SIMT kernel's to fp32 round-off; P is bf16.
 __host__ __device__ inline size_t dx_smem_bytes(int key_bound) {
     const int nkp = at_keys_padded(key_bound);
     return (size_t)nkp * 8 * 2 + (size_t)8 * (nkp + 8) * 2 + (size_t)nkp * 4;
@@ -1190,6 +1190,7 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
             split_pair(a.x * qscale, a.y * qscale, qh[0], ql[0]);
             split_pair(c.x * qscale, c.y * qscale, qh[1], ql[1]);
         }
+        const uint32_t qa[4] = {qh[0], qh[1], ql[0], ql[1]};      // m16n8k16 A fragment: columns 0-7 = Q_hi, 8-15 = Q_lo
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         float m_lo = MMT_NEG_INF, m_hi = MMT_NEG_INF, l_lo = 0.f, l_hi = 0.f;
         for (int kb = 0; kb < nkp; kb += 16) {
@@ -1199,8 +1200,7 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
                 const float2 bb = *reinterpret_cast<const float2*>(bs + kb + nt * 8 + 2 * tq);
                 sc[nt][0] = bb.x; sc[nt][1] = bb.y; sc[nt][2] = bb.x; sc[nt][3] = bb.y;
                 const uint32_t kf = *reinterpret_cast<const uint32_t*>(Ks + (size_t)(kb + nt * 8 + gq) * DH + 2 * tq);
-                mma_bf16_1688(sc[nt], qh, kf);
-                mma_bf16_1688(sc[nt], ql, kf);
+                mma_bf16_16816(sc[nt], qa, kf, kf);        // [Q_hi | Q_lo] (k = 16) . [K ; K]: both terms of Q in one instruction
             }
             float bm_lo = fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1]));
             float bm_hi = fmaxf(fmaxf(sc[0][2], sc[0][3]), fmaxf(sc[1][2], sc[1][3]));
@@ -1213,19 +1213,22 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
                 l_lo *= corr_lo; l_hi *= corr_hi;
                 acc[0] *= corr_lo; acc[1] *= corr_lo; acc[2] *= corr_hi; acc[3] *= corr_hi;
             }
-            uint32_t ph[4], pl[4];
+            // P enters the P.V product as plain bf16: its rounding (2^-9 relative per weight, averaged over the keys) is far below
+            // the bf16 rounding the attention OUTPUT receives anyway (att16 is the next GEMM's bf16 operand), so a low-order term
+            // of P only cost instructions in this issue-bound loop (4 residual packs + 1 MMA of ~95 instructions per 16 keys).
+            uint32_t ph[4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 const float e0 = ex2_approx(sc[nt][0] - m_lo), e1 = ex2_approx(sc[nt][1] - m_lo);
                 const float e2 = ex2_approx(sc[nt][2] - m_hi), e3 = ex2_approx(sc[nt][3] - m_hi);
                 l_lo += e0 + e1; l_hi += e2 + e3;
-                split_pair(e0, e1, ph[nt * 2], pl[nt * 2]);
-                split_pair(e2, e3, ph[nt * 2 + 1], pl[nt * 2 + 1]);
+                const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1), p23 = __floats2bfloat162_rn(e2, e3);
+                ph[nt * 2] = *reinterpret_cast<const uint32_t*>(&p01);
+                ph[nt * 2 + 1] = *reinterpret_cast<const uint32_t*>(&p23);
             }
             const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + (size_t)gq * vstride + kb + 2 * tq);
             const uint32_t v0 = vr[0], v1 = vr[4];
             mma_bf16_16816(acc, ph, v0, v1);
-            mma_bf16_16816(acc, pl, v0, v1);
         }
         l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
         l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
