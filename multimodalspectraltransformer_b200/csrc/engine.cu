@@ -922,9 +922,13 @@ static void plan_decoder(Arena& a, const mmt_model_desc& d, int64_t Nw, int Bmw,
     }
 }
 
-__global__ void init_block_table(int* bt, int64_t n_pages) {
+// Page map of a wave: page j of sequence n is physical page j * Nw + n ("slot-major").  At position t every sequence reads its
+// pages 0 .. t / 16, so the pages a step touches form ONE contiguous region of the pool that grows with t.  With the
+// sequence-major map (n * pps + j) a step read 8 KB pages at a 64 KB stride with a t-dependent duty cycle, which the HBM
+// channel hash spread unevenly (ncu, t = 41: busiest channel 67 % active, idlest 33 %, profiles/r02_ncu_summary.md).
+__global__ void init_block_table(int* bt, int64_t Nw, int pps) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pages) bt[i] = (int)i;   // identity page map: sequence n owns pages [n*pps, (n+1)*pps)
+    if (i < Nw * pps) bt[i] = (int)((i % pps) * Nw + i / pps);
 }
 
 struct DecodeRun {
@@ -1273,7 +1277,7 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
             MMT_CUDA(cudaMemsetAsync(b.ctl, 0, (8 + 256) * sizeof(int), s));
             set_u64x2<<<1, 1, 0, s>>>(b.rng_state, a.philox_seed, a.philox_offset);
             prof_pre(e, s);
-            init_block_table<<<(unsigned)((lane[i].Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, lane[i].Nw * pps);
+            init_block_table<<<(unsigned)((lane[i].Nw * pps + 255) / 256), 256, 0, s>>>(b.block_table, lane[i].Nw, pps);
             MMT_TRY(check_launch(e, "init_block_table", s));
             MMT_TRY(decode_prepare_wave(e, a, lane[i].b0, lane[i].Bm, b, bf16, s));
         }
