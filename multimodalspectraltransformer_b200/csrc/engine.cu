@@ -1106,7 +1106,9 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             const char* ckv = b.cross_kv + (size_t)l * 2 * R * D * b.kv_esz;
             if (bf16) {   // K | V columns of the projection land in the cache pages directly; the fp32 row keeps only Q
                 TcGemmParams p = tc_params(M, 3 * D, D);
-                p.bias = w.in_b; p.out_f32 = b.qkv; p.ld_f32 = 3 * D;
+                // (with the K | V columns going to the cache, the Q columns form a dense [N][D] buffer: a 512-byte row every 512
+                // bytes instead of every 1536)
+                p.bias = w.in_b; p.out_f32 = b.qkv; p.ld_f32 = e->use_kv_epilogue ? D : 3 * D;
                 p.kv_append = e->use_kv_epilogue ? 1 : 0; p.kv_pool = reinterpret_cast<__nv_bfloat16*>(pool); p.block_table = b.block_table; p.pps = pps; p.step = step; p.kv_heads = H;
                 MMT_TRY(launch_tc(e, p, b.x16, D, e->Wb(w.in_w), TC_EPI_STORE, s, e->Wlo(w.in_w), pdl_u));
             } else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));

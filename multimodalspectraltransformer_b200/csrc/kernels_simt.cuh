@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv
     const int h = (int)(w % HG) * 4 + hq;
     constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
     const int* bt = block_table + n * pages_per_seq;
-    const float* row = qkv + n * (3 * D) + h * DH;
+    const float* row = qkv + n * (APPEND ? 3 * D : D) + h * DH;      // APPEND = false: `qkv` is the dense [N][D] query buffer
     if (APPEND) {   // append K,V of position t: lane (hq, kl) writes element kl of its head's K and V rows
         KVT* page = kv_pool + (int64_t)bt[t / PAGE_TOKENS] * PAGE_ELEMS;
         KV::st(page + ((0 * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * DH + kl, row[D + kl]);
