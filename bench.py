@@ -381,7 +381,9 @@ def main():
         kv_cross = n_valid * 2 * 128 * esz + n_valid * 4                  # shared by the 128 candidates of a spectrum
         alg_bytes = {
             # per launch = one decoder layer, one position, one wave: DESIGN.md section 5
-            "decode_self_attention": kv_self + Nw * 2 * 128 * esz + Nw * 3 * 128 * 4 + Nw * 128 * 2,   # cache read + append + qkv in + att out
+            # cache pages read + the dense fp32 query rows in + bf16 attention rows out (bf16 mode: K | V of the new position are
+            # appended by the QKV projection's epilogue, not here; fp32 check mode reads the whole qkv row and appends)
+            "decode_self_attention": kv_self + (Nw * 128 * 4 + Nw * 128 * 2 if precision != "fp32" else Nw * 2 * 128 * esz + Nw * 3 * 128 * 4 + Nw * 128 * 4),
             "decode_layer": kv_self + Nw * 2 * 128 * esz + kv_cross + Nw * 128 * (4 + 4 + 2),
             "decode_cross_attention": kv_cross + Nw * 128 * 4 + Nw * 128 * 2,
             "decode_attn": kv_cross + kv_self + Nw * 128 * (4 + 4 + 2),
