@@ -1216,10 +1216,13 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
     const int64_t N_total = (int64_t)a.Bm * a.n_cand;
     // waves: bound the self-attention KV pool (fp32: max_len*6*2*128*4 B per sequence)
     // Sequences decoded together.  A wave's KV pool is 393 KB per sequence in bf16 (6 layers x 8 pages x 8 KB; twice that in
-    // fp32), so the default is 65,536 sequences = 25.8 GB in bf16 and 32,768 in fp32.  Larger waves amortise the ~31 kernel
+    // fp32), so the default is ~75,000 sequences = 29.8 GB in bf16 and 32,768 in fp32.  Larger waves amortise the ~31 kernel
     // boundaries of an un-fused step: measured 1376 -> 1214 us per position and 16,384 sequences going from waves of
     // 16,384 to 65,536 (profiles/r02_config3.md); 131,072 in one wave is within 1 % of that for twice the pool.
-    const int64_t max_wave_seqs = e->max_wave_seqs > 0 ? e->max_wave_seqs : (a.precision == MMT_PREC_BF16 ? 65536 : 32768);
+    // (bf16: four full rounds of 128-row tiles over the SMs -- 75,776 rows on 148 SMs, 29.8 GB of pool -- so that the
+    // tile-per-CTA kernels of a full wave do not end in a partly filled round: 1024 x 128 sequences run as 592 + 432 tiles =
+    // 4 + 3 rounds instead of 2 x 3.46 -> 2 x 4.)
+    const int64_t max_wave_seqs = e->max_wave_seqs > 0 ? e->max_wave_seqs : (a.precision == MMT_PREC_BF16 ? (int64_t)e->sm_count * 4 * 128 : 32768);
     int Bm_wave = (int)std::max<int64_t>(1, std::min<int64_t>(a.Bm, max_wave_seqs / a.n_cand));
     const int n_waves = (a.Bm + Bm_wave - 1) / Bm_wave;
     if (a.precision != MMT_PREC_FP32 && a.precision != MMT_PREC_BF16) MMT_FAIL("decode: bad precision");
