@@ -1135,8 +1135,9 @@ __global__ void __launch_bounds__(256) decode_cross_attention(const float* q_in,
 // per (head, spectrum) stages that head's K (row-major) and V (transposed) once; a warp owns 16 candidates: Q.K^T on
 // mma.sync m16n8k8, P.V on m16n8k16, online softmax in the log2 domain on the accumulator layout.  Q enters as a
 // two-term bf16 split (K and V are bf16 already): the scores equal the SIMT kernel's to fp32 round-off; P is bf16.
+__host__ __device__ inline int dx_keys_padded(int nk) { return (nk + 31) / 32 * 32; }      // 32 keys per softmax round
 __host__ __device__ inline size_t dx_smem_bytes(int key_bound) {
-    const int nkp = at_keys_padded(key_bound);
+    const int nkp = dx_keys_padded(key_bound);
     return (size_t)nkp * 8 * 2 + (size_t)8 * (nkp + 8) * 2 + (size_t)nkp * 4;
 }
 __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_in, const __nv_bfloat16* kv, int64_t rows_total,
@@ -1150,7 +1151,7 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
     const int64_t b = blockIdx.y;
     const int cnt = nk[b];
     const int64_t r0 = row_start[b];
-    const int nkp_max = at_keys_padded((int)rows_total), nkp = at_keys_padded(cnt);
+    const int nkp_max = dx_keys_padded((int)rows_total), nkp = dx_keys_padded(cnt);
     const int vstride = nkp_max + 8;
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(dx_smem);           // [nkp][8]
     __nv_bfloat16* Vt = Ks + (size_t)nkp_max * DH;                           // [8][vstride]
@@ -1193,17 +1194,19 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
         const uint32_t qa[4] = {qh[0], qh[1], ql[0], ql[1]};      // m16n8k16 A fragment: columns 0-7 = Q_hi, 8-15 = Q_lo
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         float m_lo = MMT_NEG_INF, m_hi = MMT_NEG_INF, l_lo = 0.f, l_hi = 0.f;
-        for (int kb = 0; kb < nkp; kb += 16) {
-            float sc[2][4];
+        // 32 keys per round: four score tiles first, ONE running-max update for all of them, then the exponentials and two P.V
+        // MMAs -- half the max / shuffle / rescale bookkeeping per key of a 16-key round and twice the independent work in flight
+        for (int kb = 0; kb < nkp; kb += 32) {
+            float sc[4][4];
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
+            for (int nt = 0; nt < 4; ++nt) {
                 const float2 bb = *reinterpret_cast<const float2*>(bs + kb + nt * 8 + 2 * tq);
                 sc[nt][0] = bb.x; sc[nt][1] = bb.y; sc[nt][2] = bb.x; sc[nt][3] = bb.y;
                 const uint32_t kf = *reinterpret_cast<const uint32_t*>(Ks + (size_t)(kb + nt * 8 + gq) * DH + 2 * tq);
                 mma_bf16_16816(sc[nt], qa, kf, kf);        // [Q_hi | Q_lo] (k = 16) . [K ; K]: both terms of Q in one instruction
             }
-            float bm_lo = fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1]));
-            float bm_hi = fmaxf(fmaxf(sc[0][2], sc[0][3]), fmaxf(sc[1][2], sc[1][3]));
+            float bm_lo = fmaxf(fmaxf(fmaxf(sc[0][0], sc[0][1]), fmaxf(sc[1][0], sc[1][1])), fmaxf(fmaxf(sc[2][0], sc[2][1]), fmaxf(sc[3][0], sc[3][1])));
+            float bm_hi = fmaxf(fmaxf(fmaxf(sc[0][2], sc[0][3]), fmaxf(sc[1][2], sc[1][3])), fmaxf(fmaxf(sc[2][2], sc[2][3]), fmaxf(sc[3][2], sc[3][3])));
             bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 1)); bm_lo = fmaxf(bm_lo, __shfl_xor_sync(0xffffffffu, bm_lo, 2));
             bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 1)); bm_hi = fmaxf(bm_hi, __shfl_xor_sync(0xffffffffu, bm_hi, 2));
             const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
@@ -1214,21 +1217,23 @@ __global__ void __launch_bounds__(256) decode_cross_attention_tc(const float* q_
                 acc[0] *= corr_lo; acc[1] *= corr_lo; acc[2] *= corr_hi; acc[3] *= corr_hi;
             }
             // P enters the P.V product as plain bf16: its rounding (2^-9 relative per weight, averaged over the keys) is far below
-            // the bf16 rounding the attention OUTPUT receives anyway (att16 is the next GEMM's bf16 operand), so a low-order term
-            // of P only cost instructions in this issue-bound loop (4 residual packs + 1 MMA of ~95 instructions per 16 keys).
-            uint32_t ph[4];
+            // the bf16 rounding the attention OUTPUT receives anyway (att16 is the next GEMM's bf16 operand)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const float e0 = ex2_approx(sc[nt][0] - m_lo), e1 = ex2_approx(sc[nt][1] - m_lo);
-                const float e2 = ex2_approx(sc[nt][2] - m_hi), e3 = ex2_approx(sc[nt][3] - m_hi);
-                l_lo += e0 + e1; l_hi += e2 + e3;
-                const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1), p23 = __floats2bfloat162_rn(e2, e3);
-                ph[nt * 2] = *reinterpret_cast<const uint32_t*>(&p01);
-                ph[nt * 2 + 1] = *reinterpret_cast<const uint32_t*>(&p23);
+            for (int half = 0; half < 2; ++half) {
+                uint32_t ph[4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float* c = sc[half * 2 + nt];
+                    const float e0 = ex2_approx(c[0] - m_lo), e1 = ex2_approx(c[1] - m_lo);
+                    const float e2 = ex2_approx(c[2] - m_hi), e3 = ex2_approx(c[3] - m_hi);
+                    l_lo += e0 + e1; l_hi += e2 + e3;
+                    const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1), p23 = __floats2bfloat162_rn(e2, e3);
+                    ph[nt * 2] = *reinterpret_cast<const uint32_t*>(&p01);
+                    ph[nt * 2 + 1] = *reinterpret_cast<const uint32_t*>(&p23);
+                }
+                const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + (size_t)gq * vstride + kb + half * 16 + 2 * tq);
+                mma_bf16_16816(acc, ph, vr[0], vr[4]);
             }
-            const uint32_t* vr = reinterpret_cast<const uint32_t*>(Vt + (size_t)gq * vstride + kb + 2 * tq);
-            const uint32_t v0 = vr[0], v1 = vr[4];
-            mma_bf16_16816(acc, ph, v0, v1);
         }
         l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
         l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
