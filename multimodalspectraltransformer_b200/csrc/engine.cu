@@ -5,6 +5,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_decode.cuh"
 #include "kernels_ffn.cuh"
+#include "kernels_attn5.cuh"
 #include "kernels_compact.cuh"
 #include "kernels_beam.cuh"
 
@@ -165,6 +166,7 @@ static int tc_init(mmt_engine* e) {
     const int max_smem = TC_MAX_STAGES * TC_STAGE_BYTES_WSPLIT + 1024;
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     MMT_CUDA(cudaFuncSetAttribute(gemm_bf16_tc<TC_EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    MMT_CUDA(cudaFuncSetAttribute(attn_encoder_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM_BYTES));
     MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<1>()));
     MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<1>()));
     MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<0>()));
@@ -405,6 +407,16 @@ static int launch_encoder_attention(mmt_engine* e, EncGroupRun* gr, int ng, int 
     if (dh >= 32) key_bound = std::min(key_bound, 768);
     for (int i = 0; i < ng; ++i) p.g[i].smax = key_bound;
     dim3 grid(heads, Bc, ng);
+    if (dh == A5_DH && e->use_tc_attention && e->use_tc5_attention && (bf16_out || e->tc_attention_fp32)) {
+        // opt-in (MMT_TC5_ATTENTION=1): tcgen05 attention, scores and output accumulators in TMEM (kernels_attn5.cuh).  Parity-tested, but
+        // slower than the mma.sync kernel below at these shapes (32-wide heads, 64-key chunks: 102 vs 73 us per layer at realistic peak
+        // counts, 659 vs 628 us at 582 keys, profiles/r02_attn_tc5.md): P has to round-trip through shared memory and two proxy fences
+        // per chunk, and the phases of a chunk are serial within a CTA.
+        MMT_TRY(tc_init(e));
+        prof_pre(e, s);
+        attn_encoder_tc5<<<grid, A5_THREADS, A5_SMEM_BYTES, s>>>(p);
+        return check_launch(e, "attn_encoder_tc5", s);
+    }
     if (dh == AT_DH && e->use_tc_attention && (bf16_out || e->tc_attention_fp32)) {   // encoder_cross in the tensor-core mode: mma.sync flash attention, two-term operand splits
         const size_t smem_tc = at_smem_bytes(key_bound);
         const int warps = std::min(12, std::max(1, (row_bound + 15) / 16));   // one 16-row tile per warp for realistic peak counts; <= 85 registers: two CTAs per SM
@@ -1599,6 +1611,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (const char* v = getenv("MMT_DECODE_LANES")) e->decode_lanes = std::max(1, atoi(v));
     if (getenv("MMT_DENSE_ENCODER")) e->use_compact = false;
     if (getenv("MMT_NO_TC_ATTENTION")) e->use_tc_attention = false;
+    if (getenv("MMT_TC5_ATTENTION")) e->use_tc5_attention = true;
     if (const char* v = getenv("MMT_FFN_SPLITS")) { int k = atoi(v); if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) e->ffn_splits_override = k; }
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);

@@ -130,6 +130,7 @@ struct mmt_engine {
     uint64_t graph_cache_clock = 0;
     bool use_graph_cache = true;           // MMT_NO_GRAPH_CACHE=1: capture + instantiate on every call, write the caller's tensors directly
     bool use_tc_attention = true;      // encoder_cross attention on mma.sync in the bf16 mode (MMT_NO_TC_ATTENTION=1: fp32 SIMT kernel)
+    bool use_tc5_attention = false;    // encoder_cross attention on tcgen05 / TMEM instead of mma.sync (opt-in: MMT_TC5_ATTENTION=1; correct but slower at these shapes)
     bool tc_attention_fp32 = false;    // test hook (MMT_TC_ATTENTION_FP32=1): the same kernel in the fp32 check mode, where nothing downstream amplifies its round-off
     int ffn_splits_override = 0;       // experiment knob (MMT_FFN_SPLITS): F-splits of the fused decode step's FFN
     bool use_enc_streams = true;       // ragged encoder: the five modality stacks as concurrent chains (MMT_NO_ENC_STREAMS=1 disables)

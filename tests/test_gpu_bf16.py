@@ -144,9 +144,10 @@ def test_ffn_fused_tcgen05(M, F, splits, terms):
     assert float((out.double() - ref).abs().mean()) < 2e-4
 
 
+@pytest.mark.parametrize("tc5", [False, True])
 @pytest.mark.parametrize("name,dense", [("full_b5", False), ("full_b5", True), ("maxpeaks_b2", False), ("mode_hsqc_b2", True),
-                                        ("blank_hsqc_only_b3", True)])
-def test_cross_encoder_tensor_core_attention_equals_simt(name, dense, monkeypatch):
+                                        ("blank_hsqc_only_b3", True), ("mode_ms_max_b2", True)])
+def test_cross_encoder_tensor_core_attention_equals_simt(name, dense, tc5, monkeypatch):
     """attn_encoder_tc / attn_encoder_tc8 (mma.sync, two-term operand splits, exp2; 32-wide heads of encoder_cross and
     8-wide heads of the modality encoders) reproduce the fp32 SIMT attention kernel to fp32 round-off.  Checked in the fp32 mode (test hook MMT_TC_ATTENTION_FP32), where no bf16 rounding downstream
     amplifies last-bit differences: ragged and dense key lists, bool and float key masks.  In the bf16 mode the two
@@ -159,8 +160,12 @@ def test_cross_encoder_tensor_core_attention_equals_simt(name, dense, monkeypatc
     if dense:
         monkeypatch.setenv("MMT_DENSE_ENCODER", "1")
     monkeypatch.setenv("MMT_TC_ATTENTION_FP32", "1")
+    if tc5:       # the tcgen05 / TMEM kernel for the 32-wide heads (kernels_attn5.cuh) instead of the mma.sync one
+        monkeypatch.setenv("MMT_TC5_ATTENTION", "1")
     eng_tc = Engine(s["model"].state_dict(), cfg, dev)
     monkeypatch.delenv("MMT_TC_ATTENTION_FP32")
+    if tc5:
+        monkeypatch.delenv("MMT_TC5_ATTENTION")
     monkeypatch.setenv("MMT_NO_TC_ATTENTION", "1")
     eng_simt = Engine(s["model"].state_dict(), cfg, dev)
     a = eng_tc.encode(data, case["mode"], "fp32", False)
