@@ -171,6 +171,7 @@ static int tc_init(mmt_engine* e) {
     MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<1>()));
     MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<0>()));
     MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<0>()));
+    MMT_CUDA(cudaFuncSetAttribute(ffn_fused_tc<TC_EPI_LN, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ff_smem_bytes<0, 1>()));
     e->tc_ready = true;
     return 0;
 }
@@ -272,7 +273,9 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
         if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), s, pdl, p);
         else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), s, pdl, p);
     } else {   // hi term only: the deeper pipeline variant
-        if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
+        if (epi == TC_EPI_LN && p.splits == 1 && p.F % (2 * FF_CH) == 0 && e->use_ffn_wide)      // 128-column chunks
+            launch_kernel(ffn_fused_tc<TC_EPI_LN, 0, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<0, 1>(), s, pdl, p);
+        else if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
         else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
     }
     return check_launch(e, "ffn_fused_tc", s, 4.0 * p.M * D * p.F);
@@ -1618,6 +1621,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
     if (const char* v = getenv("MMT_PDL_ROWS")) e->pdl_rows = atoi(v);
     if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
+    if (getenv("MMT_NO_FFN_WIDE")) e->use_ffn_wide = false;
     if (getenv("MMT_NO_KV_EPILOGUE")) e->use_kv_epilogue = false;
     if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;

@@ -53,28 +53,46 @@ constexpr int FF_W1_HALF = FF_CH * 128;                    // 8 KB: 64 rows x 12
 constexpr int FF_W1_STAGE = 2 * TC_SLAB_BYTES;             // W1 chunk: 2 K slabs of [64 hi rows ; 64 lo rows] x 64 k = 32 KB
 constexpr int FF_W2_STAGE = 2 * TC_SLAB_BYTES;             // W2 chunk: [128 hi rows ; 128 lo rows] x 64 k = 32 KB
 constexpr int FF_MAX_F = 2048;
-// per-variant pipeline geometry
-template <int WS> struct FfCfg;
-template <> struct FfCfg<1> {          // two-term weights
-    static constexpr int NB = 2, NS = 2;                                   // acc1 / H buffers, weight ring stages
+// per-variant pipeline geometry.  WS: two-term weights (1) or the hi term alone (0).  WIDE: chunks of 128 hidden columns instead of
+// 64 (hi term + LayerNorm epilogue only): the chunk loop is paced by the issuing threads' control instructions per chunk (two
+// waits, a fence, a commit: ~0.7 K cycles), so twice the columns per chunk halves that cost per column -- at 128 columns a chunk
+// carries ~1.0 K cycles of tensor work and the loop becomes tensor-paced.  Needs the TMEM columns and shared memory the lo term
+// vacates, and whole 128-column chunks per CTA (no split-F).
+template <int WS, int WIDE> struct FfCfg;
+template <> struct FfCfg<1, 0> {       // two-term weights
+    static constexpr int CH = FF_CH, NB = 2, NS = 2;                       // chunk width, acc1 / H buffers, weight ring stages
     static constexpr int W1_STAGE = FF_W1_STAGE, W2_STAGE = FF_W2_STAGE;   // 32 KB each (hi | lo)
     static constexpr int W1_SLAB = TC_SLAB_BYTES;                          // K slab stride inside a W1 stage
+    static constexpr int W2_KSLAB = 2 * TC_SLAB_BYTES;                     // 64-k slab stride inside a W2 stage (one slab: hi rows | lo rows)
+    static constexpr int H_BYTES = FF_H_BYTES;
     static constexpr int ACC1_STRIDE = 2 * FF_CH, ACC2_COL = 256;          // TMEM columns
 };
-template <> struct FfCfg<0> {          // hi term only: deeper pipeline in the freed TMEM / shared memory
-    static constexpr int NB = 3, NS = 4;
+template <> struct FfCfg<0, 0> {       // hi term only, 64-column chunks (split-F partial path): deeper pipeline in the freed TMEM / shared memory
+    static constexpr int CH = FF_CH, NB = 3, NS = 4;
     static constexpr int W1_STAGE = FF_W1_STAGE / 2, W2_STAGE = FF_W2_STAGE / 2;   // 16 KB each
     static constexpr int W1_SLAB = FF_W1_HALF;                             // 8 KB: [64 rows x 64 k]
+    static constexpr int W2_KSLAB = TC_SLAB_BYTES;
+    static constexpr int H_BYTES = FF_H_BYTES;
     static constexpr int ACC1_STRIDE = FF_CH, ACC2_COL = 256;
 };
-// dynamic smem: X (32 KB) | H (NB x 16 KB) | W1 ring | W2 ring + alignment slack
-template <int WS> constexpr int ff_smem_bytes() {
-    return FF_X_BYTES + FfCfg<WS>::NB * FF_H_BYTES + FfCfg<WS>::NS * (FfCfg<WS>::W1_STAGE + FfCfg<WS>::W2_STAGE) + 1024;
+template <> struct FfCfg<0, 1> {       // hi term only, 128-column chunks (LayerNorm epilogue, whole F per CTA)
+    static constexpr int CH = 2 * FF_CH, NB = 2, NS = 2;
+    static constexpr int W1_STAGE = 2 * TC_SLAB_BYTES, W2_STAGE = 2 * TC_SLAB_BYTES;   // [128 rows x 128 k] each: two 64-k slabs of 16 KB
+    static constexpr int W1_SLAB = TC_SLAB_BYTES;
+    static constexpr int W2_KSLAB = TC_SLAB_BYTES;
+    static constexpr int H_BYTES = 2 * FF_H_BYTES;                         // two 64-k slabs
+    static constexpr int ACC1_STRIDE = 2 * FF_CH, ACC2_COL = 256;
+};
+// dynamic smem: X (32 KB) | H (NB buffers) | W1 ring | W2 ring + alignment slack
+template <int WS, int WIDE = 0> constexpr int ff_smem_bytes() {
+    typedef FfCfg<WS, WIDE> C;
+    return FF_X_BYTES + C::NB * C::H_BYTES + C::NS * (C::W1_STAGE + C::W2_STAGE) + 1024;
 }
 constexpr int FF_SMEM_BYTES = ff_smem_bytes<1>();
-static_assert(FfCfg<1>::NS * (FfCfg<1>::W1_STAGE + FfCfg<1>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
-static_assert(FfCfg<0>::NS * (FfCfg<0>::W1_STAGE + FfCfg<0>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
-static_assert(ff_smem_bytes<0>() <= 227 * 1024 && ff_smem_bytes<1>() <= 227 * 1024, "shared memory budget");
+static_assert(FfCfg<1, 0>::NS * (FfCfg<1, 0>::W1_STAGE + FfCfg<1, 0>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
+static_assert(FfCfg<0, 0>::NS * (FfCfg<0, 0>::W1_STAGE + FfCfg<0, 0>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
+static_assert(FfCfg<0, 1>::NS * (FfCfg<0, 1>::W1_STAGE + FfCfg<0, 1>::W2_STAGE) >= TC_STAGING_BYTES, "final staging tile aliases the weight rings");
+static_assert(ff_smem_bytes<0>() <= 227 * 1024 && ff_smem_bytes<1>() <= 227 * 1024 && ff_smem_bytes<0, 1>() <= 227 * 1024, "shared memory budget");
 constexpr uint32_t FF_TMEM_COLS = 512;                     // WS=1: acc1 2 x (64 hi + 64 lo) | acc2 128 hi + 128 lo;  WS=0: acc1 3 x 64 | acc2 128 at column 256
 
 struct FfnParams {
@@ -130,10 +148,11 @@ struct LnView {
     const int* out_rows; int S_in; int64_t stride_b, stride_s, off;
 };
 
-template <int EPI, int WS>
+template <int EPI, int WS, int WIDE = 0>
 __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
-    typedef FfCfg<WS> C;
-    constexpr int NB = C::NB, NS = C::NS;
+    static_assert(!WIDE || (WS == 0 && EPI == TC_EPI_LN), "128-column chunks: hi term + LayerNorm epilogue only");
+    typedef FfCfg<WS, WIDE> C;
+    constexpr int NB = C::NB, NS = C::NS, CH = C::CH;
     extern __shared__ uint8_t smem_raw[];
     // "GEMM1 of chunk i retired" frees a W1 stage AND publishes acc1; "GEMM2 of chunk j retired" frees a W2 stage AND an H
     // buffer: one tcgen05.commit each (a commit costs the issuing thread a few hundred cycles), on barrier rings of
@@ -148,11 +167,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space
     uint8_t* sX = smem;
     uint8_t* sH = sX + FF_X_BYTES;
-    uint8_t* sW = sH + NB * FF_H_BYTES;   // W1 ring; the two rings together also hold the final staging tile
+    uint8_t* sW = sH + NB * C::H_BYTES;   // W1 ring; the two rings together also hold the final staging tile
     uint8_t* sW2 = sW + NS * C::W1_STAGE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int split = blockIdx.x, m0 = blockIdx.y * TC_BM;
-    const int n = (p.F / FF_CH) / p.splits;      // chunks of this CTA (host guarantees divisibility, n >= 1)
+    const int n = (p.F / CH) / p.splits;         // chunks of this CTA (host guarantees divisibility, n >= 1)
     const int c0 = split * n;
     const int cta = blockIdx.y * gridDim.x + blockIdx.x;
 #define FF_STAMP(i) do { if (p.dbg) p.dbg[cta * 16 + (i)] = clock64(); } while (0)
@@ -176,7 +195,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
     const uint32_t tmem_base = tmem_slot;
     const uint32_t tmem_acc2 = tmem_base + C::ACC2_COL;   // acc1[b] at columns [ACC1_STRIDE b, +ACC1_STRIDE): hi 64 (| lo 64)
     // N of the MMAs: both terms stacked, or the hi half alone
-    constexpr int n1 = WS ? 2 * FF_CH : FF_CH, n2 = WS ? 2 * TC_BN : TC_BN;
+    constexpr int n1 = WS ? 2 * CH : CH, n2 = WS ? 2 * TC_BN : TC_BN;
     if (threadIdx.x == 64) FF_STAMP(1);
 
     if (warp == 0) {
@@ -212,8 +231,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                     if (!((p.knock & 1) && i >= NS)) {
                         mbar_arrive_expect_tx(&w1_full[s], C::W1_STAGE);
                         uint8_t* w = sW + (size_t)s * C::W1_STAGE;          // K slab ks at ks * W1_SLAB: rows 0-63 hi (, rows 64-127 lo)
-                        tma_load_2d(w, &p.tmW1, &w1_full[s], 0, c * FF_CH);
-                        tma_load_2d(w + C::W1_SLAB, &p.tmW1, &w1_full[s], TC_BK, c * FF_CH);
+#pragma unroll
+                        for (int rh = 0; rh < CH / FF_CH; ++rh) {           // the W1 map's box is 64 rows: a 128-column chunk takes two per K slab
+                            tma_load_2d(w + rh * FF_W1_HALF, &p.tmW1, &w1_full[s], 0, c * CH + rh * FF_CH);
+                            tma_load_2d(w + C::W1_SLAB + rh * FF_W1_HALF, &p.tmW1, &w1_full[s], TC_BK, c * CH + rh * FF_CH);
+                        }
                         if (WS) {
                             tma_load_2d(w + FF_W1_HALF, &p.tmW1lo, &w1_full[s], 0, c * FF_CH);
                             tma_load_2d(w + C::W1_SLAB + FF_W1_HALF, &p.tmW1lo, &w1_full[s], TC_BK, c * FF_CH);
@@ -226,7 +248,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                     if (!((p.knock & 1) && i >= NS)) {
                         mbar_arrive_expect_tx(&w2_full[s], C::W2_STAGE);
                         uint8_t* w = sW2 + (size_t)s * C::W2_STAGE;         // rows 0-127 hi (, rows 128-255 lo)
-                        tma_load_2d(w, &p.tmW2, &w2_full[s], c * FF_CH, 0);
+#pragma unroll
+                        for (int ks = 0; ks < CH / FF_CH; ++ks) tma_load_2d(w + ks * C::W2_KSLAB, &p.tmW2, &w2_full[s], c * CH + ks * FF_CH, 0);
                         if (WS) tma_load_2d(w + TC_SLAB_BYTES, &p.tmW2lo, &w2_full[s], c * FF_CH, 0);
                     } else mbar_arrive(&w2_full[s]);
                 }
@@ -283,11 +306,13 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                 mbar_wait(&w2_full[sw], ((uint32_t)(j / NS)) & 1u);
                 mbar_wait(&h_full[b], ((uint32_t)(j / NB)) & 1u);
                 tc_fence_after();
-                const uint64_t adesc = umma_desc_sw128(smem_u32(sH + (size_t)b * FF_H_BYTES));
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(sW2 + (size_t)sw * C::W2_STAGE));
+                const uint32_t h_addr = smem_u32(sH + (size_t)b * C::H_BYTES), w2_addr = smem_u32(sW2 + (size_t)sw * C::W2_STAGE);
 #pragma unroll
-                for (int k = 0; k < FF_CH / 16; ++k)
-                    if (!(p.knock & 4) || j == 0) umma_bf16(tmem_acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < CH / 16; ++k) {
+                    const uint64_t adesc = umma_desc_sw128(h_addr + (k >> 2) * TC_SLAB_BYTES) + (uint64_t)(2 * (k & 3));
+                    const uint64_t bdesc = umma_desc_sw128(w2_addr + (k >> 2) * C::W2_KSLAB) + (uint64_t)(2 * (k & 3));
+                    if (!(p.knock & 4) || j == 0) umma_bf16(tmem_acc2, adesc, bdesc, idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&g2_done[j % R]);  // W2 stage and H buffer of chunk j reusable
             }
             umma_commit(&acc2_full);
@@ -312,40 +337,58 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         }
         for (int i = 0; i < n; ++i) {
             const int b = i % NB;
+            // this warp converts columns [hf * CH / 2, + CH / 2) of its 32 rows, 32 columns at a time
+            constexpr int CPW = CH / 2;
             // bias slice of this chunk (a decode-loop constant): in registers before the accumulator is ready
-            float4 bb[8];
-            const float4* bsrc = reinterpret_cast<const float4*>(p.b1 + (size_t)(c0 + i) * FF_CH + hf * 32);
+            float4 bias[CPW / 32][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bb[j] = __ldg(bsrc + j);
+            for (int cc = 0; cc < CPW / 32; ++cc) {
+                const float4* bsrc = reinterpret_cast<const float4*>(p.b1 + (size_t)(c0 + i) * CH + hf * CPW + cc * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bias[cc][j] = __ldg(bsrc + j);
+            }
             mbar_wait(&g1_done[i % R], ((uint32_t)(i / R)) & 1u);
             tc_fence_after();
             if (threadIdx.x == 64 && i == 0) FF_STAMP(2);
-            uint32_t pk[16];
+            uint32_t pk[CPW / 2];
             if ((p.knock & 2) && i > 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = 0x3c003c00u;
+                for (int j = 0; j < CPW / 2; ++j) pk[j] = 0x3c003c00u;
             } else {
-                uint32_t r[32], rl[32];
-                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * C::ACC1_STRIDE + hf * 32);
-                tmem_ld_32x32(t0, r);
-                if (WS) tmem_ld_32x32(t0 + FF_CH, rl);
+                // every TMEM load of the warp's columns is issued before the one wait (a load -> wait -> convert sequence per 32
+                // columns put the TMEM latency on the chunk's critical path once per 32 columns)
+                uint32_t r[CPW / 32][32], rl[WS ? CPW / 32 : 1][32];
+#pragma unroll
+                for (int cc = 0; cc < CPW / 32; ++cc) {
+                    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * C::ACC1_STRIDE + hf * CPW + cc * 32);
+                    tmem_ld_32x32(t0, r[cc]);
+                    if (WS) tmem_ld_32x32(t0 + FF_CH, rl[cc]);
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]), v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
-                    if (WS) { v0 += __uint_as_float(rl[4 * j]); v1 += __uint_as_float(rl[4 * j + 1]); v2 += __uint_as_float(rl[4 * j + 2]); v3 += __uint_as_float(rl[4 * j + 3]); }
-                    v0 = fmaxf(v0 + bb[j].x, 0.f); v1 = fmaxf(v1 + bb[j].y, 0.f); v2 = fmaxf(v2 + bb[j].z, 0.f); v3 = fmaxf(v3 + bb[j].w, 0.f);
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
-                    pk[2 * j] = *reinterpret_cast<uint32_t*>(&lo);
-                    pk[2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+                for (int cc = 0; cc < CPW / 32; ++cc) {
+                    const float4* bb = bias[cc];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v0 = __uint_as_float(r[cc][4 * j]), v1 = __uint_as_float(r[cc][4 * j + 1]), v2 = __uint_as_float(r[cc][4 * j + 2]), v3 = __uint_as_float(r[cc][4 * j + 3]);
+                        if (WS) { v0 += __uint_as_float(rl[cc][4 * j]); v1 += __uint_as_float(rl[cc][4 * j + 1]); v2 += __uint_as_float(rl[cc][4 * j + 2]); v3 += __uint_as_float(rl[cc][4 * j + 3]); }
+                        v0 = fmaxf(v0 + bb[j].x, 0.f); v1 = fmaxf(v1 + bb[j].y, 0.f); v2 = fmaxf(v2 + bb[j].z, 0.f); v3 = fmaxf(v3 + bb[j].w, 0.f);
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+                        pk[cc * 16 + 2 * j] = *reinterpret_cast<uint32_t*>(&lo);
+                        pk[cc * 16 + 2 * j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+                    }
                 }
             }
             if (i >= NB) mbar_wait(&g2_done[(i - NB) % R], ((uint32_t)((i - NB) / R)) & 1u);      // GEMM2 of the buffer's previous chunk retired
-            uint8_t* hrow = sH + (size_t)b * FF_H_BYTES + (size_t)row * 128;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {    // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
-                const int cj = hf * 4 + c4;
-                *reinterpret_cast<uint4*>(hrow + ((cj ^ (row & 7)) << 4)) = make_uint4(pk[4 * c4], pk[4 * c4 + 1], pk[4 * c4 + 2], pk[4 * c4 + 3]);
+            for (int cc = 0; cc < CPW / 32; ++cc) {
+                const int col0 = hf * CPW + cc * 32;              // column of the chunk -> 64-k slab col0 / 64, 16-byte chunk (col0 % 64) / 8 + c4
+                uint8_t* hrow = sH + (size_t)b * C::H_BYTES + (size_t)(col0 >> 6) * TC_SLAB_BYTES + (size_t)row * 128;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {    // 16-byte chunk cj of the row lands at chunk (cj ^ (row & 7)): SWIZZLE_128B
+                    const int cj = ((col0 & 63) >> 3) + c4;
+                    *reinterpret_cast<uint4*>(hrow + ((cj ^ (row & 7)) << 4)) = make_uint4(pk[cc * 16 + 4 * c4], pk[cc * 16 + 4 * c4 + 1], pk[cc * 16 + 4 * c4 + 2], pk[cc * 16 + 4 * c4 + 3]);
+                }
             }
             if (!(p.knock & 8)) fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             if (!(p.knock & 16)) tc_fence_before();
