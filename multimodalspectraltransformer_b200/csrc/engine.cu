@@ -1034,19 +1034,24 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         p.splits = splits; p.part_stride = Nw * D;
         return launch_gemm(e, p, 1, M, s);
     };
+    // The attention projections of LARGE waves run on the hi term of the bf16 weight split alone, like the small-wave kernel's
+    // (decode_attn keeps only the hi terms in shared memory): one weight slab per stage -> 68 KB instead of 100 KB of shared
+    // memory per CTA (three resident tiles per SM instead of two), half the weight TMA bytes and MMAs.
+    // MMT_DEC_PROJ_TWO_TERM=1 restores both terms.
+    auto plo = [&](const float* w) -> const __nv_bfloat16* { return (e->dec_proj_single && M > e->dec_proj_single_rows) ? nullptr : e->Wlo(w); };
     // tensor-core variants: plain projection (fp32 or bf16 out) and projection + residual + LN in place on x / x16
     auto tc = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, float* C32, __nv_bfloat16* C16, int N, int K, int act, int splits) -> int {
         TcGemmParams p = tc_params(M, N, K);
         p.bias = bias; p.act = act; p.out_f32 = C32; p.ld_f32 = N; p.out_b16 = C16; p.ld_b16 = N;
         p.splits = splits; p.part_stride = Nw * D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s, e->Wlo(W), pdl_u);
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_STORE, s, plo(W), pdl_u);
     };
     auto tc_ln = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, int K, const float* gamma, const float* beta,
                      const TcChain* chain = nullptr) -> int {
         TcGemmParams p = tc_params(M, D, K);
         p.bias = bias; p.res = b.x; p.gamma = gamma; p.beta = beta;
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, e->Wlo(W), pdl_u, chain);
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, chain ? e->Wlo(W) : plo(W), pdl_u, chain);
     };
     // The decoder FFN runs on the hi term of the bf16 weight split alone: measured on the 12 golden cases the lo term changes
     // the worst logit error from 5.75e-3 to 5.76e-3 of the row scale (profiles/r02_bf16_error.md) for twice the tensor work.
@@ -1124,12 +1129,14 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 // (with the K | V columns going to the cache, the Q columns form a dense [N][D] buffer: a 512-byte row every 512
                 // bytes instead of every 1536)
                 p.bias = w.in_b; p.out_f32 = b.qkv; p.ld_f32 = e->use_kv_epilogue ? D : 3 * D;
-                p.kv_append = e->use_kv_epilogue ? 1 : 0; p.kv_pool = reinterpret_cast<__nv_bfloat16*>(pool); p.block_table = b.block_table; p.pps = pps; p.step = step; p.kv_heads = H;
-                MMT_TRY(launch_tc(e, p, b.x16, D, e->Wb(w.in_w), TC_EPI_STORE, s, e->Wlo(w.in_w), pdl_u));
+                p.kv_append = e->use_kv_epilogue ? (e->kv_tok_major && H % 8 == 0 ? 2 : 1) : 0; p.kv_pool = reinterpret_cast<__nv_bfloat16*>(pool); p.block_table = b.block_table; p.pps = pps; p.step = step; p.kv_heads = H;
+                MMT_TRY(launch_tc(e, p, b.x16, D, e->Wb(w.in_w), TC_EPI_STORE, s, plo(w.in_w), pdl_u));
             } else MMT_TRY(gemm(b.x, D, w.in_w, w.in_b, b.qkv, 3 * D, D, 0, 1));
             prof_pre(e, s);
             const unsigned sa_blocks = (unsigned)((Nw * (H / 4) + 7) / 8);     // a warp per (sequence, 4 heads)
-            if (bf16 && e->use_kv_epilogue) launch_args(decode_self_attention_g8<8, __nv_bfloat16, false>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
+            if (bf16 && e->use_kv_epilogue && e->kv_tok_major && H % 8 == 0)      // token-major pages: a warp per (sequence, 8 heads)
+                launch_args(decode_self_attention_tm<8>, dim3((unsigned)((Nw * (H / 8) + 7) / 8)), dim3(256), 0, s, pdl_u, (const float*)b.qkv, (const __nv_bfloat16*)reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, b.att16);
+            else if (bf16 && e->use_kv_epilogue) launch_args(decode_self_attention_g8<8, __nv_bfloat16, false>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
             else if (bf16) launch_args(decode_self_attention_g8<8, __nv_bfloat16>, dim3(sa_blocks), dim3(256), 0, s, pdl_u, (const float*)b.qkv, reinterpret_cast<__nv_bfloat16*>(pool), (const int*)b.block_table, pps, Nw, H, scale, step, (float*)nullptr, b.att16);
             else decode_self_attention_g8<8, float><<<sa_blocks, 256, 0, s>>>(b.qkv, reinterpret_cast<float*>(pool), b.block_table, pps, Nw, H, scale, step, b.att, b.att16);
             MMT_TRY(check_launch(e, "decode_self_attention", s));
@@ -1619,10 +1626,13 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_TC_ATTENTION_FP32")) e->tc_attention_fp32 = true;
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
+    if (getenv("MMT_DEC_PROJ_TWO_TERM")) e->dec_proj_single = false;
+    if (const char* v = getenv("MMT_DEC_PROJ_SINGLE_ROWS")) e->dec_proj_single_rows = atoi(v);
     if (const char* v = getenv("MMT_PDL_ROWS")) e->pdl_rows = atoi(v);
     if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
     if (getenv("MMT_NO_FFN_WIDE")) e->use_ffn_wide = false;
     if (getenv("MMT_NO_KV_EPILOGUE")) e->use_kv_epilogue = false;
+    if (getenv("MMT_KV_HEAD_MAJOR")) e->kv_tok_major = false;
     if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));

@@ -1065,6 +1065,103 @@ __global__ void __launch_bounds__(256) decode_self_attention_g8(const float* qkv
     if (out16) out16[n * D + h * DH + kl] = __float2bfloat16_rn(o);
 }
 
+// Large bf16 waves: TOKEN-MAJOR pages, [PAGE_TOKENS][2 (K,V)][H][DH] -- the K | V of one token are 512 contiguous bytes.
+// With the head-major page every (K|V, head) plane of the OPEN page is a 256-byte run of which (t % 16 + 1) x 16 bytes are
+// valid, and the memory system fetches the whole 128-byte lines: ncu read the full 8 KB of the open page at every step
+// (1902 MB of DRAM reads against 1670 MB of valid rows at t = 41).  Token-major, the valid tokens of the open page are one
+// contiguous prefix, and the QKV projection's epilogue appends a token as two 256-byte row segments instead of 32 scattered
+// 16-byte pieces.  Mapping: a warp serves eight heads of a sequence, lane (h8, kl) owns the keys j = kl (mod 4) of head h8:
+// one load instruction covers 4 tokens x 128 contiguous bytes.  Online softmax, two keys per lane in flight and two more
+// prefetched; the 8 output dimensions are reduce-scattered over the 4 lanes of a head (lane kl keeps dimensions 2 kl,
+// 2 kl + 1), so a warp stores 128 consecutive bytes.  K / V of position t are already in the cache (kernels_tc.cuh).
+template <int DH>
+__global__ void __launch_bounds__(256) decode_self_attention_tm(const float* qd, const __nv_bfloat16* kv_pool, const int* block_table,
+                                                                int pages_per_seq, int64_t N, int H, float scale,
+                                                                const int* step, __nv_bfloat16* out16) {
+    static_assert(DH == 8, "8-element key rows");
+    typedef KvRow<__nv_bfloat16> KV;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = *step;
+    const int HG = H / 8;                                  // head groups per sequence
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= N * HG) return;
+    const int lane = threadIdx.x & 31, h8 = lane >> 2, kl = lane & 3;
+    const int64_t n = w / HG;
+    const int h = (int)(w % HG) * 8 + h8;
+    constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
+    const int* bt = block_table + n * pages_per_seq;
+    const float* row = qd + n * D + h * DH;
+    float q[DH], acc[DH];
+    {
+        const float4 a = *reinterpret_cast<const float4*>(row), b = *reinterpret_cast<const float4*>(row + 4);
+        q[0] = a.x * scale; q[1] = a.y * scale; q[2] = a.z * scale; q[3] = a.w * scale;
+        q[4] = b.x * scale; q[5] = b.y * scale; q[6] = b.z * scale; q[7] = b.w * scale;
+    }
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+    float m = MMT_NEG_INF, l = 0.f;
+    auto row_ptr = [&](int j) { return kv_pool + (int64_t)bt[j / PAGE_TOKENS] * PAGE_ELEMS + (j % PAGE_TOKENS) * (2 * D) + h * DH; };
+    typename KV::Raw rk0, rk1, rv0, rv1;
+    if (kl <= t) {
+        const __nv_bfloat16* p0 = row_ptr(kl);
+        const __nv_bfloat16* p1 = row_ptr(kl + 4 <= t ? kl + 4 : kl);
+        rk0 = KV::ld(p0); rk1 = KV::ld(p1);
+        rv0 = KV::ld(p0 + D); rv1 = KV::ld(p1 + D);
+    }
+    for (int j0 = kl; j0 <= t; j0 += 8) {
+        const bool has1 = j0 + 4 <= t;
+        const typename KV::Raw ck0 = rk0, ck1 = rk1, cv0 = rv0, cv1 = rv1;
+        const int jn = j0 + 8;
+        if (jn <= t) {
+            const __nv_bfloat16* p0 = row_ptr(jn);
+            const __nv_bfloat16* p1 = row_ptr(jn + 4 <= t ? jn + 4 : jn);
+            rk0 = KV::ld(p0); rk1 = KV::ld(p1);
+            rv0 = KV::ld(p0 + D); rv1 = KV::ld(p1 + D);
+        }
+        float k0[DH], k1[DH];
+        KV::unpack(ck0, k0); KV::unpack(ck1, k1);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) { s0 = fmaf(q[d], k0[d], s0); s1 = fmaf(q[d], k1[d], s1); }
+        if (!has1) s1 = MMT_NEG_INF;
+        const float mn = fmaxf(m, fmaxf(s0, s1));
+        if (mn > m) {
+            const float corr = expf(m - mn);
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] *= corr;
+            m = mn;
+        }
+        const float e0 = expf(s0 - m), e1 = has1 ? expf(s1 - m) : 0.f;
+        l += e0 + e1;
+        float v0[DH], v1[DH];
+        KV::unpack(cv0, v0); KV::unpack(cv1, v1);
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[d] = fmaf(e1, v1[d], fmaf(e0, v0[d], acc[d]));
+    }
+    // merge the four per-lane partial softmaxes of a head (lanes without a key carry m = -inf, l = 0)
+    float Mx = m;
+    Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, 1)); Mx = fmaxf(Mx, __shfl_xor_sync(0xffffffffu, Mx, 2));
+    const float corr = (m == MMT_NEG_INF) ? 0.f : expf(m - Mx);
+    l *= corr;
+    l += __shfl_xor_sync(0xffffffffu, l, 1); l += __shfl_xor_sync(0xffffffffu, l, 2);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] *= corr;
+#pragma unroll
+    for (int off = 2; off >= 1; off >>= 1) {          // 8-value reduce-scatter over the 4 lanes: lane kl keeps dimensions 2 kl, 2 kl + 1
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 2 * off; ++i) {
+            const float send = up ? acc[i] : acc[i + 2 * off];
+            const float keep = up ? acc[i + 2 * off] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    const __nv_bfloat162 o = __floats2bfloat162_rn(acc[0] / l, acc[1] / l);
+    *reinterpret_cast<__nv_bfloat162*>(out16 + n * D + h * DH + 2 * kl) = o;
+}
+
 // Cross-attention of the new position over the (compacted) projected memory;
 // one warp per (sequence, head).  K/V layout: [spectrum][K|V][H][rows_total = rows per spectrum][DH] of KVT.
 template <int DH, typename KVT>

@@ -59,7 +59,8 @@ struct TcGemmParams {
     // Decoder self-attention QKV projection (N = 384): columns 128.. (K, V of the new position) go straight into the paged bf16
     // KV cache of the layer -- page block_table[row * pps + t / 16], slot t % 16, t = *step -- instead of an fp32 row the
     // attention kernel would re-read and append; only the Q columns are stored to out_f32.
-    int kv_append; __nv_bfloat16* kv_pool; const int* block_table; int pps; const int* step; int kv_heads;
+    int kv_append;   // 0 none, 1 head-major pages, 2 token-major pages
+    __nv_bfloat16* kv_pool; const int* block_table; int pps; const int* step; int kv_heads;
     // Chained projection (LayerNorm epilogue only): chain_out[r] = bf16(LN output row r) . Wc^T + chain_bias, Wc [128,128] as a
     // two-term bf16 split.  The decoder's "out-proj + LN1" and "cross-attention query projection" as ONE launch: the
     // normalised rows go to shared memory as the A operand of a second MMA instead of round-tripping through HBM.
@@ -278,12 +279,14 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
 
 // the KV-append fields exist in TcGemmParams only (the fused FFN shares this epilogue and has none)
 __device__ __forceinline__ bool epi_kv_append(const TcGemmParams& p) { return p.kv_append != 0; }
+__device__ __forceinline__ bool epi_kv_tok_major(const TcGemmParams& p) { return p.kv_append == 2; }
 __device__ __forceinline__ const int* epi_kv_step(const TcGemmParams& p) { return p.step; }
 __device__ __forceinline__ int epi_kv_heads(const TcGemmParams& p) { return p.kv_heads; }
 __device__ __forceinline__ __nv_bfloat16* epi_kv_pool(const TcGemmParams& p) { return p.kv_pool; }
 __device__ __forceinline__ const int* epi_kv_bt(const TcGemmParams& p) { return p.block_table; }
 __device__ __forceinline__ int epi_kv_pps(const TcGemmParams& p) { return p.pps; }
 template <class P> __device__ __forceinline__ bool epi_kv_append(const P&) { return false; }
+template <class P> __device__ __forceinline__ bool epi_kv_tok_major(const P&) { return false; }
 template <class P> __device__ __forceinline__ const int* epi_kv_step(const P&) { return nullptr; }
 template <class P> __device__ __forceinline__ int epi_kv_heads(const P&) { return 1; }
 template <class P> __device__ __forceinline__ __nv_bfloat16* epi_kv_pool(const P&) { return nullptr; }
@@ -328,12 +331,14 @@ __device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, i
         __nv_bfloat16* const pool = epi_kv_pool(p);
         const int* bt = epi_kv_bt(p);
         const int pps = epi_kv_pps(p);
+        // head-major page [K|V][H][16][dh]; token-major page [16][K|V][H][dh] (a warp then writes one 256-byte run per row)
+        const int off = epi_kv_tok_major(p) ? ((t % PAGE_TOKENS) * 2 + kv) * D + cc : ((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * dh + d0;
 #pragma unroll 4
         for (int i = 0; i < rows; ++i) {
             const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS);
             const float4 v = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
             const int64_t page = bt[(int64_t)(row0 + i) * pps + t / PAGE_TOKENS];
-            *reinterpret_cast<uint2*>(pool + page * (2 * PAGE_TOKENS * D) + ((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * dh + d0) = pack_bf16x4(v);
+            *reinterpret_cast<uint2*>(pool + page * (2 * PAGE_TOKENS * D) + off) = pack_bf16x4(v);
         }
         return;
     }

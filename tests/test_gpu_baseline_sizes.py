@@ -271,7 +271,9 @@ def test_chained_projection_equals_two_launches(monkeypatch):
     s = setup()
     from multimodalspectraltransformer_b200 import synthetic
     M = s["M"]
-    m_chain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0")
+    # (head-major pages on both sides: the token-major self-attention kernel partitions the keys of a head over four lanes
+    # instead of eight, another summation order -- covered by test_token_major_pages_equal_head_major_pages)
+    m_chain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_KV_HEAD_MAJOR="1")
     m_plain = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_NO_GEMM_CHAIN="1", MMT_NO_FFN_PROLOGUE="1", MMT_NO_KV_EPILOGUE="1")
     for B, K, T in ((41, 7, 10), (300, 16, 6), (19, 128, 5)):
         data = synthetic.make_spectra(B, seed=700 + B)
@@ -282,3 +284,34 @@ def test_chained_projection_equals_two_launches(monkeypatch):
             torch.manual_seed(11)
             out.append(M.multinomial_sequence_multi(m, memory, mask, STOI, cfg, n_candidates=K))
         assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), (B, K)
+
+
+def test_token_major_pages_equal_head_major_pages(monkeypatch):
+    """Large bf16 waves keep the self-attention cache in TOKEN-major pages ([16][K|V][H][8]: the QKV projection's epilogue
+    appends a token as contiguous rows, `decode_self_attention_tm` reads only the valid prefix of the open page); the
+    head-major pages + `decode_self_attention_g8` remain behind MMT_KV_HEAD_MAJOR=1.  Same values in the cache, another
+    partition of a head's keys over lanes (fp32 round-off of the attention row before its bf16 rounding): positions 0..3
+    have at most one key per lane in both kernels -> the first sampled tokens are identical; afterwards ids equal except
+    at near-ties, probabilities to bf16 accuracy.  T = 40 crosses two page boundaries (closed pages + an open page); the
+    last case is a wave with a partial last tile."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    M = s["M"]
+    m_tm = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0")
+    m_hm = model_with(monkeypatch, MMT_FUSED_DECODE_ROWS="0", MMT_KV_HEAD_MAJOR="1")
+    for B, K, T in ((24, 16, 40), (19, 128, 20), (5, 3, 33)):
+        data = synthetic.make_spectra(B, seed=900 + B)
+        cfg = cfg_for(precision="bf16", max_len=T)
+        memory, mask, *_ = M.run_model(s["model"], data, cfg)
+        out = []
+        for m in (m_tm, m_hm):
+            torch.manual_seed(13)
+            mt, mp_ = M.multinomial_sequence_multi(m, memory, mask, STOI, cfg, n_candidates=K)
+            gt, gp = M.greedy_sequence(m, STOI, None, memory, mask, cfg, n_candidates=K)
+            out.append((mt, mp_, gt, gp))
+        a, b = out
+        for x_tok, x_pr, y_tok, y_pr in ((a[0], a[1], b[0], b[1]), (a[2], a[3], b[2], b[3])):
+            assert torch.equal(x_tok[:2], y_tok[:2]), (B, K)
+            same = (x_tok == y_tok).all(dim=0)
+            assert same.float().mean().item() >= 0.7, (B, K, same.float().mean().item())
+            assert float((x_pr[:, same] - y_pr[:, same]).abs().max()) < 2e-2
