@@ -274,7 +274,7 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
         else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<1>(), s, pdl, p);
     } else {   // hi term only: the deeper pipeline variant
         if (epi == TC_EPI_LN && p.splits == 1 && p.F % (2 * FF_CH) == 0 && e->use_ffn_wide)      // 128-column chunks
-            launch_kernel(ffn_fused_tc<TC_EPI_LN, 0, 1>, grid, dim3(FF_THREADS), ff_smem_bytes<0, 1>(), s, pdl, p);
+            launch_kernel(ffn_fused_tc<TC_EPI_LN, 0, 1>, grid, dim3(ff_threads<0, 1>()), ff_smem_bytes<0, 1>(), s, pdl, p);
         else if (epi == TC_EPI_LN) launch_kernel(ffn_fused_tc<TC_EPI_LN, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
         else launch_kernel(ffn_fused_tc<TC_EPI_STORE, 0>, grid, dim3(FF_THREADS), ff_smem_bytes<0>(), s, pdl, p);
     }

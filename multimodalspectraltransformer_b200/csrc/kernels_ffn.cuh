@@ -46,7 +46,8 @@ namespace mmt {
 
 constexpr int FF_CH = 64;                                  // hidden columns per chunk
 constexpr int FF_THREADS = TC_THREADS + 32;                // producer + GEMM1 issuer + 8 epilogue warps + GEMM2 issuer
-constexpr int FF_G2_WARP = 2 + TC_EPI_WARPS;               // warp 10 (the epilogue warps must be 2-9: TMEM lane quarter = warp id % 4)
+// (the epilogue warps start at warp 2: TMEM lane quarter = warp id % 4; the GEMM2 issuer is the warp after them)
+template <int WS, int WIDE> constexpr int ff_threads();    // 64 + 32 * epilogue warps + 32
 constexpr int FF_X_BYTES = 2 * TC_SLAB_BYTES;              // X: two K slabs of [128 rows x 64]
 constexpr int FF_H_BYTES = TC_SLAB_BYTES;                  // one H buffer: [128 rows x 64] bf16
 constexpr int FF_W1_HALF = FF_CH * 128;                    // 8 KB: 64 rows x 128 B (one term of one K slab)
@@ -61,6 +62,7 @@ constexpr int FF_MAX_F = 2048;
 template <int WS, int WIDE> struct FfCfg;
 template <> struct FfCfg<1, 0> {       // two-term weights
     static constexpr int CH = FF_CH, NB = 2, NS = 2;                       // chunk width, acc1 / H buffers, weight ring stages
+    static constexpr int EW = TC_EPI_WARPS;                                // epilogue warps
     static constexpr int W1_STAGE = FF_W1_STAGE, W2_STAGE = FF_W2_STAGE;   // 32 KB each (hi | lo)
     static constexpr int W1_SLAB = TC_SLAB_BYTES;                          // K slab stride inside a W1 stage
     static constexpr int W2_KSLAB = 2 * TC_SLAB_BYTES;                     // 64-k slab stride inside a W2 stage (one slab: hi rows | lo rows)
@@ -69,6 +71,7 @@ template <> struct FfCfg<1, 0> {       // two-term weights
 };
 template <> struct FfCfg<0, 0> {       // hi term only, 64-column chunks (split-F partial path): deeper pipeline in the freed TMEM / shared memory
     static constexpr int CH = FF_CH, NB = 3, NS = 4;
+    static constexpr int EW = TC_EPI_WARPS;
     static constexpr int W1_STAGE = FF_W1_STAGE / 2, W2_STAGE = FF_W2_STAGE / 2;   // 16 KB each
     static constexpr int W1_SLAB = FF_W1_HALF;                             // 8 KB: [64 rows x 64 k]
     static constexpr int W2_KSLAB = TC_SLAB_BYTES;
@@ -77,12 +80,17 @@ template <> struct FfCfg<0, 0> {       // hi term only, 64-column chunks (split-
 };
 template <> struct FfCfg<0, 1> {       // hi term only, 128-column chunks (LayerNorm epilogue, whole F per CTA)
     static constexpr int CH = 2 * FF_CH, NB = 2, NS = 2;
+    // 16 epilogue warps (four per TMEM lane quarter): per 128-row tile the epilogue warps carry ~32 K cycles of latency-bound
+    // work (two LayerNorm passes of 8 K cycles at 16 rows per warp, 16 conversions) against ~17 K cycles of tensor time --
+    // with twice the warps every one of those chains is half as long
+    static constexpr int EW = 2 * TC_EPI_WARPS;
     static constexpr int W1_STAGE = 2 * TC_SLAB_BYTES, W2_STAGE = 2 * TC_SLAB_BYTES;   // [128 rows x 128 k] each: two 64-k slabs of 16 KB
     static constexpr int W1_SLAB = TC_SLAB_BYTES;
     static constexpr int W2_KSLAB = TC_SLAB_BYTES;
     static constexpr int H_BYTES = 2 * FF_H_BYTES;                         // two 64-k slabs
     static constexpr int ACC1_STRIDE = 2 * FF_CH, ACC2_COL = 256;
 };
+template <int WS, int WIDE> constexpr int ff_threads() { return 64 + 32 * FfCfg<WS, WIDE>::EW + 32; }
 // dynamic smem: X (32 KB) | H (NB buffers) | W1 ring | W2 ring + alignment slack
 template <int WS, int WIDE = 0> constexpr int ff_smem_bytes() {
     typedef FfCfg<WS, WIDE> C;
@@ -149,17 +157,19 @@ struct LnView {
 };
 
 template <int EPI, int WS, int WIDE = 0>
-__global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
+__global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(const __grid_constant__ FfnParams p) {
     static_assert(!WIDE || (WS == 0 && EPI == TC_EPI_LN), "128-column chunks: hi term + LayerNorm epilogue only");
     typedef FfCfg<WS, WIDE> C;
     constexpr int NB = C::NB, NS = C::NS, CH = C::CH;
+    constexpr int EW = C::EW, NP = EW / 4, RPW = 32 / NP;      // epilogue warps, warps per TMEM lane quarter, rows per warp in the row passes
+    constexpr int FF_G2_WARP = 2 + EW;
     extern __shared__ uint8_t smem_raw[];
     // "GEMM1 of chunk i retired" frees a W1 stage AND publishes acc1; "GEMM2 of chunk j retired" frees a W2 stage AND an H
     // buffer: one tcgen05.commit each (a commit costs the issuing thread a few hundred cycles), on barrier rings of
     // R = lcm(NS, NB) slots so that every waiter (whatever its buffer count) finds chunk i's barrier at slot i % R
     constexpr int R = 12;
     static_assert(R % NS == 0 && R % NB == 0, "barrier ring must be a multiple of both buffer counts");
-    __shared__ __align__(8) uint64_t x_full, w1_full[NS], w2_full[NS], h_full[NB], g1_done[R], g2_done[R], acc2_full;
+    __shared__ __align__(8) uint64_t x_full, w1_full[NS], w2_full[NS], h_full[NB], acc1_free[NB], g1_done[R], g2_done[R], acc2_full;
     __shared__ __align__(8) uint64_t pro_w_full, pro_acc_full, x2_ready;
     const bool pro = EPI == TC_EPI_LN && p.pro;
     __shared__ uint32_t tmem_slot;
@@ -183,9 +193,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         if (WS) { tma_prefetch_desc(&p.tmW1lo); tma_prefetch_desc(&p.tmW2lo); }
         mbar_init(&x_full, 1); mbar_init(&acc2_full, 1);
         for (int s = 0; s < NS; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w2_full[s], 1); }
-        for (int s = 0; s < NB; ++s) mbar_init(&h_full[s], TC_EPI_WARPS);     // one arrival per epilogue warp (256 arrivals on one barrier serialise)
+        for (int s = 0; s < NB; ++s) { mbar_init(&acc1_free[s], EW); mbar_init(&h_full[s], EW); }     // one arrival per epilogue warp (256 arrivals on one barrier serialise)
         for (int s = 0; s < R; ++s) { mbar_init(&g1_done[s], 1); mbar_init(&g2_done[s], 1); }
-        if (pro) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmPlo); mbar_init(&pro_w_full, 1); mbar_init(&pro_acc_full, 1); mbar_init(&x2_ready, TC_EPI_WARPS); }
+        if (pro) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmPlo); mbar_init(&pro_w_full, 1); mbar_init(&pro_acc_full, 1); mbar_init(&x2_ready, EW); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, FF_TMEM_COLS);
@@ -284,7 +294,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             for (int i = 0; i < n; ++i) {
                 const int s = i % NS;
                 mbar_wait(&w1_full[s], ((uint32_t)(i / NS)) & 1u);
-                if (i >= NB) mbar_wait(&h_full[i % NB], ((uint32_t)((i - NB) / NB)) & 1u);
+                // acc1[i % NB] is free once every epilogue warp has READ chunk i - NB out of it (acc1_free), well before that
+                // chunk's H tile is written and fenced (h_full): the round trip "conversion done -> GEMM1 two chunks on -> its
+                // commit -> next conversion" was the chunk loop's critical path (1.1 K cycles per chunk with every MMA, TMA
+                // load and conversion removed)
+                if (i >= NB) mbar_wait(&acc1_free[i % NB], ((uint32_t)((i - NB) / NB)) & 1u);
                 tc_fence_after();
                 const uint32_t w1 = smem_u32(sW + (size_t)s * C::W1_STAGE);
                 const uint32_t acc1 = tmem_base + (uint32_t)((i % NB) * C::ACC1_STRIDE);
@@ -319,17 +333,18 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         }
     } else {
         // ---------------- epilogue warps: warp (id % 4) owns TMEM lanes [32*(id%4), +32); thread = row;
-        // the two warps of a quarter split the chunk's 64 columns
+        // the NP warps of a quarter split the chunk's columns (hf = 0 .. NP - 1)
+        static_assert(!WS || NP == 2, "epi_tmem2_to_stage splits the columns in halves");
         const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         if (pro) {
             mbar_wait(&pro_acc_full, 0);
             tc_fence_after();
             float* stage_p = reinterpret_cast<float*>(sW) + (q * 32) * TC_LDS;
-            epi_tmem_to_stage<TC_BN>(tmem_acc2, q, hf, lane, stage_p);
-            epi_bar_sync();
+            epi_tmem_to_stage<TC_BN, NP>(tmem_acc2, q, hf, lane, stage_p);
+            epi_bar_sync<EW>();
             LnView v{p.pro_bias, p.pro_gamma, p.pro_beta, p.res, p.pro_out, nullptr, D, D, p.M, p.eps, nullptr, p.M > 0 ? p.M : 1, 0, 1, 0};
-            epi_rows_ln(v, stage_p + (hf * 16) * TC_LDS, m0 + q * 32 + hf * 16, 16, lane, sX, q * 32 + hf * 16);
+            epi_rows_ln(v, stage_p + (hf * RPW) * TC_LDS, m0 + q * 32 + hf * RPW, RPW, lane, sX, q * 32 + hf * RPW);
             fence_proxy_async_smem();          // the rewritten X tile -> visible to the tensor core
             tc_fence_before();
             __syncwarp();
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         for (int i = 0; i < n; ++i) {
             const int b = i % NB;
             // this warp converts columns [hf * CH / 2, + CH / 2) of its 32 rows, 32 columns at a time
-            constexpr int CPW = CH / 2;
+            constexpr int CPW = CH / NP;
             // bias slice of this chunk (a decode-loop constant): in registers before the accumulator is ready
             float4 bias[CPW / 32][8];
 #pragma unroll
@@ -354,6 +369,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
             if ((p.knock & 2) && i > 0) {
 #pragma unroll
                 for (int j = 0; j < CPW / 2; ++j) pk[j] = 0x3c003c00u;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc1_free[b]);
             } else {
                 // every TMEM load of the warp's columns is issued before the one wait (a load -> wait -> convert sequence per 32
                 // columns put the TMEM latency on the chunk's critical path once per 32 columns)
@@ -365,6 +382,9 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
                     if (WS) tmem_ld_32x32(t0 + FF_CH, rl[cc]);
                 }
                 tmem_ld_wait();
+                tc_fence_before();                 // the accumulator is in registers: GEMM1 of chunk i + NB may overwrite it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc1_free[b]);
 #pragma unroll
                 for (int cc = 0; cc < CPW / 32; ++cc) {
                     const float4* bb = bias[cc];
@@ -403,12 +423,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_fused_tc(const __grid_const
         tc_fence_after();
         if (threadIdx.x == 64) FF_STAMP(4);
         if (WS) epi_tmem2_to_stage(tmem_acc2, q, hf, lane, stage_q);
-        else epi_tmem_to_stage<TC_BN>(tmem_acc2, q, hf, lane, stage_q);
-        epi_bar_sync();
+        else epi_tmem_to_stage<TC_BN, NP>(tmem_acc2, q, hf, lane, stage_q);
+        epi_bar_sync<EW>();
         if (threadIdx.x == 64) FF_STAMP(5);
-        const float* st = stage_q + (hf * 16) * TC_LDS;
-        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane);
-        else epi_rows_store(p, st, m0 + q * 32 + hf * 16, 16, 0, split, lane);
+        const float* st = stage_q + (hf * RPW) * TC_LDS;
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * RPW, RPW, lane);
+        else epi_rows_store(p, st, m0 + q * 32 + hf * RPW, RPW, 0, split, lane);
         if (threadIdx.x == 64) FF_STAMP(6);
     }
     tc_fence_before();

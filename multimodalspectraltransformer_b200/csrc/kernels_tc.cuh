@@ -179,11 +179,13 @@ constexpr int EPI_ILP = 8;
 // Epilogue warp e = warp - 2 owns TMEM lane quarter q = warp % 4 (hardware rule) and half hf = e / 4:
 // it moves the hf-th half of the accumulator columns of its 32 rows into the staging tile, and after
 // epi_bar_sync() processes rows [16*hf, 16*hf + 16) of the quarter.
-template <int NCOLS>
+// (NP = epilogue warps per lane quarter: 2 by default; the wide fused-FFN variant runs 4, each moving a quarter of the columns
+// and then 8 of the quarter's rows)
+template <int NCOLS, int NP = 2>
 __device__ __forceinline__ void epi_tmem_to_stage(uint32_t tmem_acc, int q, int hf, int lane, float* stage_q) {
 #pragma unroll
-    for (int cc = 0; cc < NCOLS / 64; ++cc) {
-        const int c = hf * (NCOLS / 64) + cc;
+    for (int cc = 0; cc < NCOLS / 32 / NP; ++cc) {
+        const int c = hf * (NCOLS / 32 / NP) + cc;
         uint32_t r[32];
         tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         tmem_ld_wait();
@@ -194,7 +196,8 @@ __device__ __forceinline__ void epi_tmem_to_stage(uint32_t tmem_acc, int q, int 
                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     }
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory"); }
+template <int EW = TC_EPI_WARPS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); }
 
 __device__ __forceinline__ void warp_sum_ilp(float (&s)[EPI_ILP]) {
 #pragma unroll
