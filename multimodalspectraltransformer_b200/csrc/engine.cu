@@ -218,11 +218,11 @@ static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int
     if (p.wsplit) MMT_TRY(make_tmap(&p.tmW2, Wlo, p.N, p.K, p.K));
     size_t smem = (size_t)std::max(p.stages * (p.wsplit ? TC_STAGE_BYTES_WSPLIT : TC_STAGE_BYTES), TC_STAGING_BYTES) + 1024;
     if (chain) {
-        if (epi != TC_EPI_LN || !chain->W || !chain->Wlo || !chain->bias || !chain->out) MMT_FAIL("chained projection needs the LayerNorm epilogue and a two-term weight");
-        p.chain = 1; p.chain_bias = chain->bias; p.chain_out = chain->out; p.ld_chain = chain->ld;
+        if (epi != TC_EPI_LN || !chain->W || !chain->bias || !chain->out) MMT_FAIL("chained projection needs the LayerNorm epilogue and a weight");
+        p.chain = chain->Wlo ? 2 : 1; p.chain_bias = chain->bias; p.chain_out = chain->out; p.ld_chain = chain->ld;
         MMT_TRY(make_tmap(&p.tmC, chain->W, D, D, D));
-        MMT_TRY(make_tmap(&p.tmC2, chain->Wlo, D, D, D));
-        smem = ((smem - 1024 + 1023) & ~size_t(1023)) + TC_CHAIN_BYTES + 1024;
+        if (chain->Wlo) MMT_TRY(make_tmap(&p.tmC2, chain->Wlo, D, D, D));
+        smem = ((smem - 1024 + 1023) & ~size_t(1023)) + (chain->Wlo ? TC_CHAIN_BYTES : TC_CHAIN_BYTES - 2 * TC_SLAB_BYTES) + 1024;
     }
     dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
     prof_pre(e, s);
@@ -260,11 +260,11 @@ static int launch_ffn(mmt_engine* e, FfnParams& p, const __nv_bfloat16* X, int64
         MMT_TRY(make_tmap(&p.tmW2lo, W2lo, D, p.F, p.F));
     }
     if (pro) {
-        if (epi != TC_EPI_LN || p.splits != 1 || !pro->W || !pro->Wlo || !pro->out || p.res != pro->out)
-            MMT_FAIL("fused FFN prologue needs the LayerNorm epilogue, a two-term weight and the residual buffer as its output");
-        p.pro = 1; p.pro_bias = pro->bias; p.pro_gamma = pro->gamma; p.pro_beta = pro->beta; p.pro_out = pro->out;
+        if (epi != TC_EPI_LN || p.splits != 1 || !pro->W || !pro->out || p.res != pro->out)
+            MMT_FAIL("fused FFN prologue needs the LayerNorm epilogue, a weight and the residual buffer as its output");
+        p.pro = pro->Wlo ? 2 : 1; p.pro_bias = pro->bias; p.pro_gamma = pro->gamma; p.pro_beta = pro->beta; p.pro_out = pro->out;
         MMT_TRY(make_tmap(&p.tmP, pro->W, D, D, D));
-        MMT_TRY(make_tmap(&p.tmPlo, pro->Wlo, D, D, D));
+        if (pro->Wlo) MMT_TRY(make_tmap(&p.tmPlo, pro->Wlo, D, D, D));
     }
     dim3 grid(p.splits, (p.M + TC_BM - 1) / TC_BM);
     if (const char* v = getenv("MMT_FFN_KNOCK")) p.knock = atoi(v);
@@ -1034,11 +1034,13 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         p.splits = splits; p.part_stride = Nw * D;
         return launch_gemm(e, p, 1, M, s);
     };
-    // The attention projections of LARGE waves run on the hi term of the bf16 weight split alone, like the small-wave kernel's
-    // (decode_attn keeps only the hi terms in shared memory): one weight slab per stage -> 68 KB instead of 100 KB of shared
-    // memory per CTA (three resident tiles per SM instead of two), half the weight TMA bytes and MMAs.
+    // The four attention projections of the un-fused step run on the hi term of the bf16 weight split alone, like the small-wave
+    // kernel's (decode_attn keeps only the hi terms in shared memory): one weight slab per stage -> 68 KB instead of 100 KB of
+    // shared memory per CTA (three resident tiles per SM instead of two), half the weight TMA bytes and MMAs.  At every wave
+    // size, so that a shard decoded alone reproduces its rows of the full call bit for bit.  Measured on the golden cases:
+    // worst logit error 6.37e-3 -> 6.20e-3 of the row scale, mean +12 % (profiles/r02_bf16_error_dec_proj_terms.txt).
     // MMT_DEC_PROJ_TWO_TERM=1 restores both terms.
-    auto plo = [&](const float* w) -> const __nv_bfloat16* { return (e->dec_proj_single && M > e->dec_proj_single_rows) ? nullptr : e->Wlo(w); };
+    auto plo = [&](const float* w) -> const __nv_bfloat16* { return e->dec_proj_single ? nullptr : e->Wlo(w); };
     // tensor-core variants: plain projection (fp32 or bf16 out) and projection + residual + LN in place on x / x16
     auto tc = [&](const __nv_bfloat16* A, int64_t lda, const float* W, const float* bias, float* C32, __nv_bfloat16* C16, int N, int K, int act, int splits) -> int {
         TcGemmParams p = tc_params(M, N, K);
@@ -1051,7 +1053,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         TcGemmParams p = tc_params(M, D, K);
         p.bias = bias; p.res = b.x; p.gamma = gamma; p.beta = beta;
         p.out_f32 = b.x; p.ld_f32 = D; p.out_b16 = b.x16; p.ld_b16 = D;
-        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, chain ? e->Wlo(W) : plo(W), pdl_u, chain);
+        return launch_tc(e, p, A, lda, e->Wb(W), TC_EPI_LN, s, plo(W), pdl_u, chain);
     };
     // The decoder FFN runs on the hi term of the bf16 weight split alone: measured on the 12 golden cases the lo term changes
     // the worst logit error from 5.75e-3 to 5.76e-3 of the row scale (profiles/r02_bf16_error.md) for twice the tensor work.
@@ -1145,7 +1147,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 // kernel holds 192 KB of shared memory (one CTA per SM instead of three), which costs more than the saved launch
                 // once there are several tiles per SM (measured: 1383 -> 1357 us per position at 16,384 rows, 4851 -> 4901 at 65,536)
                 if (e->use_gemm_chain && Nw <= 24576) {
-                    const TcChain ch{e->Wb(w.ca_in_w), e->Wlo(w.ca_in_w), w.ca_in_b, b.qc, D};
+                    const TcChain ch{e->Wb(w.ca_in_w), plo(w.ca_in_w), w.ca_in_b, b.qc, D};
                     MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b, &ch));
                 } else {
                     MMT_TRY(tc_ln(b.att16, D, w.out_w, w.out_b, D, w.n1_w, w.n1_b));
@@ -1173,7 +1175,7 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                         f.dbg = l == 3 ? e->ffn_dbg : nullptr;
                     }
                     if (ffn_pro) {
-                        const FfnPro pr{e->Wb(w.ca_out_w), e->Wlo(w.ca_out_w), w.ca_out_b, w.n2_w, w.n2_b, b.x};
+                        const FfnPro pr{e->Wb(w.ca_out_w), plo(w.ca_out_w), w.ca_out_b, w.n2_w, w.n2_b, b.x};
                         MMT_TRY(launch_ffn(e, f, b.att16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_LN, s, pdl_u, &pr));
                     } else
                     MMT_TRY(launch_ffn(e, f, b.x16, D, e->Wb(w.l1_w), dlo(w.l1_w), e->Wb(w.l2_w), dlo(w.l2_w), TC_EPI_LN, s, pdl_u));
@@ -1627,7 +1629,6 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (const char* v = getenv("MMT_FUSED_DECODE_ROWS")) e->fused_decode_rows = atoi(v);
     if (getenv("MMT_DEC_FFN_TWO_TERM")) e->dec_ffn_single = false;
     if (getenv("MMT_DEC_PROJ_TWO_TERM")) e->dec_proj_single = false;
-    if (const char* v = getenv("MMT_DEC_PROJ_SINGLE_ROWS")) e->dec_proj_single_rows = atoi(v);
     if (const char* v = getenv("MMT_PDL_ROWS")) e->pdl_rows = atoi(v);
     if (getenv("MMT_NO_GEMM_CHAIN")) e->use_gemm_chain = false;
     if (getenv("MMT_NO_FFN_WIDE")) e->use_ffn_wide = false;

@@ -124,7 +124,7 @@ struct FfnParams {
     // the kernel first computes  x = LN(res + X . Wp^T + pro_bias) * pro_gamma + pro_beta  (the decoder's cross-attention
     // out-projection + norm2), writes it to pro_out (fp32, the residual of the FFN's own LayerNorm) and to the X tile in shared
     // memory (bf16), then runs the FFN on it: one launch and one HBM round trip of the activations less per layer.
-    int pro;
+    int pro;                         // 0 none, 1 Wp hi term only, 2 both terms
     CUtensorMap tmP, tmPlo;          // Wp [128,128] bf16 hi / lo, box {64,128}
     const float *pro_bias, *pro_gamma, *pro_beta; float* pro_out;
     int knock;                       // timing experiments only (MMT_FFN_KNOCK, results garbage): 1 no weight TMA after the first ring fill,
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(cons
         for (int s = 0; s < NS; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w2_full[s], 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(&acc1_free[s], EW); mbar_init(&h_full[s], EW); }     // one arrival per epilogue warp (256 arrivals on one barrier serialise)
         for (int s = 0; s < R; ++s) { mbar_init(&g1_done[s], 1); mbar_init(&g2_done[s], 1); }
-        if (pro) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmPlo); mbar_init(&pro_w_full, 1); mbar_init(&pro_acc_full, 1); mbar_init(&x2_ready, EW); }
+        if (pro) { tma_prefetch_desc(&p.tmP); if (p.pro == 2) tma_prefetch_desc(&p.tmPlo); mbar_init(&pro_w_full, 1); mbar_init(&pro_acc_full, 1); mbar_init(&x2_ready, EW); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, FF_TMEM_COLS);
@@ -221,10 +221,10 @@ __global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(cons
             if (pro) {
                 // prologue weights (decode-loop constants) into the still idle W2 ring, then the attention output tile; the
                 // weight rings start only when the prologue is over: its staging tile lies over them
-                mbar_arrive_expect_tx(&pro_w_full, 4 * TC_SLAB_BYTES);
+                mbar_arrive_expect_tx(&pro_w_full, (p.pro == 2 ? 4 : 2) * TC_SLAB_BYTES);
                 for (int ks = 0; ks < 2; ++ks) {
                     tma_load_2d(sW2 + ks * TC_SLAB_BYTES, &p.tmP, &pro_w_full, ks * TC_BK, 0);
-                    tma_load_2d(sW2 + (2 + ks) * TC_SLAB_BYTES, &p.tmPlo, &pro_w_full, ks * TC_BK, 0);
+                    if (p.pro == 2) tma_load_2d(sW2 + (2 + ks) * TC_SLAB_BYTES, &p.tmPlo, &pro_w_full, ks * TC_BK, 0);
                 }
                 pdl_wait(); load_x();
                 mbar_wait(&x2_ready, 0);
@@ -279,8 +279,7 @@ __global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(cons
                 const uint32_t idescP = umma_idesc_bf16(TC_BM, TC_BN);
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint64_t adesc = umma_desc_sw128(x_addr + ks * TC_SLAB_BYTES);
-#pragma unroll
-                    for (int t2 = 0; t2 < 2; ++t2) {
+                    for (int t2 = 0; t2 < p.pro; ++t2) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(sW2 + (2 * t2 + ks) * TC_SLAB_BYTES));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)

@@ -64,7 +64,7 @@ struct TcGemmParams {
     // Chained projection (LayerNorm epilogue only): chain_out[r] = bf16(LN output row r) . Wc^T + chain_bias, Wc [128,128] as a
     // two-term bf16 split.  The decoder's "out-proj + LN1" and "cross-attention query projection" as ONE launch: the
     // normalised rows go to shared memory as the A operand of a second MMA instead of round-tripping through HBM.
-    int chain;
+    int chain;                // 0 none, 1 Wc hi term only, 2 both terms
     CUtensorMap tmC, tmC2;    // Wc hi / lo, box {64,128}, SWIZZLE_128B
     const float* chain_bias; float* chain_out; int64_t ld_chain;
 };
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
         if (p.wsplit) tma_prefetch_desc(&p.tmW2);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
-        if (chain) { tma_prefetch_desc(&p.tmC); tma_prefetch_desc(&p.tmC2); mbar_init(&chain_w_bar, 1); mbar_init(&chain_a_bar, TC_EPI_WARPS); mbar_init(&chain_acc_bar, 1); }
+        if (chain) { tma_prefetch_desc(&p.tmC); if (p.chain == 2) tma_prefetch_desc(&p.tmC2); mbar_init(&chain_w_bar, 1); mbar_init(&chain_a_bar, TC_EPI_WARPS); mbar_init(&chain_acc_bar, 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, tmem_cols);
@@ -405,10 +405,10 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             if (chain) {             // the chained weights are decode-loop constants: in flight before the PDL wait
-                mbar_arrive_expect_tx(&chain_w_bar, 4 * TC_SLAB_BYTES);
+                mbar_arrive_expect_tx(&chain_w_bar, (p.chain == 2 ? 4 : 2) * TC_SLAB_BYTES);
                 for (int ks = 0; ks < 2; ++ks) {
                     tma_load_2d(sC + (2 + ks) * TC_SLAB_BYTES, &p.tmC, &chain_w_bar, ks * TC_BK, 0);
-                    tma_load_2d(sC + (4 + ks) * TC_SLAB_BYTES, &p.tmC2, &chain_w_bar, ks * TC_BK, 0);
+                    if (p.chain == 2) tma_load_2d(sC + (4 + ks) * TC_SLAB_BYTES, &p.tmC2, &chain_w_bar, ks * TC_BK, 0);
                 }
             }
             pdl_wait();              // A is the predecessor's output
@@ -452,8 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
                 tc_fence_after();
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint64_t adesc = umma_desc_sw128(smem_u32(sC + ks * TC_SLAB_BYTES));
-#pragma unroll
-                    for (int t2 = 0; t2 < 2; ++t2) {
+                    for (int t2 = 0; t2 < p.chain; ++t2) {
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(sC + (2 + 2 * t2 + ks) * TC_SLAB_BYTES));
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)
