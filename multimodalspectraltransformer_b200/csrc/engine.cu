@@ -199,6 +199,14 @@ static TcGemmParams tc_params(int M, int N, int K) {
 
 // A [M,K] bf16 (row pitch lda), W [N,K] bf16 (dense), optional low-order weight term Wlo; the
 // rest of `p` is filled by the caller
+// sample_tokens keeps fc_out in dynamic shared memory (33 KB at the 64-row maximum, next to 20 KB of static row buffers)
+static int sample_init(mmt_engine* e) {
+    if (e->sample_ready) return 0;
+    MMT_CUDA(cudaFuncSetAttribute(sample_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sample_smem_bytes(VOCAB_MAX)));
+    e->sample_ready = true;
+    return 0;
+}
+
 struct TcChain { const __nv_bfloat16 *W, *Wlo; const float* bias; float* out; int64_t ld; };
 static int launch_tc(mmt_engine* e, TcGemmParams& p, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int epi, cudaStream_t s,
                      const __nv_bfloat16* Wlo = nullptr, bool pdl = false, const TcChain* chain = nullptr) {
@@ -1221,9 +1229,10 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     }
     prof_pre(e, s);
     {   // rows per CTA and pass: 2 when the input is still spread over FFN2 partials, else 8; at most four resident waves of CTAs
-        const int rpc = sp.part ? 2 : 8;
+        const int rpc = sp.part ? 2 : SAMPLE_ROWS;
         const int64_t groups = (Nw + rpc - 1) / rpc;
-        launch_kernel(sample_tokens, dim3((unsigned)std::min<int64_t>(groups, (int64_t)e->sm_count * 4)), dim3(256), 0, s, pdl || pdl_u, sp);
+        MMT_TRY(sample_init(e));
+        launch_kernel(sample_tokens, dim3((unsigned)std::min<int64_t>(groups, (int64_t)e->sm_count * 4)), dim3(256), sample_smem_bytes(sp.V), s, pdl || pdl_u, sp);
     }
     MMT_TRY(check_launch(e, "sample_tokens", s));
     return 0;
@@ -1885,7 +1894,8 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
     sp.advance = 0;
     cudaStream_t cs = (cudaStream_t)stream;
     prof_pre(e, cs);
-    sample_tokens<<<(unsigned)std::min<int64_t>((N + 7) / 8, (int64_t)e->sm_count * 4), 256, 0, cs>>>(sp);
+    MMT_TRY(sample_init(e));
+    sample_tokens<<<(unsigned)std::min<int64_t>((N + SAMPLE_ROWS - 1) / SAMPLE_ROWS, (int64_t)e->sm_count * 4), 256, sample_smem_bytes(sp.V), cs>>>(sp);
     return check_launch(e, "sample_tokens", cs);
 }
 

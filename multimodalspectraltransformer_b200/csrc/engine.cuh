@@ -126,6 +126,7 @@ struct mmt_engine {
     bool use_ffn_wide = true;          // hi-term FFN with the LayerNorm epilogue: 128-column chunks (MMT_NO_FFN_WIDE=1: 64)
     bool use_gemm_chain = true;        // un-fused decode step: out-proj + LN1 + cross-attention query projection as one launch (MMT_NO_GEMM_CHAIN=1 disables)
     bool dec_proj_single = true;       // un-fused bf16 step: attention projections on the hi weight term only (MMT_DEC_PROJ_TWO_TERM=1: both terms)
+    bool sample_ready = false;         // sample_tokens' dynamic shared memory attribute set
     bool dec_ffn_single = true;        // decoder FFN on the hi weight term only (MMT_DEC_FFN_TWO_TERM=1: both terms)
     bool use_compact = true;           // ragged encoder: compute distinct token rows only (MMT_DENSE_ENCODER=1 disables)
     struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int64_t launches_per_group; uint64_t stamp; };

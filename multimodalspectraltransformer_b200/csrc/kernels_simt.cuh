@@ -1379,13 +1379,98 @@ struct SampleParams {
 };
 
 // CTA = 8 warps.  Rows are taken in groups of `rpc` per CTA, grid-stride: a CTA stages fc_out once and keeps sampling
-// groups (large waves: 2048 CTAs each re-loading the 22 KB matrix cost more than the sampling itself).  rpc = 8: one warp
-// per row.  rpc = 2 (fused decoder path, whose input is still spread over the FFN2 split partials): four warps per row,
-// each with a quarter of the partials in flight at once -- the reduction is an L2 round trip per pass, so its depth sets
-// the kernel's latency on the 13-kernel chain of a small wave.
+// groups (large waves: 2048 CTAs each re-loading the 22 KB matrix cost more than the sampling itself).
+// rpc = 32 (dense input): a warp owns FOUR rows and walks fc_out once for all of them -- with one row per warp the 43 x 128
+// projection is 384 shared-memory loads per row (the kernel was bound by them: 173 us per position of 75,776 rows); four
+// rows share every weight load and read x as broadcast float4 (96 per row).  Every accumulator still sums k = 0 .. 127 in
+// order: the logits are bit-identical to the one-row form.
+// rpc = 2 (fused decoder path, whose input is still spread over the FFN2 split partials): four warps per row in the input
+// phase, each with a quarter of the partials in flight at once -- the reduction is an L2 round trip per pass, so its depth
+// sets the kernel's latency on the 13-kernel chain of a small wave -- then one row per warp.
+constexpr int SAMPLE_NR = 4;             // rows per warp (dense input)
+constexpr int SAMPLE_ROWS = 8 * SAMPLE_NR;
+
+template <int NR>
+__device__ __forceinline__ void sample_rows(const SampleParams& p, const float* Ws, const float (*xs)[D], int r0, int64_t n0, int t, int lane, int& my_nonpad) {
+    const int v0 = lane, v1 = lane + 32;
+    float a0[NR], a1[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
+    const float* w0 = Ws + v0 * (D + 1);
+    const float* w1 = Ws + (v1 < p.V ? v1 : 0) * (D + 1);
+#pragma unroll 2
+    for (int k = 0; k < D; k += 4) {
+        const float w00 = w0[k], w01 = w0[k + 1], w02 = w0[k + 2], w03 = w0[k + 3];
+        const float w10 = w1[k], w11 = w1[k + 1], w12 = w1[k + 2], w13 = w1[k + 3];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(&xs[r0 + r][k]);
+            a0[r] = fmaf(xv.x, w00, a0[r]); a1[r] = fmaf(xv.x, w10, a1[r]);
+            a0[r] = fmaf(xv.y, w01, a0[r]); a1[r] = fmaf(xv.y, w11, a1[r]);
+            a0[r] = fmaf(xv.z, w02, a0[r]); a1[r] = fmaf(xv.z, w12, a1[r]);
+            a0[r] = fmaf(xv.w, w03, a0[r]); a1[r] = fmaf(xv.w, w13, a1[r]);
+        }
+    }
+    const bool ok0 = v0 < p.V, ok1 = v1 < p.V;
+    const float b0 = ok0 ? p.b[v0] : 0.f, b1 = ok1 ? p.b[v1] : 0.f;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int64_t n = n0 + r;
+        if (n >= p.N) break;
+        float lg0 = ok0 ? a0[r] + b0 : MMT_NEG_INF;
+        float lg1 = ok1 ? a1[r] + b1 : MMT_NEG_INF;
+        if (p.logits) {
+            float* out = p.logits + ((int64_t)t * p.ldn + n) * p.V;
+            if (ok0) out[v0] = lg0;
+            if (ok1) out[v1] = lg1;
+        }
+        if (p.mode == 2) continue;
+        float z0 = ok0 ? lg0 / p.temperature : MMT_NEG_INF;
+        float z1 = ok1 ? lg1 / p.temperature : MMT_NEG_INF;
+        float mx = warp_max(fmaxf(z0, z1));
+        float e0 = ok0 ? expf(z0 - mx) : 0.f;
+        float e1 = ok1 ? expf(z1 - mx) : 0.f;
+        float sum = warp_sum(e0 + e1);
+        float p0 = e0 / sum, p1 = e1 / sum;
+        if (p.target) {       // probability of the given token (validate_generate_MMT_v15_4.py:372-374)
+            const int64_t tg = p.target[(int64_t)t * p.ldn + n];
+            const float a = __shfl_sync(0xffffffffu, p0, (int)(tg & 31)), b = __shfl_sync(0xffffffffu, p1, (int)(tg & 31));
+            if (lane == 0) p.target_prob[(int64_t)t * p.ldn + n] = (tg < 0 || tg >= p.V) ? 0.f : (tg < 32 ? a : b);
+        }
+        float r0v = p0, r1v = p1;
+        if (p.mode == 1) {
+            RngGeom g = p.rng;
+            if (p.rng_dev) { g.seed = p.rng_dev[0]; g.offset = p.rng_dev[1]; }
+            g.offset += (uint64_t)t * p.rng_inc;
+            int64_t li = (p.seq_index_base + n) * p.V;
+            if (ok0) r0v = p0 / torch_exponential_at(g, li + v0);
+            if (ok1) r1v = p1 / torch_exponential_at(g, li + v1);
+        }
+        // argmax with lowest-index ties (torch argmax / multinomial)
+        float best = ok0 ? r0v : MMT_NEG_INF;
+        int bi = ok0 ? v0 : 0x7fffffff;
+        float bp = p0;
+        if (ok1 && (r1v > best)) { best = r1v; bi = v1; bp = p1; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            float op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bp = op; }
+        }
+        if (lane == 0) {
+            if (p.tokens) p.tokens[(int64_t)t * p.ldn + n] = bi;
+            if (p.probs) p.probs[(int64_t)t * p.ldn + n] = bp;
+            my_nonpad += (bi != 0);
+        }
+    }
+}
+
+// dynamic shared memory: fc_out as V padded rows (sample_smem_bytes)
+__host__ __device__ constexpr size_t sample_smem_bytes(int V) { return (size_t)V * (D + 1) * sizeof(float); }
 __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ SampleParams p) {
-    __shared__ float Ws[VOCAB_MAX * (D + 1)];
-    __shared__ __align__(16) float xs[8][D];
+    extern __shared__ float Ws[];
+    __shared__ __align__(16) float xs[SAMPLE_ROWS][D];
     __shared__ __align__(16) float psum[8][D];
     __shared__ int s_nonpad;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1399,39 +1484,33 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
     if (threadIdx.x == 0) s_nonpad = 0;
     pdl_wait();
     const int t = p.ctl.step ? *p.ctl.step : 0;
-    const int rpc = p.part ? 2 : 8;                 // rows per CTA and pass
-    const int wpr = 8 / rpc;                        // warps per row in the input phase
+    const int rpc = p.part ? 2 : SAMPLE_ROWS;       // rows per CTA and pass
     int my_nonpad = 0;
     for (int64_t base = (int64_t)blockIdx.x * rpc; base < p.N; base += (int64_t)gridDim.x * rpc) {
-        {   // ---- input rows -> xs
+        if (p.part) {   // ---- input rows -> xs: four warps per row over the FFN2 partials
+            const int wpr = 4;
             const int r = warp / wpr, sl = warp % wpr;
             const int64_t n = base + r;
             if (n < p.N) {
-                if (p.part) {
-                    // slice sl sums partials sl, sl + wpr, ... (all in flight together), fixed order
-                    float4 q[8];
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k0 = sl; k0 < p.splits; k0 += 8 * wpr) {
+                // slice sl sums partials sl, sl + wpr, ... (all in flight together), fixed order
+                float4 q[8];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k0 = sl; k0 < p.splits; k0 += 8 * wpr) {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int k = k0 + u * wpr;
-                            q[u] = (k < p.splits) ? *reinterpret_cast<const float4*>(p.part + (int64_t)k * p.part_stride + n * D + lane * 4)
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) { a.x += q[u].x; a.y += q[u].y; a.z += q[u].z; a.w += q[u].w; }
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u * wpr;
+                        q[u] = (k < p.splits) ? *reinterpret_cast<const float4*>(p.part + (int64_t)k * p.part_stride + n * D + lane * 4)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    *reinterpret_cast<float4*>(&psum[warp][lane * 4]) = a;
-                } else if (sl == 0) {
-                    *reinterpret_cast<float4*>(&xs[r][lane * 4]) = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { a.x += q[u].x; a.y += q[u].y; a.z += q[u].z; a.w += q[u].w; }
                 }
+                *reinterpret_cast<float4*>(&psum[warp][lane * 4]) = a;
             }
-        }
-        if (p.part) {
             __syncthreads();
             if (warp < rpc && base + warp < p.N) {   // x <- LN3(x + b2 + sum of the slices), slices in fixed order
-                const int64_t n = base + warp;
-                float4 v = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+                const int64_t n2 = base + warp;
+                float4 v = *reinterpret_cast<const float4*>(p.x + n2 * D + lane * 4);
                 float4 sum = *reinterpret_cast<const float4*>(p.pbias + lane * 4);
                 for (int j = 0; j < wpr; ++j) {
                     const float4 q = *reinterpret_cast<const float4*>(&psum[warp * wpr + j][lane * 4]);
@@ -1440,68 +1519,16 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
                 v = ln_row(make_float4(v.x + sum.x, v.y + sum.y, v.z + sum.z, v.w + sum.w), p.pgamma, p.pbeta, p.eps, lane);
                 *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = v;
             }
-        }
-        __syncthreads();
-        const int64_t n = base + warp;
-        if (warp < rpc && n < p.N) {
-            const int v0 = lane, v1 = lane + 32;
-            float a0 = 0.f, a1 = 0.f;
-            const float* w0 = Ws + v0 * (D + 1);
-            const float* w1 = Ws + (v1 < p.V ? v1 : 0) * (D + 1);
-#pragma unroll 8
-            for (int k = 0; k < D; ++k) {
-                float xv = xs[warp][k];
-                a0 = fmaf(xv, w0[k], a0);
-                a1 = fmaf(xv, w1[k], a1);
-            }
-            const bool ok0 = v0 < p.V, ok1 = v1 < p.V;
-            float lg0 = ok0 ? a0 + p.b[v0] : MMT_NEG_INF;
-            float lg1 = ok1 ? a1 + p.b[v1] : MMT_NEG_INF;
-            if (p.logits) {
-                float* out = p.logits + ((int64_t)t * p.ldn + n) * p.V;
-                if (ok0) out[v0] = lg0;
-                if (ok1) out[v1] = lg1;
-            }
-            if (p.mode != 2) {
-                float z0 = ok0 ? lg0 / p.temperature : MMT_NEG_INF;
-                float z1 = ok1 ? lg1 / p.temperature : MMT_NEG_INF;
-                float mx = warp_max(fmaxf(z0, z1));
-                float e0 = ok0 ? expf(z0 - mx) : 0.f;
-                float e1 = ok1 ? expf(z1 - mx) : 0.f;
-                float sum = warp_sum(e0 + e1);
-                float p0 = e0 / sum, p1 = e1 / sum;
-                if (p.target) {       // probability of the given token (validate_generate_MMT_v15_4.py:372-374)
-                    const int64_t tg = p.target[(int64_t)t * p.ldn + n];
-                    const float a = __shfl_sync(0xffffffffu, p0, (int)(tg & 31)), b = __shfl_sync(0xffffffffu, p1, (int)(tg & 31));
-                    if (lane == 0) p.target_prob[(int64_t)t * p.ldn + n] = (tg < 0 || tg >= p.V) ? 0.f : (tg < 32 ? a : b);
-                }
-                float r0 = p0, r1 = p1;
-                if (p.mode == 1) {
-                    RngGeom g = p.rng;
-                    if (p.rng_dev) { g.seed = p.rng_dev[0]; g.offset = p.rng_dev[1]; }
-                    g.offset += (uint64_t)t * p.rng_inc;
-                    int64_t li = (p.seq_index_base + n) * p.V;
-                    if (ok0) r0 = p0 / torch_exponential_at(g, li + v0);
-                    if (ok1) r1 = p1 / torch_exponential_at(g, li + v1);
-                }
-                // argmax with lowest-index ties (torch argmax / multinomial)
-                float best = ok0 ? r0 : MMT_NEG_INF;
-                int bi = ok0 ? v0 : 0x7fffffff;
-                float bp = p0;
-                if (ok1 && (r1 > best)) { best = r1; bi = v1; bp = p1; }
+            __syncthreads();
+            if (warp < rpc && base + warp < p.N) sample_rows<1>(p, Ws, xs, warp, base + warp, t, lane, my_nonpad);
+        } else {        // ---- dense input: each warp stages and samples its own four rows
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    float op = __shfl_xor_sync(0xffffffffu, bp, o);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; bp = op; }
-                }
-                if (lane == 0) {
-                    if (p.tokens) p.tokens[(int64_t)t * p.ldn + n] = bi;
-                    if (p.probs) p.probs[(int64_t)t * p.ldn + n] = bp;
-                    my_nonpad += (bi != 0);
-                }
+            for (int r = 0; r < SAMPLE_NR; ++r) {
+                const int64_t n = base + warp * SAMPLE_NR + r;
+                if (n < p.N) *reinterpret_cast<float4*>(&xs[warp * SAMPLE_NR + r][lane * 4]) = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
             }
+            __syncthreads();      // (also orders the Ws staging of the first pass)
+            if (base + warp * SAMPLE_NR < p.N) sample_rows<SAMPLE_NR>(p, Ws, xs, warp * SAMPLE_NR, base + warp * SAMPLE_NR, t, lane, my_nonpad);
         }
         __syncthreads();          // xs / psum are rewritten by the next group
     }
