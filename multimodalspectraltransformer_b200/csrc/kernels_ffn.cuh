@@ -337,13 +337,16 @@ __global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(cons
         const int q = warp & 3, hf = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         if (pro) {
+            LnView v{p.pro_bias, p.pro_gamma, p.pro_beta, p.res, p.pro_out, nullptr, D, D, p.M, p.eps, nullptr, p.M > 0 ? p.M : 1, 0, 1, 0};
+            pdl_wait();                        // the residual rows are the predecessor's output
+            LnPre pre;
+            epi_ln_prefetch(v, m0 + q * 32 + hf * RPW, RPW, lane, pre);     // in flight under the X load and the prologue MMAs
             mbar_wait(&pro_acc_full, 0);
             tc_fence_after();
             float* stage_p = reinterpret_cast<float*>(sW) + (q * 32) * TC_LDS;
             epi_tmem_to_stage<TC_BN, NP>(tmem_acc2, q, hf, lane, stage_p);
             epi_bar_sync<EW>();
-            LnView v{p.pro_bias, p.pro_gamma, p.pro_beta, p.res, p.pro_out, nullptr, D, D, p.M, p.eps, nullptr, p.M > 0 ? p.M : 1, 0, 1, 0};
-            epi_rows_ln(v, stage_p + (hf * RPW) * TC_LDS, m0 + q * 32 + hf * RPW, RPW, lane, sX, q * 32 + hf * RPW);
+            epi_rows_ln(v, stage_p + (hf * RPW) * TC_LDS, m0 + q * 32 + hf * RPW, RPW, lane, sX, q * 32 + hf * RPW, &pre);
             fence_proxy_async_smem();          // the rewritten X tile -> visible to the tensor core
             tc_fence_before();
             __syncwarp();
@@ -418,6 +421,9 @@ __global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(cons
         }
         float* stage_q = reinterpret_cast<float*>(sW) + (q * 32) * TC_LDS;
         pdl_wait();                            // (already satisfied: acc2 depends on X) orders the stores below explicitly
+        LnPre pre;
+        // residual rows of the final LayerNorm (with the prologue: rows this very thread wrote) in flight while the last GEMM2 retires
+        if (EPI == TC_EPI_LN) epi_ln_prefetch(p, m0 + q * 32 + hf * RPW, RPW, lane, pre);
         mbar_wait(&acc2_full, 0);
         tc_fence_after();
         if (threadIdx.x == 64) FF_STAMP(4);
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__((ff_threads<WS, WIDE>()), 1) ffn_fused_tc(cons
         epi_bar_sync<EW>();
         if (threadIdx.x == 64) FF_STAMP(5);
         const float* st = stage_q + (hf * RPW) * TC_LDS;
-        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * RPW, RPW, lane);
+        if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * RPW, RPW, lane, nullptr, 0, &pre);
         else epi_rows_store(p, st, m0 + q * 32 + hf * RPW, RPW, 0, split, lane);
         if (threadIdx.x == 64) FF_STAMP(6);
     }

@@ -226,16 +226,37 @@ struct RowStep {
     }
 };
 
+// What a LayerNorm row pass reads from global memory that does not depend on the accumulator: bias / gamma / beta slices and
+// the residual rows of the pass's first batch.  Issued BEFORE the wait for the accumulator (all epilogue warps otherwise sit
+// through the same ~1-2 K cycles of load latency together, after the accumulator is ready and with nothing to overlap it).
+struct LnPre { float4 bias, ga, be; float4 rs[EPI_ILP]; };
+template <class P>
+__device__ __forceinline__ void epi_ln_prefetch(const P& p, int row0, int nrows, int lane, LnPre& pre) {
+    const int col = lane * 4;
+    pre.bias = p.bias ? *reinterpret_cast<const float4*>(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pre.ga = *reinterpret_cast<const float4*>(p.gamma + col);
+    pre.be = *reinterpret_cast<const float4*>(p.beta + col);
+    const int rows = min(nrows, p.M - row0);
+    const float* res = p.res + (int64_t)row0 * D + col;
+#pragma unroll
+    for (int u = 0; u < EPI_ILP; ++u)
+        pre.rs[u] = u < rows ? *reinterpret_cast<const float4*>(res + (int64_t)u * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // out[map(r)] = LN(stage[r] + bias + res[r]) * gamma + beta for the warp's 32 rows (N == 128)
 // a2 != nullptr: the normalised rows are also written as bf16 into a 128B-swizzled K-major operand tile (two K slabs of
 // [128 rows x 64]); a2_row0 = tile-local index of the warp's first row
 template <class P>
-__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int nrows, int lane, uint8_t* a2 = nullptr, int a2_row0 = 0) {
+__device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int row0, int nrows, int lane, uint8_t* a2 = nullptr, int a2_row0 = 0,
+                                            const LnPre* pre = nullptr) {
     const int col = lane * 4;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + col);
-    const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col);
-    const float4 be = *reinterpret_cast<const float4*>(p.beta + col);
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), ga, be;
+    if (pre) { bias = pre->bias; ga = pre->ga; be = pre->be; }
+    else {
+        if (p.bias) bias = *reinterpret_cast<const float4*>(p.bias + col);
+        ga = *reinterpret_cast<const float4*>(p.gamma + col);
+        be = *reinterpret_cast<const float4*>(p.beta + col);
+    }
     const int rows = min(nrows, p.M - row0);
     if (rows <= 0) return;
     const float* res = p.res + (int64_t)row0 * D + col;
@@ -250,7 +271,8 @@ __device__ __forceinline__ void epi_rows_ln(const P& p, const float* stage, int 
 #pragma unroll
         for (int u = 0; u < EPI_ILP; ++u) {
             const bool ok = i0 + u < rows;
-            const float4 rs = ok ? *reinterpret_cast<const float4*>(res + (int64_t)(i0 + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 rs = (pre && i0 == 0) ? pre->rs[u]
+                            : ok ? *reinterpret_cast<const float4*>(res + (int64_t)(i0 + u) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 a = *reinterpret_cast<const float4*>(stage + (i0 + u) * TC_LDS + col);
             v[u] = make_float4(a.x + bias.x + rs.x, a.y + bias.y + rs.y, a.z + bias.z + rs.z, a.w + bias.w + rs.w);
             s[u] = v[u].x + v[u].y + v[u].z + v[u].w;
@@ -472,6 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_bf16_tc(const __grid_constant
         epi_tmem_to_stage<TC_BN>(tmem_base, q, hf, lane, stage_q);
         epi_bar_sync();
         const float* st = stage_q + (hf * 16) * TC_LDS;
+        // (no LnPre here: measured, the prefetch registers cost this kernel its second resident CTA -- 28.9 -> 42 us per launch)
         if (EPI == TC_EPI_LN) epi_rows_ln(p, st, m0 + q * 32 + hf * 16, 16, lane, chain ? sC : nullptr, q * 32 + hf * 16);
         else epi_rows_store(p, st, m0 + q * 32 + hf * 16, 16, n0, split, lane);
         if (chain) {
