@@ -358,11 +358,15 @@ __device__ __forceinline__ void epi_rows_store(const P& p, const float* stage, i
         const int pps = epi_kv_pps(p);
         // head-major page [K|V][H][16][dh]; token-major page [16][K|V][H][dh] (a warp then writes one 256-byte run per row)
         const int off = epi_kv_tok_major(p) ? ((t % PAGE_TOKENS) * 2 + kv) * D + cc : ((kv * H + h) * PAGE_TOKENS + (t % PAGE_TOKENS)) * dh + d0;
+        // the rows' page numbers in one load (lane i holds row i's): a block-table load per row put an L2 round trip in front of
+        // every batch of stores
+        const int my_page = lane < rows ? bt[(int64_t)(row0 + lane) * pps + t / PAGE_TOKENS] : 0;
+        const unsigned live = __activemask();      // (N = 384 here: all lanes; lanes past N have returned above)
 #pragma unroll 4
         for (int i = 0; i < rows; ++i) {
             const float4 a = *reinterpret_cast<const float4*>(st + i * TC_LDS);
             const float4 v = make_float4(a.x + bias.x, a.y + bias.y, a.z + bias.z, a.w + bias.w);
-            const int64_t page = bt[(int64_t)(row0 + i) * pps + t / PAGE_TOKENS];
+            const int64_t page = __shfl_sync(live, my_page, i);
             *reinterpret_cast<uint2*>(pool + page * (2 * PAGE_TOKENS * D) + off) = pack_bf16x4(v);
         }
         return;

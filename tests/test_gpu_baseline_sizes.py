@@ -315,3 +315,4 @@ def test_token_major_pages_equal_head_major_pages(monkeypatch):
             same = (x_tok == y_tok).all(dim=0)
             assert same.float().mean().item() >= 0.7, (B, K, same.float().mean().item())
             assert float((x_pr[:, same] - y_pr[:, same]).abs().max()) < 2e-2
+
