@@ -61,6 +61,21 @@ static void launch_kernel(void (*kernel)(P), dim3 grid, dim3 block, size_t smem,
     cudaLaunchKernelEx(&cfg, kernel, params);     // errors surface through cudaGetLastError() in check_launch
 }
 
+// the same as a thread-block-cluster launch (cluster_x CTAs along x; grid.x must be a multiple of it)
+template <typename P>
+static void launch_kernel_cluster(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, unsigned cluster_x, const P& params) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 // the same for kernels that take their arguments one by one
 template <typename... KArgs, typename... Args>
 static void launch_args(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
@@ -1077,14 +1092,19 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
         if (!e->da_ready) {
             MMT_CUDA(cudaFuncSetAttribute(decode_attn<8, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
             MMT_CUDA(cudaFuncSetAttribute(decode_attn<8, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES));
+            MMT_CUDA(cudaFuncSetAttribute(decode_attn<8, __nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_BYTES_CL));
             e->da_ready = true;
         }
-        const unsigned blocks = (unsigned)((Nw + DA_R - 1) / DA_R);
+        unsigned blocks = (unsigned)((Nw + DA_R - 1) / DA_R);
+        // tensor-core mode: the FFN runs inside decode_attn, as clusters of DA_CL CTAs (kernels_decode.cuh)
+        const bool cl_ffn = bf16 && e->use_cluster_ffn && d.d_ff == DA_FF;
+        if (cl_ffn) blocks = (blocks + DA_CL - 1) / DA_CL * DA_CL;
         // bf16: F/64 = 32 chunks over (splits x M/128) CTAs -- enough splits to cover the SMs
         ffn_splits = pick_splits(M, D, d.d_ff);
         if (bf16) { ffn_splits = 32; while (ffn_splits > 1 && (int64_t)(ffn_splits / 2) * ((M + 127) / 128) >= e->sm_count) ffn_splits /= 2; }
         if (bf16 && e->ffn_splits_override > 0) ffn_splits = e->ffn_splits_override;
-        if ((int64_t)ffn_splits * Nw > b.part_rows) MMT_FAIL("decode: FFN partial buffer too small for this wave (plan_decoder)");
+        if (!cl_ffn && (int64_t)ffn_splits * Nw > b.part_rows) MMT_FAIL("decode: FFN partial buffer too small for this wave (plan_decoder)");
+        if (cl_ffn) ffn_splits = 0;
         for (int l = 0; l < d.n_dec_layers; ++l) {
             const LayerW& w = e->dec[l];
             DecAttnParams q;
@@ -1095,8 +1115,14 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
                 q.sos = 3; q.ldn = ldn; q.E_tok = e->W("embed_trg.weight"); q.E_pos = e->W("pe_trg.weight"); q.vocab = d.vocab;
             } else {
                 const LayerW& pw = e->dec[l - 1];
-                q.x_in = b.x; q.part = b.part; q.splits = ffn_splits; q.part_stride = Nw * D;
-                q.pbias = pw.l2_b; q.pgamma = pw.n3_w; q.pbeta = pw.n3_b;
+                q.x_in = b.x;
+                if (!cl_ffn) { q.part = b.part; q.splits = ffn_splits; q.part_stride = Nw * D; q.pbias = pw.l2_b; q.pgamma = pw.n3_w; q.pbeta = pw.n3_b; }
+            }
+            if (cl_ffn) {
+                MMT_TRY(tc_init(e));
+                MMT_TRY(make_tmap(&q.tmW1, e->Wb(w.l1_w), d.d_ff, D, D));
+                MMT_TRY(make_tmap(&q.tmW2, e->Wb(w.l2_w), D, d.d_ff, d.d_ff));
+                q.b1 = w.l1_b; q.b2 = w.l2_b; q.n3_w = w.n3_w; q.n3_b = w.n3_b; q.x_out = b.x;
             }
             q.in_w = w.in_w; q.in_b = w.in_b; q.out_w = w.out_w; q.out_b = w.out_b; q.n1_w = w.n1_w; q.n1_b = w.n1_b;
             q.kv_pool = b.kv_pool + (size_t)l * b.pool_pages * 2 * PAGE_TOKENS * D * b.kv_esz; q.block_table = b.block_table; q.pps = pps;
@@ -1109,9 +1135,11 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
             q.dbg = (e->da_dbg && l == 3) ? e->da_dbg : nullptr;
             prof_pre(e, s);
             const bool pdl_l = pdl && !(l == 0 && r.serial_first);
-            if (bf16) launch_kernel(decode_attn<8, __nv_bfloat16>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl_l, q);
+            if (cl_ffn) launch_kernel_cluster(decode_attn<8, __nv_bfloat16, true>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES_CL, s, pdl_l, DA_CL, q);
+            else if (bf16) launch_kernel(decode_attn<8, __nv_bfloat16>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl_l, q);
             else launch_kernel(decode_attn<8, float>, dim3(blocks), dim3(DA_THREADS), DA_SMEM_BYTES, s, pdl_l, q);
             MMT_TRY(check_launch(e, "decode_attn", s));
+            if (cl_ffn) continue;
             if (bf16) {
                 FfnParams f = ffn_params(M, d.d_ff);
                 f.b1 = w.l1_b; f.splits = ffn_splits; f.out_f32 = b.part; f.part_stride = Nw * D;
@@ -1222,14 +1250,15 @@ static int decode_step(mmt_engine* e, const DecodeRun& r, int64_t n0, int64_t Nw
     sp.target = r.target ? r.target + n0 : nullptr; sp.target_prob = r.target_prob ? r.target_prob + n0 : nullptr;
     sp.ctl.step = b.ctl; sp.ctl.done_ctas = b.ctl + 1; sp.ctl.nonpad = (r.mode == 0) ? b.ctl + 8 : nullptr;
     sp.advance = 1;
-    if (fused) {   // norm3 of the last layer over the FFN2 partials
+    if (fused && ffn_splits > 0) {   // norm3 of the last layer over the FFN2 partials (the cluster variant has applied it)
         const LayerW& pw = e->dec[d.n_dec_layers - 1];
         sp.part = b.part; sp.splits = ffn_splits; sp.part_stride = Nw * D;
         sp.pbias = pw.l2_b; sp.pgamma = pw.n3_w; sp.pbeta = pw.n3_b; sp.eps = 1e-5f;
     }
     prof_pre(e, s);
     {   // rows per CTA and pass: 2 when the input is still spread over FFN2 partials, else 8; at most four resident waves of CTAs
-        const int rpc = sp.part ? 2 : SAMPLE_ROWS;
+        sp.rows_per_warp = Nw >= 8192 ? SAMPLE_NR : 1;       // small waves: one row per warp (latency), large: four (shared-memory traffic)
+        const int rpc = sp.part ? 2 : 8 * sp.rows_per_warp;
         const int64_t groups = (Nw + rpc - 1) / rpc;
         MMT_TRY(sample_init(e));
         launch_kernel(sample_tokens, dim3((unsigned)std::min<int64_t>(groups, (int64_t)e->sm_count * 4)), dim3(256), sample_smem_bytes(sp.V), s, pdl || pdl_u, sp);
@@ -1440,8 +1469,9 @@ static int run_decode(mmt_engine* e, const DecodeRun& r, int32_t* h_steps, cudaS
         const int blocks = (int)std::min<int64_t>(4096, (std::min<int64_t>(N_total, max_wave_seqs) + DA_R - 1) / DA_R);
         for (int bshow : {0, blocks / 2, blocks - 1}) {
             fprintf(stderr, "decode_attn phases, CTA %d:", bshow);
-            for (int i = 1; i <= 10; ++i) fprintf(stderr, " %lld", e->da_dbg[bshow * 16 + i] - e->da_dbg[bshow * 16 + i - 1]);
-            fprintf(stderr, "  total %lld\n", e->da_dbg[bshow * 16 + 10] - e->da_dbg[bshow * 16]);
+            const int last = e->da_dbg[bshow * 16 + 14] ? 14 : 10;     // cluster variant: 10 gather | 11 GEMM1 | 12 GEMM2 | 13 scatter | 14 norm3
+            for (int i = 1; i <= last; ++i) fprintf(stderr, " %lld", e->da_dbg[bshow * 16 + i] - e->da_dbg[bshow * 16 + i - 1]);
+            fprintf(stderr, "  total %lld\n", e->da_dbg[bshow * 16 + last] - e->da_dbg[bshow * 16]);
         }
         for (int bshow : {1, blocks / 2}) {
             const long long* d = e->da_dbg + (1024 + bshow) * 16;
@@ -1643,6 +1673,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_NO_FFN_WIDE")) e->use_ffn_wide = false;
     if (getenv("MMT_NO_KV_EPILOGUE")) e->use_kv_epilogue = false;
     if (getenv("MMT_KV_HEAD_MAJOR")) e->kv_tok_major = false;
+    if (getenv("MMT_NO_CLUSTER_FFN")) e->use_cluster_ffn = false;
     if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));
@@ -1895,7 +1926,8 @@ int32_t mmt_sample(mmt_engine* e, const float* d_x, int64_t N, float temperature
     cudaStream_t cs = (cudaStream_t)stream;
     prof_pre(e, cs);
     MMT_TRY(sample_init(e));
-    sample_tokens<<<(unsigned)std::min<int64_t>((N + SAMPLE_ROWS - 1) / SAMPLE_ROWS, (int64_t)e->sm_count * 4), 256, sample_smem_bytes(sp.V), cs>>>(sp);
+    sp.rows_per_warp = N >= 8192 ? SAMPLE_NR : 1;
+    sample_tokens<<<(unsigned)std::min<int64_t>((N + 8 * sp.rows_per_warp - 1) / (8 * sp.rows_per_warp), (int64_t)e->sm_count * 4), 256, sample_smem_bytes(sp.V), cs>>>(sp);
     return check_launch(e, "sample_tokens", cs);
 }
 

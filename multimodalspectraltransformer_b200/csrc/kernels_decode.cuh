@@ -32,6 +32,8 @@
 // weight rows in shared memory) with 16 outputs per warp pass, finished by a shuffle reduce-scatter.
 #pragma once
 #include "common.cuh"
+#include "kernels_simt.cuh"   // ldmatrix_x4, mma_bf16_16816
+#include "kernels_tc.cuh"     // TMA / mbarrier wrappers (the cluster variant stages FFN weight tiles with cp.async.bulk.tensor)
 
 namespace mmt {
 
@@ -189,18 +191,64 @@ struct DecAttnParams {
     // tensor-core mode: the four projection matrices as bf16 (hi term of the two-term split), same shapes as the fp32 ones
     const __nv_bfloat16 *in_w16, *out_w16, *cq_w16, *co_w16;
     long long* dbg;                            // optional [gridDim.x][16] phase timestamps (MMT_DA_DEBUG)
+    // FFN = true (cluster variant, tensor-core mode): the layer's FFN + norm3 run inside this kernel
+    CUtensorMap tmW1, tmW2;                    // linear1 [F][128], linear2 [128][F] (hi terms, F = DA_FF), box {64 k, 128 rows}, SWIZZLE_128B
+    const float *b1, *b2, *n3_w, *n3_b;
+    float* x_out;                              // [M][D] layer output (the next layer's x_in / the sampler's x)
 };
 
-template <int DH, typename KVT>
+// ---- thread-block-cluster primitives (the FFN variant runs as clusters of DA_CL CTAs)
+constexpr int DA_CL = 4;                       // CTAs per cluster: 8 rows share one pass over the FFN weights
+constexpr int DA_FF = 2048;                    // d_ff
+constexpr int DA_FS = DA_FF / DA_CL;           // hidden columns per CTA
+constexpr int DA_XG_LD = D + 8;                // padded bf16 row of the gathered FFN input (conflict-free B fragments)
+constexpr int DA_HS_LD = DA_FS + 8;            // padded bf16 row of the hidden activation
+constexpr int DA_RED_LD = D + 4;               // padded fp32 row of the K-split partial outputs
+constexpr int DA_BOX = 16384;                  // one weight box: [128 rows][64 k] bf16, 128-byte rows, 16-byte chunks XOR (row & 7)
+constexpr int DA_SMEM_BYTES_CL = DA_SMEM_BYTES + 1024;     // + slack to align the weight buffer to the swizzle period
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_map(const void* local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(da_smem_u32(local)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_st_u32x2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void cluster_st_f32x2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+// FFN = true: the kernel is launched as clusters of DA_CL CTAs (8 rows) and ends with the layer's FFN and norm3 instead
+// of handing x2 to a separate FFN kernel:  the LN2 rows of the cluster are gathered (bf16) into every CTA through
+// distributed shared memory; CTA c computes hidden columns [c * 512, +512) for all 8 rows and its K-slice of the second
+// product on mma.sync m16n8k16 with the weight fragments read straight from L2 (256 KB per CTA and layer); the partial
+// outputs are scattered to the row owners, which add them in rank order, apply bias + residual + LayerNorm and write the
+// layer output.  This removes the FFN kernel, its two hand-offs and the split-F partial exchange through HBM from the
+// latency chain of a small wave (13 -> 7 launches per position).
+template <int DH, typename KVT, bool FFN = false>
 __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_constant__ DecAttnParams p) {
     static_assert(DH == 8 && DH * DA_H == D, "8-element key rows, 16 heads");
+    static_assert(!FFN || sizeof(KVT) == 2, "the in-kernel FFN exists in the tensor-core mode only");
     typedef KvRow<KVT> KV;
     extern __shared__ __align__(128) uint8_t da_smem[];
     constexpr bool W16 = sizeof(KVT) == 2;            // tensor-core mode: bf16 projection weights, all four resident at once
-    float* Wbuf = reinterpret_cast<float*>(da_smem);
-    __nv_bfloat16* Wb16 = reinterpret_cast<__nv_bfloat16*>(da_smem);    // W16 layout: in_w [384][128] | out_w | cq_w | co_w (192 KB)
+    // (cluster variant: the weight buffer later receives 128B-swizzled TMA boxes -> 1024-byte aligned)
+    uint8_t* const da_base = FFN ? da_smem + ((1024u - (da_smem_u32(da_smem) & 1023u)) & 1023u) : da_smem;
+    float* Wbuf = reinterpret_cast<float*>(da_base);
+    __nv_bfloat16* Wb16 = reinterpret_cast<__nv_bfloat16*>(da_base);    // W16 layout: in_w [384][128] | out_w | cq_w | co_w (192 KB)
     float* Ps = Wbuf + DA_W_FLOATS;
     __shared__ __align__(8) uint64_t bars[4];      // 0: in_w + vectors, 1: out_w, 2: cq_w, 3: co_w
+    // cluster variant: FFN weight boxes land in the regions the attention weights vacate --
+    // fb[0]: W1 boxes 0-5 -> in_w region | fb[1]: W1 boxes 6, 7 -> out_w | fb[2]: W2 boxes 0, 1 -> cq_w | fb[3]: W2 boxes 2, 3 -> co_w |
+    // fb[4], fb[5]: W2 boxes 4, 5 / 6, 7 -> in_w region once the first product has consumed W1
+    __shared__ __align__(8) uint64_t fb[6];
+    const uint32_t ffn_rank = FFN ? cluster_ctarank() : 0u;
+    const int f_base = (int)ffn_rank * DA_FS;
+    // W1 box j = (128-row block j / 2, K slab j % 2) of this CTA's 512 hidden columns; W2 box b = hidden columns [64 b, +64), all 128 rows
+    auto ffn_load_w1 = [&](int j, uint64_t* bar) { tma_load_2d(da_base + (size_t)j * DA_BOX, &p.tmW1, bar, (j & 1) * 64, f_base + (j >> 1) * 128); };
+    auto ffn_load_w2 = [&](int b, uint8_t* dst, uint64_t* bar) { tma_load_2d(dst, &p.tmW2, bar, f_base + b * 64, 0); };
     __shared__ __align__(16) float xs[DA_R][D];
     __shared__ __align__(16) float qkv[DA_R][3 * D];
     __shared__ __align__(16) float att[DA_R][D];
@@ -215,12 +263,14 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
 #define DA_STAMP2(i) do { if (p.dbg && threadIdx.x == 5 * 32) p.dbg[(1024 + blockIdx.x) * 16 + (i)] = clock64(); } while (0)
     DA_STAMP(0);
     pdl_launch_dependents();
+    if (FFN) cluster_arrive();     // "this CTA has started": waited for before the first remote shared-memory store
 
     // ---- weights of the first phase + every small vector: bulk async copies, issued before anything else
     // (one copy per lane of warp 0: a single thread issuing ~25 copies costs microseconds)
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < 4; ++i) da_mbar_init(&bars[i], 1);
+            if (FFN) { for (int i = 0; i < 6; ++i) da_mbar_init(&fb[i], 1); tma_prefetch_desc(&p.tmW1); tma_prefetch_desc(&p.tmW2); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const uint32_t vec_bytes = (uint32_t)(3 * D + 7 * D + (p.part ? 3 * D : 0)) * 4u;
             da_mbar_expect_tx(&bars[0], (W16 ? 3u * D * D * 2u : (uint32_t)DA_W_FLOATS * 4u) + vec_bytes);
@@ -307,6 +357,15 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         }
         __syncthreads();
         da_mbar_wait(&bars[0], 0);
+    } else if (FFN) {
+        // the previous layer's kernel has applied its norm3: x_in is the layer input
+        if (warp < DA_R) {
+            const int64_t nn = row0 + warp;
+            *reinterpret_cast<float4*>(&xs[warp][lane * 4]) =
+                nn < p.M ? *reinterpret_cast<const float4*>(p.x_in + nn * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        da_mbar_wait(&bars[0], 0);
     } else {
         // x = LN3(x_in + pbias + sum_s part[s]): the partial sums are spread over all warps (one L2
         // round trip), reduced through shared memory in a fixed order (deterministic)
@@ -366,6 +425,13 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             }                                                                                               \
         }                                                                                                   \
     } while (0)
+    // cluster variant: the first six boxes of this CTA's W1 slice replace the (dead) QKV matrix while the self-attention runs
+#define DA_ISSUE_FFN_W1A() do {                                                                             \
+        if (FFN && warp == 0 && lane == 0) {                                                                \
+            mbar_arrive_expect_tx(&fb[0], 6 * DA_BOX);                                                      \
+            for (int j_ = 0; j_ < 6; ++j_) ffn_load_w1(j_, &fb[0]);                                         \
+        }                                                                                                   \
+    } while (0)
     // ---- KV append + causal self-attention: one warp per (row, head)
     constexpr int PAGE_ELEMS = 2 * PAGE_TOKENS * D;
     KVT* const pool = reinterpret_cast<KVT*>(p.kv_pool);
@@ -401,6 +467,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
             }
         }
         DA_ISSUE_ROUND2();   // after this warp's K loads: the 192 KB of weights must not queue ahead of them on the SM's ingress
+        DA_ISSUE_FFN_W1A();
 #pragma unroll
         for (int i = 0; i < MAXK; ++i) {
             const int j = lane + i * 32;
@@ -452,9 +519,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
         DA_STAMP2(3);
     } else {
         DA_ISSUE_ROUND2();
+        DA_ISSUE_FFN_W1A();
         if (lane < DH) att[r][h * DH + lane] = 0.f;
     }
 #undef DA_ISSUE_ROUND2
+#undef DA_ISSUE_FFN_W1A
     __syncthreads();
     DA_STAMP2(4);
     DA_STAMP(4);
@@ -465,6 +534,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     if (W16) gemv_rows_w16(Wb16 + 3 * D * D, Ps + DA_P_OUTB, D, att, &qkv[0][0], 3 * D, warp, lane);
     else gemv_rows(Wbuf, Ps + DA_P_OUTB, D, att, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
+    if (FFN && warp == 1 && lane == 0) {       // out_w is dead: the last two W1 boxes
+        mbar_arrive_expect_tx(&fb[1], 2 * DA_BOX);
+        ffn_load_w1(6, &fb[1]); ffn_load_w1(7, &fb[1]);
+    }
     if (warp < DA_R) {
         const float4 a = *reinterpret_cast<const float4*>(&xs[warp][lane * 4]);
         const float4 y = *reinterpret_cast<const float4*>(&qkv[warp][lane * 4]);
@@ -479,6 +552,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     if (W16) gemv_rows_w16(Wb16 + 4 * D * D, Ps + DA_P_CQB, D, x1s, &xs[0][0], D, warp, lane);
     else gemv_rows(Wbuf + D * D, Ps + DA_P_CQB, D, x1s, &xs[0][0], D, warp, lane);
     __syncthreads();
+    if (FFN && warp == 0 && lane == 0) {       // cq_w is dead: W2 boxes 0, 1 (hidden columns 0..127 of the slice)
+        mbar_arrive_expect_tx(&fb[2], 2 * DA_BOX);
+        ffn_load_w2(0, da_base + 8 * DA_BOX, &fb[2]); ffn_load_w2(1, da_base + 9 * DA_BOX, &fb[2]);
+    }
     DA_STAMP(7);
 
     // ---- cross-attention over the projected memory: one warp per (row, head)
@@ -537,7 +614,119 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
     if (W16) gemv_rows_w16(Wb16 + 5 * D * D, Ps + DA_P_COB, D, att, &qkv[0][0], 3 * D, warp, lane);
     else gemv_rows(Wbuf + 2 * D * D, Ps + DA_P_COB, D, att, &qkv[0][0], 3 * D, warp, lane);
     __syncthreads();
+    if (FFN && warp == 2 && lane == 0) {       // co_w is dead: W2 boxes 2, 3
+        mbar_arrive_expect_tx(&fb[3], 2 * DA_BOX);
+        ffn_load_w2(2, da_base + 10 * DA_BOX, &fb[3]); ffn_load_w2(3, da_base + 11 * DA_BOX, &fb[3]);
+    }
     DA_STAMP(9);
+    if constexpr (FFN) {
+        // ================= in-kernel FFN over the cluster's 8 rows =================
+        // Both products are computed transposed -- out^T = W . in^T -- so that the 8 rows of the cluster are exactly the N = 8
+        // of mma.sync m16n8k16 and the weights are the A operand (ldmatrix from the swizzled boxes).
+        __shared__ __align__(16) float yp[DA_CL][DA_R][D];        // partial outputs of this CTA's rows, one slot per source CTA (remote stores)
+        // psum (16 KB) is unused in this variant: hidden activation | gathered FFN input (remote stores)
+        uint8_t* scratch = reinterpret_cast<uint8_t*>(&psum[0][0]);
+        __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(scratch);                        // [8][DA_HS_LD]
+        __nv_bfloat16* xg = reinterpret_cast<__nv_bfloat16*>(scratch + 8 * DA_HS_LD * 2);      // [8][DA_XG_LD]
+        static_assert(8 * DA_HS_LD * 2 + 8 * DA_XG_LD * 2 <= DA_WARPS * D * 4, "FFN scratch must fit the psum buffer");
+        float* red = reinterpret_cast<float*>(da_base + 6 * DA_BOX);                          // [4 K quarters][8][DA_RED_LD]: the out_w region, once W1 is consumed
+        static_assert(4 * 8 * DA_RED_LD * 4 <= 2 * DA_BOX, "K-split scratch must fit the out_w region");
+        const uint32_t rank = ffn_rank;
+        const int g = lane >> 2, tq = lane & 3;
+        // ldmatrix.x4 row address of this lane inside a 16-row weight tile: matrices (rows 0-7 | 8-15) x (chunk c | c + 1)
+        const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8, lm_chunk = lane >> 4;
+        cluster_wait();                       // every CTA of the cluster is running: remote stores may begin
+        if (warp < DA_R) {
+            const int64_t nn = row0 + warp;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nn < p.M) {
+                const float4 a = *reinterpret_cast<const float4*>(&x1s[warp][lane * 4]);
+                const float4 y = *reinterpret_cast<const float4*>(&qkv[warp][lane * 4]);
+                o = ln_row(make_float4(a.x + y.x, a.y + y.y, a.z + y.z, a.w + y.w), Ps + DA_P_N2W, Ps + DA_P_N2B, p.eps, lane);
+            }
+            *reinterpret_cast<float4*>(&x1s[warp][lane * 4]) = o;       // fp32 residual of norm3
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            const __nv_bfloat16* dst = xg + (rank * DA_R + warp) * DA_XG_LD + lane * 4;
+#pragma unroll
+            for (uint32_t d = 0; d < DA_CL; ++d)
+                cluster_st_u32x2(cluster_map(dst, d), *reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
+        // bias of this warp's 16 hidden columns (rows g and g + 8 of its tile)
+        const float b1_lo = p.b1[f_base + warp * 16 + g], b1_hi = p.b1[f_base + warp * 16 + g + 8];
+        cluster_arrive();
+        cluster_wait();                       // the 8 input rows are in every CTA
+        DA_STAMP(10);
+        {   // ---- h^T[f_base + 16 warp .., :] = relu(W1 . x^T + b1): one 16-row tile of W1 per warp, K = 128
+            mbar_wait(&fb[warp < 24 ? 0 : 1], 0);
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t tile = smem_u32(da_base) + (uint32_t)((warp >> 3) * 2 * DA_BOX + ((warp & 7) * 16 + lm_row) * 128);
+            const __nv_bfloat16* xrow = xg + g * DA_XG_LD + 2 * tq;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t a[4];
+                ldmatrix_x4(a, tile + (uint32_t)((ks >> 2) * DA_BOX + ((((ks & 3) * 2 + lm_chunk) ^ (lane & 7)) << 4)));
+                mma_bf16_16816(c, a, *reinterpret_cast<const uint32_t*>(xrow + ks * 16), *reinterpret_cast<const uint32_t*>(xrow + ks * 16 + 8));
+            }
+            // c[0], c[1]: hidden column 16 warp + g of rows 2 tq, 2 tq + 1; c[2], c[3]: column + 8
+            __nv_bfloat16* hcol = hs + warp * 16 + g;
+            hcol[(2 * tq) * DA_HS_LD] = __float2bfloat16_rn(fmaxf(c[0] + b1_lo, 0.f));
+            hcol[(2 * tq + 1) * DA_HS_LD] = __float2bfloat16_rn(fmaxf(c[1] + b1_lo, 0.f));
+            hcol[(2 * tq) * DA_HS_LD + 8] = __float2bfloat16_rn(fmaxf(c[2] + b1_hi, 0.f));
+            hcol[(2 * tq + 1) * DA_HS_LD + 8] = __float2bfloat16_rn(fmaxf(c[3] + b1_hi, 0.f));
+        }
+        DA_STAMP(11);
+        __syncthreads();                      // hs complete; W1 consumed
+        if (warp == 0 && lane == 0) {         // the second half of the W2 slice into the in_w region
+            mbar_arrive_expect_tx(&fb[4], 2 * DA_BOX);
+            ffn_load_w2(4, da_base + 0 * DA_BOX, &fb[4]); ffn_load_w2(5, da_base + 1 * DA_BOX, &fb[4]);
+            mbar_arrive_expect_tx(&fb[5], 2 * DA_BOX);
+            ffn_load_w2(6, da_base + 2 * DA_BOX, &fb[5]); ffn_load_w2(7, da_base + 3 * DA_BOX, &fb[5]);
+        }
+        {   // ---- y^T partial = W2[:, K quarter] . h^T: warp = (16-row output tile mt, K quarter kq of 128 hidden columns)
+            const int mt = warp & 7, kq = warp >> 3;
+            mbar_wait(&fb[2 + kq], 0);
+            const uint32_t boxes = smem_u32(da_base) + (uint32_t)((kq < 2 ? 8 + 2 * kq : 2 * (kq - 2)) * DA_BOX + (mt * 16 + lm_row) * 128);
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const __nv_bfloat16* hrow = hs + g * DA_HS_LD + kq * 128 + 2 * tq;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t a[4];
+                ldmatrix_x4(a, boxes + (uint32_t)((ks >> 2) * DA_BOX + ((((ks & 3) * 2 + lm_chunk) ^ (lane & 7)) << 4)));
+                mma_bf16_16816(c, a, *reinterpret_cast<const uint32_t*>(hrow + ks * 16), *reinterpret_cast<const uint32_t*>(hrow + ks * 16 + 8));
+            }
+            // c[0], c[1]: output column 16 mt + g of rows 2 tq, 2 tq + 1; c[2], c[3]: column + 8
+            float* rq = red + (size_t)kq * 8 * DA_RED_LD + mt * 16 + g;
+            rq[(2 * tq) * DA_RED_LD] = c[0]; rq[(2 * tq + 1) * DA_RED_LD] = c[1];
+            rq[(2 * tq) * DA_RED_LD + 8] = c[2]; rq[(2 * tq + 1) * DA_RED_LD + 8] = c[3];
+        }
+        DA_STAMP(12);
+        __syncthreads();
+        {   // K quarters added in a fixed order; row i / 128 of the cluster belongs to CTA (row / DA_R), local row row % DA_R
+            const int row = threadIdx.x >> 7, col = threadIdx.x & (D - 1);
+            const float* rq = red + row * DA_RED_LD + col;
+            const float v = ((rq[0] + rq[8 * DA_RED_LD]) + rq[2 * 8 * DA_RED_LD]) + rq[3 * 8 * DA_RED_LD];
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_map(&yp[rank][row % DA_R][col], (uint32_t)(row / DA_R))), "f"(v) : "memory");
+        }
+        cluster_arrive();
+        cluster_wait();                       // the four partial outputs of this CTA's rows have landed
+        DA_STAMP(13);
+        if (warp < DA_R) {
+            const int64_t nn = row0 + warp;
+            if (nn < p.M) {
+                float4 a = *reinterpret_cast<const float4*>(p.b2 + lane * 4);
+#pragma unroll
+                for (int sr = 0; sr < DA_CL; ++sr) {          // fixed order: deterministic
+                    const float4 q = *reinterpret_cast<const float4*>(&yp[sr][warp][lane * 4]);
+                    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+                }
+                const float4 res = *reinterpret_cast<const float4*>(&x1s[warp][lane * 4]);
+                const float4 o = ln_row(make_float4(a.x + res.x, a.y + res.y, a.z + res.z, a.w + res.w), p.n3_w, p.n3_b, p.eps, lane);
+                *reinterpret_cast<float4*>(p.x_out + nn * D + lane * 4) = o;
+            }
+        }
+        DA_STAMP(14);
+        return;
+    }
     if (warp < DA_R) {
         const int64_t nn = row0 + warp;
         if (nn < p.M) {

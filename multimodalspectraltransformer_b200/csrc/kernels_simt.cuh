@@ -1376,6 +1376,7 @@ struct SampleParams {
     // optional prologue (fused decoder path): x <- LN(x + pbias + sum_s part[s]) -- the last layer's FFN2 + norm3
     const float* part; int splits; int64_t part_stride;
     const float* pbias; const float* pgamma; const float* pbeta; float eps;
+    int rows_per_warp;       // dense input: 1 or SAMPLE_NR rows per warp (0 = 1)
 };
 
 // CTA = 8 warps.  Rows are taken in groups of `rpc` per CTA, grid-stride: a CTA stages fc_out once and keeps sampling
@@ -1484,7 +1485,8 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
     if (threadIdx.x == 0) s_nonpad = 0;
     pdl_wait();
     const int t = p.ctl.step ? *p.ctl.step : 0;
-    const int rpc = p.part ? 2 : SAMPLE_ROWS;       // rows per CTA and pass
+    const bool nr4 = p.rows_per_warp == SAMPLE_NR;
+    const int rpc = p.part ? 2 : (nr4 ? SAMPLE_ROWS : 8);       // rows per CTA and pass
     int my_nonpad = 0;
     for (int64_t base = (int64_t)blockIdx.x * rpc; base < p.N; base += (int64_t)gridDim.x * rpc) {
         if (p.part) {   // ---- input rows -> xs: four warps per row over the FFN2 partials
@@ -1521,7 +1523,7 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
             }
             __syncthreads();
             if (warp < rpc && base + warp < p.N) sample_rows<1>(p, Ws, xs, warp, base + warp, t, lane, my_nonpad);
-        } else {        // ---- dense input: each warp stages and samples its own four rows
+        } else if (nr4) {   // ---- dense input: each warp stages and samples its own four rows
 #pragma unroll
             for (int r = 0; r < SAMPLE_NR; ++r) {
                 const int64_t n = base + warp * SAMPLE_NR + r;
@@ -1529,6 +1531,11 @@ __global__ void __launch_bounds__(256) sample_tokens(const __grid_constant__ Sam
             }
             __syncthreads();      // (also orders the Ws staging of the first pass)
             if (base + warp * SAMPLE_NR < p.N) sample_rows<SAMPLE_NR>(p, Ws, xs, warp * SAMPLE_NR, base + warp * SAMPLE_NR, t, lane, my_nonpad);
+        } else {            // ---- dense input, small waves: one row per warp (more CTAs, shorter chain)
+            const int64_t n = base + warp;
+            if (n < p.N) *reinterpret_cast<float4*>(&xs[warp][lane * 4]) = *reinterpret_cast<const float4*>(p.x + n * D + lane * 4);
+            __syncthreads();
+            if (n < p.N) sample_rows<1>(p, Ws, xs, warp, n, t, lane, my_nonpad);
         }
         __syncthreads();          // xs / psum are rewritten by the next group
     }

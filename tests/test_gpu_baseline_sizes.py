@@ -316,3 +316,40 @@ def test_token_major_pages_equal_head_major_pages(monkeypatch):
             assert same.float().mean().item() >= 0.7, (B, K, same.float().mean().item())
             assert float((x_pr[:, same] - y_pr[:, same]).abs().max()) < 2e-2
 
+
+
+def test_cluster_ffn_decode_equals_separate_ffn_kernel(monkeypatch):
+    """Small bf16 waves run the decoder FFN + norm3 INSIDE `decode_attn`, launched as clusters of four CTAs (the 8 rows of a
+    cluster are gathered through distributed shared memory, every CTA owns 512 hidden columns on mma.sync, partial outputs
+    scattered to the row owners); `MMT_NO_CLUSTER_FFN=1` keeps the separate tcgen05 FFN kernel + split-F partials.  Same
+    operands (bf16 x and h, hi weight term), another accumulation order: teacher-forced logits agree to 2e-3 of the row
+    scale (the two differ from the fp32 reference by ~5e-3), free-running ids agree except at near-ties.  Row counts: one
+    partly filled cluster (5 rows), several clusters with a dead tail CTA (37 x 1), candidates sharing a memory (19 x 7 =
+    133 rows), and 256 rows in two concurrent lanes (the bench geometry)."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    M = s["M"]
+    m_cl = model_with(monkeypatch)
+    m_sep = model_with(monkeypatch, MMT_NO_CLUSTER_FFN="1")
+    for B, K, T in ((5, 1, 12), (37, 1, 20), (19, 7, 12), (256, 1, 24)):
+        data = synthetic.make_spectra(B, seed=1500 + B)
+        cfg = cfg_for(precision="bf16", max_len=T)
+        memory, mask, *_ = M.run_model(s["model"], data, cfg)
+        g = torch.Generator().manual_seed(B)
+        trg = torch.randint(4, 43, (T, B * K), generator=g)
+        trg[0] = 3
+        la = M.teacher_forced_logits(m_cl, memory, mask, trg.cuda(), cfg, n_candidates=K)
+        lb = M.teacher_forced_logits(m_sep, memory, mask, trg.cuda(), cfg, n_candidates=K)
+        scale = lb.abs().amax(dim=-1, keepdim=True)
+        assert float(((la - lb).abs() / scale).max()) < 2e-3, (B, K, float(((la - lb).abs() / scale).max()))
+        out = []
+        for m in (m_cl, m_sep):
+            torch.manual_seed(23)
+            mt, mp_ = M.multinomial_sequence_multi(m, memory, mask, STOI, cfg, n_candidates=K)
+            gt, gp = M.greedy_sequence(m, STOI, None, memory, mask, cfg, n_candidates=K)
+            out.append((mt, mp_, gt, gp))
+        a, b = out
+        for x_tok, x_pr, y_tok, y_pr in ((a[0], a[1], b[0], b[1]), (a[2], a[3], b[2], b[3])):
+            same = (x_tok == y_tok).all(dim=0)
+            assert same.float().mean().item() >= 0.7, (B, K, same.float().mean().item())
+            assert float((x_pr[:, same] - y_pr[:, same]).abs().max()) < 2e-2
