@@ -1673,7 +1673,7 @@ int32_t mmt_create(const mmt_model_desc* desc, const float* h_weights, int64_t n
     if (getenv("MMT_NO_FFN_WIDE")) e->use_ffn_wide = false;
     if (getenv("MMT_NO_KV_EPILOGUE")) e->use_kv_epilogue = false;
     if (getenv("MMT_KV_HEAD_MAJOR")) e->kv_tok_major = false;
-    if (getenv("MMT_NO_CLUSTER_FFN")) e->use_cluster_ffn = false;
+    if (getenv("MMT_CLUSTER_FFN")) e->use_cluster_ffn = true;
     if (getenv("MMT_NO_FFN_PROLOGUE")) e->use_ffn_prologue = false;
     if (getenv("MMT_ENC_FFN_SINGLE")) e->enc_ffn_single = true;
     if (const char* v = getenv("MMT_DECODE_LANES_LARGE")) e->decode_lanes_large = std::max(1, atoi(v));

@@ -121,7 +121,7 @@ struct mmt_engine {
     int max_wave_seqs = 0;             // sequences decoded together; larger runs go wave by wave (bounds the self-attention KV pool); 0 = default by precision (MMT_MAX_WAVE_SEQS overrides)
     bool enc_ffn_single = false;       // experiment (MMT_ENC_FFN_SINGLE=1): encoder FFN with the hi weight term only
     bool use_ffn_prologue = true;      // un-fused decode step, >= 2048 rows: cross-attention out-projection + norm2 inside the FFN kernel (MMT_NO_FFN_PROLOGUE=1 disables)
-    bool use_cluster_ffn = true;       // small bf16 waves: the FFN runs inside decode_attn, launched as clusters of 4 CTAs (MMT_NO_CLUSTER_FFN=1: separate fused-FFN kernel)
+    bool use_cluster_ffn = false;      // MMT_CLUSTER_FFN=1: small bf16 waves run the FFN inside decode_attn, launched as clusters of 4 CTAs (parity-tested; measured equal to the separate fused-FFN kernel in the bench, profiles/r02_cluster_probe.md)
     bool kv_tok_major = true;          // un-fused bf16 step with the KV epilogue: token-major cache pages + decode_self_attention_tm (MMT_KV_HEAD_MAJOR=1: head-major pages + decode_self_attention_g8)
     bool use_kv_epilogue = true;       // un-fused bf16 step: the QKV projection's epilogue writes K | V of the new position into the cache pages (MMT_NO_KV_EPILOGUE=1: the attention kernel appends)
     bool use_ffn_wide = true;          // hi-term FFN with the LayerNorm epilogue: 128-column chunks (MMT_NO_FFN_WIDE=1: 64)

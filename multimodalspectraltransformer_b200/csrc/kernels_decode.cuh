@@ -746,4 +746,5 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attn(const __grid_consta
 #undef DA_STAMP2
 }
 
+
 }  // namespace mmt

@@ -319,9 +319,9 @@ def test_token_major_pages_equal_head_major_pages(monkeypatch):
 
 
 def test_cluster_ffn_decode_equals_separate_ffn_kernel(monkeypatch):
-    """Small bf16 waves run the decoder FFN + norm3 INSIDE `decode_attn`, launched as clusters of four CTAs (the 8 rows of a
-    cluster are gathered through distributed shared memory, every CTA owns 512 hidden columns on mma.sync, partial outputs
-    scattered to the row owners); `MMT_NO_CLUSTER_FFN=1` keeps the separate tcgen05 FFN kernel + split-F partials.  Same
+    """Opt-in (`MMT_CLUSTER_FFN=1`): small bf16 waves run the decoder FFN + norm3 INSIDE `decode_attn`, launched as clusters of
+    four CTAs (the 8 rows of a cluster are gathered through distributed shared memory, every CTA owns 512 hidden columns on
+    mma.sync, partial outputs scattered to the row owners) instead of the separate tcgen05 FFN kernel + split-F partials.  Same
     operands (bf16 x and h, hi weight term), another accumulation order: teacher-forced logits agree to 2e-3 of the row
     scale (the two differ from the fp32 reference by ~5e-3), free-running ids agree except at near-ties.  Row counts: one
     partly filled cluster (5 rows), several clusters with a dead tail CTA (37 x 1), candidates sharing a memory (19 x 7 =
@@ -329,8 +329,8 @@ def test_cluster_ffn_decode_equals_separate_ffn_kernel(monkeypatch):
     s = setup()
     from multimodalspectraltransformer_b200 import synthetic
     M = s["M"]
-    m_cl = model_with(monkeypatch)
-    m_sep = model_with(monkeypatch, MMT_NO_CLUSTER_FFN="1")
+    m_cl = model_with(monkeypatch, MMT_CLUSTER_FFN="1")
+    m_sep = model_with(monkeypatch)
     for B, K, T in ((5, 1, 12), (37, 1, 20), (19, 7, 12), (256, 1, 24)):
         data = synthetic.make_spectra(B, seed=1500 + B)
         cfg = cfg_for(precision="bf16", max_len=T)
