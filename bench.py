@@ -408,6 +408,10 @@ def main():
                 kj = tj["kernels"][dom]
                 roof["traffic"] = kj["dram_bytes_read"] + kj["dram_bytes_write"]
                 roof["traffic_source"] = f"profiles/r02_ncu_traffic.json ({kj.get('note', 'ncu --set full')}; same source hash as this build)"
+                if kj.get("algorithmic_bytes_of_captured_launch"):     # the capture is ONE position; `achieved` averages all of them
+                    roof["traffic_capture"] = kj.get("capture")
+                    roof["traffic_algorithmic_bytes"] = kj["algorithmic_bytes_of_captured_launch"]
+                    roof["traffic_over_algorithmic"] = roof["traffic"] / kj["algorithmic_bytes_of_captured_launch"]
             else:
                 roof["traffic_source"] = "none: profiles/r02_ncu_traffic.json was captured from another build (source hash differs)"
         except (OSError, ValueError, KeyError):
