@@ -353,3 +353,26 @@ def test_cluster_ffn_decode_equals_separate_ffn_kernel(monkeypatch):
             same = (x_tok == y_tok).all(dim=0)
             assert same.float().mean().item() >= 0.7, (B, K, same.float().mean().item())
             assert float((x_pr[:, same] - y_pr[:, same]).abs().max()) < 2e-2
+
+
+def test_large_wave_split_is_bit_invisible_in_bf16(monkeypatch):
+    """96 spectra x 128 candidates (12,288 sequences) as one wave against three waves of 4,096: the un-fused bf16 step tiles
+    every GEMM by 128 rows whatever the wave size, the token-major self-attention and the candidate cross attention are per
+    sequence / per spectrum, and the sampler's four-rows-per-warp form (waves >= 8,192 rows) computes every logit in the same
+    order as the one-row form (smaller waves) -- tokens and probabilities are bit-identical."""
+    s = setup()
+    from multimodalspectraltransformer_b200 import synthetic
+    M = s["M"]
+    m_one = model_with(monkeypatch)
+    m_waves = model_with(monkeypatch, MMT_MAX_WAVE_SEQS="4096")
+    data = synthetic.make_spectra(96, seed=4711)
+    cfg = cfg_for(precision="bf16", max_len=20)
+    memory, mask, *_ = M.run_model(s["model"], data, cfg)
+    out = []
+    for m in (m_one, m_waves):
+        torch.manual_seed(29)
+        mt, mp_ = M.multinomial_sequence_multi(m, memory, mask, STOI, cfg, n_candidates=128)
+        gt, gp = M.greedy_sequence(m, STOI, None, memory, mask, cfg, n_candidates=128)
+        out.append((mt, mp_, gt, gp))
+    for x, y in zip(*out):
+        assert torch.equal(x, y)
