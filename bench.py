@@ -457,9 +457,10 @@ def main():
                 del Pd, dup, mem, msk
             except Exception as exc:      # never let a comparator cost the bench line
                 line["gpu_eager_baseline"] = {"error": str(exc)[:200]}
-            v, toks, sec, threads = cpu_reference_tokens_per_s(steps=1, warmup=0)
+            CPU_STEPS = 5       # ~10-15 s of host work: 5 spectra after one untimed warm-up spectrum
+            v, toks, sec, threads = cpu_reference_tokens_per_s(steps=CPU_STEPS, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": REF_SAMPLE_TEXT + f" ({toks} tokens, {sec:.1f} s)"}
+                                    "sample": REF_SAMPLE_TEXT + f" ({CPU_STEPS} such steps timed: {toks} tokens and {sec:.1f} s each)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
