@@ -9,7 +9,7 @@ reference's production call, mmt_result_test_functions_15_4.py:504-570): config_
 sampling of 128 candidates for each of 1024 synthetic 1H+13C+HSQC+COSY+IR(+MF+MW) spectra, 128 tokens each
 = 131,072 sequences, 16,777,216 generated tokens per step.  STRONG scaling: the 1024 spectra are sharded over the N
 ranks by ``scheduler.generate_sharded`` (contiguous blocks, shard-invariant Philox draws), every rank encodes its
-spectra once, decodes its candidates in waves of up to 75,776 sequences and the ids are all-gathered over NCCL as bytes on a
+spectra once, decodes its candidates in waves of up to 151,552 sequences (one wave per rank here) and the ids are all-gathered over NCCL as bytes on a
 side stream (overlapping the next step).  One "step" = encode + every wave + gather for all 1024 spectra.
 
 Extra keys of the JSON line: ``config2`` (BASELINE.json configs[1]: greedy, 256 spectra per GPU x 128 tokens, weak
@@ -149,7 +149,7 @@ REF_SAMPLE_TEXT = (f"1 of the {N_SPECTRA} spectra x {REF_SAMPLE_CAND} of its {N_
 
 def workload_config(n_gpus, precision, ref_sample=False):
     c = {"workload": f"MMT config_V8 random-init, multinomial sampling, {N_SPECTRA} synthetic spectra x {N_CAND} candidates x {MAX_LEN} tokens "
-                     "(BASELINE.json configs[2]; encode + KV-cached decode in waves of up to 75,776 sequences + NCCL all-gather of the ids per step)",
+                     "(BASELINE.json configs[2]; encode + KV-cached decode in waves of up to 151,552 sequences (one wave per rank) + NCCL all-gather of the ids per step)",
          "spectra_total": N_SPECTRA, "candidates": N_CAND, "max_len": MAX_LEN, "sequences_total": N_SPECTRA * N_CAND,
          "spectra_per_gpu": (N_SPECTRA + n_gpus - 1) // n_gpus, "peaks": "realistic", "precision": precision,
          "parallelism": f"dp{n_gpus}",
@@ -365,7 +365,7 @@ def main():
     pk = peaks()
     roof = None
     if rank == 0:
-        wave = min(592, hi - lo)             # one wave as the timed loop runs it on this rank (148 SMs x 4 rounds of 128-row tiles at most)
+        wave = min(1184, hi - lo)            # one wave as the timed loop runs it on this rank (148 SMs x 8 rounds of 128-row tiles at most)
         data_w = {k: v[:wave] for k, v in resident.items()}
         eng.profile(True)
         memory, mask, *_ = M.run_model(model, data_w, cfg)

@@ -107,6 +107,7 @@ struct Arena {
 struct mmt_engine {
     mmt_model_desc desc;
     int device = 0, sm_count = 0, max_threads_per_sm = 0;
+    size_t total_mem = 0;              // device memory (default decode wave size)
     mmt::Registry reg;
     float* w32 = nullptr;
     __nv_bfloat16* w16 = nullptr;      // bf16(w32)
